@@ -1,0 +1,156 @@
+/* pvw_b200.h -- C ABI of the B200-native PVW hot path (libpvw_b200.so).
+ *
+ * This is the drop-in boundary a Rust shim of gnosisguild/pvw-rs binds with `extern "C"`.
+ * The reference has no FFI of its own: the boundary is its public Rust API (src/lib.rs:31-55).  Every entry point
+ * below names the reference interface it replaces (paths relative to the reference repository).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; the library never takes ownership of caller memory.
+ *  - host polynomial layout = the reference's: one polynomial is u64[L][ell] row-major, canonical residues in
+ *    [0, q_j), NTT representation (fhe-math Poly.coefficients, src/params/parameters.rs:455-458).
+ *    Matrices / vectors of polynomials are plain C arrays of such blocks.
+ *  - every function returns 0 on success or a negative pvw_status that maps 1:1 onto a PvwError variant
+ *    (src/errors.rs:11-70); pvw_last_error() returns the message.  No exception or abort crosses the boundary.
+ *  - a context is bound to ONE CUDA device and ONE shard of parties [row0, row0+nrows) (rows of the global public
+ *    key B).  One process per GPU; collectives (NCCL) are issued by the host layer on the device pointers that
+ *    pvw_ct_c1_device_ptr() exposes.  A context is not thread-safe; guard it with a mutex (the Rust shim does).
+ *  - `PVW_IO_DEVICE` in `flags` means the data pointers of that call are CUDA device pointers on the context's
+ *    device (inputs already resident in HBM); otherwise they are host pointers and the call performs the copies.
+ *  - there is no CPU fallback: without a CUDA device pvw_ctx_create fails with PVW_ERR_INTERNAL.
+ */
+#ifndef PVW_B200_H
+#define PVW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pvw_ctx pvw_ctx;
+
+typedef enum {
+  PVW_OK = 0,
+  PVW_ERR_INVALID_PARAMETERS = -1, /* PvwError::InvalidParameters   errors.rs:14 */
+  PVW_ERR_DIMENSION_MISMATCH = -2, /* PvwError::DimensionMismatch   errors.rs:56 */
+  PVW_ERR_INDEX_OUT_OF_BOUNDS = -3,/* PvwError::IndexOutOfBounds    errors.rs:59 */
+  PVW_ERR_ENCRYPTION = -4,         /* PvwError::EncryptionError     errors.rs:20 */
+  PVW_ERR_DECRYPTION = -5,         /* PvwError::DecryptionError     errors.rs:23 */
+  PVW_ERR_KEYGEN = -6,             /* PvwError::KeyGenerationError  errors.rs:26 */
+  PVW_ERR_INTERNAL = -7            /* PvwError::InternalError       errors.rs:68 (CUDA failures, missing device) */
+} pvw_status;
+
+enum { PVW_IO_HOST = 0u, PVW_IO_DEVICE = 1u };
+
+/* Replaces PvwParametersBuilder::build (src/params/parameters.rs:117-195) + fhe-math Context::new.
+ * Same validation: n > 0, k > 0, ell a power of two >= 8, moduli prime, < 2^62, = 1 mod 2*ell, distinct,
+ * error bounds > 0 (bounds >= 2^63 are not representable here; the reference type is BigInt but every
+ * call site uses <= u32, parameters.rs:110-114). */
+typedef struct {
+  uint32_t n;              /* number of parties                                   */
+  uint32_t k;              /* LWE dimension                                       */
+  uint32_t ell;            /* redundancy parameter = ring degree                  */
+  uint32_t L;              /* number of RNS moduli                                */
+  const uint64_t *moduli;  /* [L]                                                 */
+  const uint64_t *psi;     /* [L] primitive 2*ell-th roots, or NULL = derive like fhe-math's NttOperator
+                              (ChaCha8 seed 0 search; recalled)   */
+  float secret_variance;   /* default 0.5  (parameters.rs:166); only recorded     */
+  uint64_t error_bound_1;  /* default 100  (parameters.rs:167)                    */
+  uint64_t error_bound_2;  /* default 200  (parameters.rs:168)                    */
+  uint32_t row0;           /* first party (row of B) held by this context         */
+  uint32_t nrows;          /* number of rows held; 0 = all n                      */
+  int32_t device;          /* CUDA device ordinal                                 */
+} pvw_params_desc;
+
+int pvw_ctx_create(pvw_ctx **out, const pvw_params_desc *desc);
+void pvw_ctx_destroy(pvw_ctx *ctx);
+/* message of the last failing call on this context (or of the last failing pvw_ctx_create when ctx == NULL) */
+const char *pvw_last_error(const pvw_ctx *ctx);
+
+/* PvwParameters accessors: delta() / delta_power_l_minus_1() / q_total() (parameters.rs:369-386) as little-endian
+ * u64 words (`cap` = capacity of out; *nwords receives the count), the psi actually used, and
+ * verify_correctness_condition() (parameters.rs:510-551; returns 1/0 in *ok). which: 0 = Q, 1 = delta, 2 = delta^(ell-1) */
+int pvw_params_bigint(const pvw_ctx *ctx, int which, uint64_t *out, uint32_t cap, uint32_t *nwords);
+int pvw_params_psi(const pvw_ctx *ctx, uint64_t *out /* [L] */);
+int pvw_params_correctness_condition(const pvw_ctx *ctx, int *ok);
+
+/* PvwCrs storage (src/params/crs.rs:12-17): A is k x k polynomials in NTT form, A[i][j] at ((i*k + j)*L*ell). */
+int pvw_crs_upload(pvw_ctx *ctx, const uint64_t *A /* [k][k][L][ell] */, uint32_t flags);
+int pvw_crs_download(pvw_ctx *ctx, uint64_t *A /* [k][k][L][ell] */);
+
+/* GlobalPublicKey storage (src/keys/public_key.rs:43-54): add_public_key (:214-250) for rows [row, row+count) of B.
+ * `row` is a GLOBAL party index and must lie inside this context's shard.  num_keys = max(index)+1 as in :245-247. */
+int pvw_pk_upload_rows(pvw_ctx *ctx, uint32_t row, uint32_t count, const uint64_t *B /* [count][k][L][ell] */, uint32_t flags);
+int pvw_pk_download_rows(pvw_ctx *ctx, uint32_t row, uint32_t count, uint64_t *B /* [count][k][L][ell] */);
+/* GlobalPublicKey::is_full (public_key.rs:349-351) restricted to this shard: every local row index < num_keys */
+int pvw_pk_num_keys(const pvw_ctx *ctx, uint32_t *num_keys);
+
+/* Batched key generation: PublicKey::generate (public_key.rs:111-147) + PvwCrs::multiply_by_secret_key
+ * (crs.rs:138-171) for `count` parties starting at global index `row`, with the error e supplied explicitly:
+ *   b_p[c] = sum_j NTT(s_p[j]) (.) A[j][c] + NTT(e_p[c]).   Rows land in the device-resident B. */
+int pvw_keygen_batch(pvw_ctx *ctx, uint32_t row, uint32_t count, const int64_t *sk /* [count][k][ell] */,
+                     const int64_t *e /* [count][k][ell] */, uint32_t flags);
+
+/* PvwCrs::multiply_by_randomness (crs.rs:177-205): out[i] = sum_j A[i][j] (.) r[j] for D independent vectors.
+ * r_hat and out are NTT-form polynomials in the host layout.  len != k is the caller's DimensionMismatch. */
+int pvw_crs_multiply_by_randomness(pvw_ctx *ctx, uint32_t D, const uint64_t *r_hat /* [D][k][L][ell] */,
+                                   uint64_t *out /* [D][k][L][ell] */);
+
+/* Device-resident ciphertext store: `capacity` dealers; slot d holds PvwCiphertext{c1 (k polys), c2 (nrows polys)}
+ * (src/crypto/encryption.rs:15-24).  Re-reserving discards the contents. */
+int pvw_ct_reserve(pvw_ctx *ctx, uint32_t capacity);
+
+/* encrypt (encryption.rs:105-214) / encrypt_party_shares (:221-245) / encrypt_all_party_shares (:253-286) for D
+ * dealers with the randomness the reference draws from thread_rng() passed in explicitly:
+ *   c1_d[i] = sum_j A[i][j] (.) NTT(r_d[j]) + NTT(e1_d[i])
+ *   c2_d[p] = sum_j B[p][j] (.) NTT(r_d[j]) + NTT((m_d[p] as i64) * g) + NTT(e2_d[p])      for local rows p
+ * Results go to store slots [slot0, slot0+D).  c1 is computed only for dealers [c1_lo, c1_hi) of the batch (use
+ * 0, D on a single GPU; with row sharding each rank computes a slice and the host layer all-gathers the rest into
+ * the store, see pvw_ct_c1_device_ptr).  e1 may be NULL when c1_lo == c1_hi.
+ * Fails like the reference when the key is not full (:117) or the correctness condition is false (:124). */
+int pvw_encrypt_batch(pvw_ctx *ctx, uint32_t slot0, uint32_t D, uint32_t c1_lo, uint32_t c1_hi,
+                      const uint64_t *m /* [D][nrows] */, const int64_t *r /* [D][k][ell] */,
+                      const int64_t *e1 /* [D][k][ell] */, const int64_t *e2 /* [D][nrows][ell] */, uint32_t flags);
+
+/* PvwCiphertext download / upload in the reference layout (c1 [k][L][ell], c2 [nrows][L][ell]); NULL = skip. */
+int pvw_ct_download(pvw_ctx *ctx, uint32_t slot, uint64_t *c1, uint64_t *c2);
+int pvw_ct_upload(pvw_ctx *ctx, uint32_t slot, const uint64_t *c1, const uint64_t *c2);
+/* device address of c1 of store slot `slot` (layout [slot][L][k][ell], contiguous over slots: *slot_stride u64
+ * elements apart) so that the host layer can run collectives (NCCL all-gather over dealers) in place. */
+int pvw_ct_c1_device_ptr(pvw_ctx *ctx, uint32_t slot, void **ptr, uint64_t *slot_stride);
+
+/* decrypt_party_value (src/crypto/decryption.rs:249-278) / decrypt_party_shares (:281-325) for P local parties
+ * x D stored ciphertexts:  out[p*D + d] = decode( sum_j NTT(s_p[j]) (.) c1_d[j] - c2_d[party_idx[p]] ).
+ * dealer_slots == NULL means slots 0..D-1.  party_idx are GLOBAL indices inside the shard.
+ * This is the subset form of examples/pvw_valid_dec.rs:198-210; the "exactly n ciphertexts" rule of
+ * decrypt_party_shares (:295) is enforced by the host layer. */
+int pvw_decrypt_batch(pvw_ctx *ctx, uint32_t D, const uint32_t *dealer_slots /* [D] host, or NULL */, uint32_t P,
+                      const uint32_t *party_idx /* [P] host */, const int64_t *sk /* [P][k][ell] */,
+                      uint64_t *out /* [P][D] */, uint32_t flags);
+
+/* decode_scalar_pvw_rns (decryption.rs:10-58) on `count` noisy polynomials given in the host layout. */
+int pvw_decode_batch(pvw_ctx *ctx, uint32_t count, const uint64_t *zhat /* [count][L][ell] */, uint64_t *out /* [count] */);
+
+/* small signed coefficients -> NTT form: Poly::from_coefficients + change_representation(Ntt)
+ * (encryption.rs:147-154, secret_key.rs:98-112, parameters.rs:264-284). */
+int pvw_ntt_forward_small(pvw_ctx *ctx, uint32_t count, const int64_t *coeffs /* [count][ell] */,
+                          uint64_t *out /* [count][L][ell] */);
+
+/* PvwParameters::encode_scalar (parameters.rs:346-367) for `count` scalars: out = NTT((m as i64) * [1, D, .., D^(l-1)]) */
+int pvw_encode_scalars(pvw_ctx *ctx, uint32_t count, const uint64_t *m /* [count] */, uint64_t *out /* [count][L][ell] */);
+
+/* blocks until all work queued by this context has finished; returns a sticky CUDA error if one occurred */
+int pvw_ctx_synchronize(pvw_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of the context is ordered on, for CUDA-event timing by the caller */
+void *pvw_ctx_stream(pvw_ctx *ctx);
+/* tuning / introspection: "gemm_impl" (0 = synchronous tiles, 1 = TMA bulk-copy pipeline), "dealer_tile" ... */
+int pvw_ctx_set_option(pvw_ctx *ctx, const char *name, int64_t value);
+/* number of kernels launched by this context so far */
+uint64_t pvw_ctx_launch_count(const pvw_ctx *ctx);
+const char *pvw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVW_B200_H */

@@ -1,0 +1,640 @@
+// capi.cu -- the C ABI of libpvw_b200.so (include/pvw_b200.h): context, device residency of A / B / ciphertexts
+// and the host-side sequencing of the kernels in ntt.cu, mac.cu and decode.cu.
+//
+// Device layout ("limb-major", see kernels.cuh):
+//   A    u64[L][k][k][ell]          A[i][j] at ((limb*k + i)*k + j)*ell          PvwCrs.matrix          crs.rs:12-17
+//   At   u64[L][k][k][ell]          At[c][j] = A[j][c] (built lazily for keygen)  multiply_by_secret_key crs.rs:152-165
+//   B    u64[L][nrows][k][ell]      local rows of GlobalPublicKey.matrix           public_key.rs:43-54
+//   c1   u64[cap][L][k][ell]        ciphertext store, PvwCiphertext.c1             encryption.rs:15-24
+//   c2   u64[cap][L][nrows][ell]                      PvwCiphertext.c2 (local rows)
+// Host layout at the boundary is always the reference's: polynomial = u64[L][ell] row-major.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pvw_b200.h"
+#include "hostparams.hpp"
+#include "kernels.cuh"
+
+using namespace pvw;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+std::string fmt(const char* f, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+
+#define CUDA_CHECK(expr)                                                                                        \
+  do {                                                                                                          \
+    cudaError_t e__ = (expr);                                                                                   \
+    if (e__ != cudaSuccess)                                                                                     \
+      throw PvwException(PVW_ERR_INTERNAL, fmt("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #expr)); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t need) {
+    if (need <= bytes) return;
+    if (p) CUDA_CHECK(cudaFree(p));
+    p = nullptr; bytes = 0;
+    CUDA_CHECK(cudaMalloc(&p, need));
+    bytes = need;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct pvw_ctx {
+  HostParams hp;
+  int device = 0;
+  uint32_t row0 = 0, nrows = 0;
+  cudaStream_t stream = nullptr;
+  DevTables T{};
+  DevBuf tables;                 // one allocation holding every constant table
+  DevBuf A, At, B;
+  bool A_set = false, At_valid = false;
+  uint32_t num_keys = 0;         // max uploaded global index + 1 (public_key.rs:245-247)
+  uint32_t cap = 0;
+  DevBuf c1s, c2s;
+  // grow-only scratch
+  DevBuf stage, rhat, in_small, in_small2, in_m, shat, z, y, X, outd, idxd, idxp;
+  std::string err;
+  uint64_t launches = 0;
+  int gemm_impl = 1;
+  int64_t decrypt_chunk_shares = 1 << 19;
+  int64_t upload_chunk_bytes = 256ll << 20;
+
+  size_t poly() const { return (size_t)hp.L * hp.ell; }
+  void use() { CUDA_CHECK(cudaSetDevice(device)); }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// constant tables -> device
+// ------------------------------------------------------------------------------------------------------------
+uint32_t lift_template_width(uint32_t nw) {
+  static const uint32_t widths[] = {2, 4, 8, 17, 33, 64};
+  for (uint32_t w : widths) if (nw <= w) return w;
+  throw PvwException(PVW_ERR_INVALID_PARAMETERS, "modulus product wider than 4096 bits is not supported");
+}
+
+void upload_tables(pvw_ctx* c) {
+  const HostParams& hp = c->hp;
+  const uint32_t L = hp.L, ell = hp.ell, NW = hp.NW, NWT = lift_template_width(NW), LB = hp.LB;
+  std::vector<uint64_t> blob;
+  auto put = [&](const uint64_t* src, size_t n) { size_t off = blob.size(); blob.insert(blob.end(), src, src + n); return off; };
+  auto pad2 = [&]() { if (blob.size() & 1) blob.push_back(0); };
+  static_assert(sizeof(LimbConst) % 8 == 0, "LimbConst must be a whole number of words");
+  size_t o_lc = put(reinterpret_cast<const uint64_t*>(hp.lc.data()), (size_t)L * sizeof(LimbConst) / 8); pad2();
+  size_t o_tw = put(hp.tw.data(), (size_t)L * ell), o_tws = put(hp.tw_sh.data(), (size_t)L * ell);
+  size_t o_twi = put(hp.twi.data(), (size_t)L * ell), o_twis = put(hp.twi_sh.data(), (size_t)L * ell);
+  size_t o_g = put(hp.gadget_hat.data(), (size_t)L * ell);
+  std::vector<uint64_t> qhat_t((size_t)L * NWT, 0), qsh_t((size_t)LB * (NWT + 1), 0);
+  for (uint32_t j = 0; j < L; j++) memcpy(&qhat_t[(size_t)j * NWT], &hp.qhat[(size_t)j * NW], (size_t)NW * 8);
+  for (uint32_t b = 0; b < LB; b++) memcpy(&qsh_t[(size_t)b * (NWT + 1)], &hp.Qsh[(size_t)b * (NW + 1)], (size_t)(NW + 1) * 8);
+  size_t o_qhat = put(qhat_t.data(), qhat_t.size()), o_qsh = put(qsh_t.data(), qsh_t.size());
+  size_t o_Q = put(hp.Qw.data(), NW), o_hQ = put(hp.halfQ.data(), NW), o_M = put(hp.Mw.data(), NW), o_hM = put(hp.halfM.data(), NW),
+         o_D = put(hp.Dw.data(), NW);
+  std::vector<uint64_t> dM(hp.divM.v), d2D(hp.div2D.v);
+  size_t o_dM = put(dM.data(), dM.size()), o_d2D = put(d2D.data(), d2D.size());
+  c->tables.ensure(blob.size() * 8);
+  CUDA_CHECK(cudaMemcpy(c->tables.p, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
+  const u64* base = c->tables.as<u64>();
+  DevTables& T = c->T;
+  T.lc = reinterpret_cast<const LimbConst*>(base + o_lc);
+  T.tw = base + o_tw; T.tw_sh = base + o_tws; T.twi = base + o_twi; T.twi_sh = base + o_twis; T.gadget_hat = base + o_g;
+  T.qhat = base + o_qhat; T.Qsh = base + o_qsh;
+  T.Qw = base + o_Q; T.halfQ = base + o_hQ; T.Mw = base + o_M; T.halfM = base + o_hM; T.Dw = base + o_D;
+  T.divM_v = base + o_dM; T.div2D_v = base + o_d2D;
+  T.L = L; T.ell = ell; T.NW = NW; T.NWT = NWT; T.LB = LB;
+  T.divM_n = hp.divM.n; T.divM_shift = hp.divM.shift; T.divM_vinv = hp.divM.vinv;
+  T.div2D_n = hp.div2D.n; T.div2D_shift = hp.div2D.shift; T.div2D_vinv = hp.div2D.vinv;
+}
+
+void check_launch(pvw_ctx* c, size_t n = 1) {
+  c->launches += n;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// copy `bytes` from a caller pointer (host or device, per flags) into a device scratch buffer
+const void* stage_in(pvw_ctx* c, DevBuf& buf, const void* src, size_t bytes, uint32_t flags) {
+  if (flags & PVW_IO_DEVICE) return src;
+  buf.ensure(bytes);
+  CUDA_CHECK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return buf.p;
+}
+
+// host-layout polynomials [count][L][ell]  <->  limb-major [L][count][ell] slice inside a bigger array
+void to_limb_major(pvw_ctx* c, const u64* in_host_layout, uint64_t count, u64* out, size_t out_limb_stride) {
+  const uint32_t L = c->hp.L, ell = c->hp.ell;
+  launch_permute(in_host_layout, out, 1, count, L, ell, 0, (size_t)L * ell, ell, 0, ell, out_limb_stride, c->stream);
+  check_launch(c);
+}
+void from_limb_major(pvw_ctx* c, const u64* in, size_t in_limb_stride, uint64_t count, u64* out_host_layout) {
+  const uint32_t L = c->hp.L, ell = c->hp.ell;
+  // x = limb is the fastest thread axis here so that the host-layout side (the output) is written contiguously
+  launch_permute(in, out_host_layout, 1, L, count, ell, 0, in_limb_stride, ell, 0, ell, (size_t)L * ell, c->stream);
+  check_launch(c);
+}
+
+// upload `count` polynomials given in host layout (host or device memory) into limb-major dst (+ offset handled by caller)
+void upload_polys(pvw_ctx* c, const uint64_t* src, uint64_t count, u64* dst, size_t dst_limb_stride, uint32_t flags) {
+  const size_t poly = c->poly();
+  if (flags & PVW_IO_DEVICE) { to_limb_major(c, reinterpret_cast<const u64*>(src), count, dst, dst_limb_stride); return; }
+  uint64_t per = std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / (poly * 8));
+  for (uint64_t o = 0; o < count; o += per) {
+    uint64_t n = std::min(per, count - o);
+    c->stage.ensure(n * poly * 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->stage.p, src + o * poly, n * poly * 8, cudaMemcpyHostToDevice, c->stream));
+    to_limb_major(c, c->stage.as<u64>(), n, dst + o * c->hp.ell, dst_limb_stride);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
+  }
+}
+void download_polys(pvw_ctx* c, const u64* src, size_t src_limb_stride, uint64_t count, uint64_t* dst_host) {
+  const size_t poly = c->poly();
+  uint64_t per = std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / (poly * 8));
+  for (uint64_t o = 0; o < count; o += per) {
+    uint64_t n = std::min(per, count - o);
+    c->stage.ensure(n * poly * 8);
+    from_limb_major(c, src + o * c->hp.ell, src_limb_stride, n, c->stage.as<u64>());
+    CUDA_CHECK(cudaMemcpyAsync(dst_host + o * poly, c->stage.p, n * poly * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+}
+
+void require(bool cond, int code, const std::string& msg) { if (!cond) throw PvwException(code, msg); }
+
+void gemm(pvw_ctx* c, const GemmArgs& a) {
+  launch_mac_gemm(a, c->gemm_impl, c->stream);
+  check_launch(c, mac_gemm_launches(a));
+}
+
+void ensure_At(pvw_ctx* c) {
+  if (c->At_valid) return;
+  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+  const size_t kk = (size_t)k * k * ell;
+  c->At.ensure((size_t)L * kk * 8);
+  // At[limb][cidx][j] = A[limb][j][cidx]; x = j walks the output's contiguous axis
+  launch_permute(c->A.as<u64>(), c->At.as<u64>(), L, k, k, ell, kk, (size_t)k * ell, ell, kk, ell, (size_t)k * ell, c->stream);
+  check_launch(c);
+  c->At_valid = true;
+}
+
+template <class F>
+int guarded(pvw_ctx* c, F&& f) {
+  if (!c) return PVW_ERR_INVALID_PARAMETERS;
+  try {
+    c->use();
+    f();
+    return PVW_OK;
+  } catch (const PvwException& e) {
+    c->err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = e.what();
+    return PVW_ERR_INTERNAL;
+  } catch (...) {
+    c->err = "unknown failure";
+    return PVW_ERR_INTERNAL;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pvw_ctx_create(pvw_ctx** out, const pvw_params_desc* d) {
+  if (!out || !d) { g_create_error = "null argument"; return PVW_ERR_INVALID_PARAMETERS; }
+  *out = nullptr;
+  pvw_ctx* c = nullptr;
+  try {
+    c = new pvw_ctx();
+    c->hp.build(d->n, d->k, d->ell, d->L, d->moduli, d->psi, d->secret_variance, d->error_bound_1, d->error_bound_2);
+    c->row0 = d->row0;
+    c->nrows = d->nrows == 0 ? d->n - std::min(d->row0, d->n) : d->nrows;
+    require((uint64_t)c->row0 + c->nrows <= d->n && c->nrows > 0, PVW_ERR_INVALID_PARAMETERS,
+            fmt("party shard [%u, %u) is outside [0, n=%u)", c->row0, c->row0 + c->nrows, d->n));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw PvwException(PVW_ERR_INTERNAL, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    require(d->device >= 0 && d->device < ndev, PVW_ERR_INVALID_PARAMETERS, fmt("device %d out of range (%d devices)", d->device, ndev));
+    c->device = d->device;
+    c->use();
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    upload_tables(c);
+    *out = c;
+    return PVW_OK;
+  } catch (const PvwException& e) {
+    g_create_error = e.what();
+    int code = e.code;
+    delete c;
+    return code;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete c;
+    return PVW_ERR_INTERNAL;
+  }
+}
+
+void pvw_ctx_destroy(pvw_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp})
+    b->release();
+  delete c;
+}
+
+const char* pvw_last_error(const pvw_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int pvw_params_bigint(const pvw_ctx* c, int which, uint64_t* out, uint32_t cap, uint32_t* nwords) {
+  if (!c) return PVW_ERR_INVALID_PARAMETERS;
+  const BigU* b = which == 0 ? &c->hp.Q : which == 1 ? &c->hp.delta : which == 2 ? &c->hp.delta_pow : nullptr;
+  if (!b) return PVW_ERR_INVALID_PARAMETERS;
+  if (nwords) *nwords = (uint32_t)b->w.size();
+  if (out) {
+    if (cap < b->w.size()) return PVW_ERR_DIMENSION_MISMATCH;
+    b->to_words(out, cap);
+  }
+  return PVW_OK;
+}
+int pvw_params_psi(const pvw_ctx* c, uint64_t* out) {
+  if (!c || !out) return PVW_ERR_INVALID_PARAMETERS;
+  memcpy(out, c->hp.psi.data(), (size_t)c->hp.L * 8);
+  return PVW_OK;
+}
+int pvw_params_correctness_condition(const pvw_ctx* c, int* ok) {
+  if (!c || !ok) return PVW_ERR_INVALID_PARAMETERS;
+  *ok = c->hp.correctness_condition() ? 1 : 0;
+  return PVW_OK;
+}
+
+int pvw_crs_upload(pvw_ctx* c, const uint64_t* A, uint32_t flags) {
+  return guarded(c, [&] {
+    require(A != nullptr, PVW_ERR_INVALID_PARAMETERS, "A is null");
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+    const size_t kk = (size_t)k * k;
+    c->A.ensure((size_t)L * kk * ell * 8);
+    upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, flags);
+    c->A_set = true;
+    c->At_valid = false;
+  });
+}
+int pvw_crs_download(pvw_ctx* c, uint64_t* A) {
+  return guarded(c, [&] {
+    require(c->A_set, PVW_ERR_INVALID_PARAMETERS, "CRS has not been uploaded");
+    const size_t kk = (size_t)c->hp.k * c->hp.k;
+    download_polys(c, c->A.as<u64>(), kk * c->hp.ell, kk, A);
+  });
+}
+
+static void ensure_B(pvw_ctx* c) {
+  const size_t bytes = (size_t)c->hp.L * c->nrows * c->hp.k * c->hp.ell * 8;
+  if (c->B.bytes >= bytes) return;
+  c->B.ensure(bytes);
+  CUDA_CHECK(cudaMemsetAsync(c->B.p, 0, bytes, c->stream));  // GlobalPublicKey::new fills with zero polys, public_key.rs:196-208
+}
+static void check_rows(pvw_ctx* c, uint32_t row, uint32_t count) {
+  if ((uint64_t)row + count > c->hp.n)  // add_public_key: index >= n, public_key.rs:216-221
+    throw PvwException(PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("party index %u exceeds n=%u", row + count - 1, c->hp.n));
+  require(row >= c->row0 && (uint64_t)row + count <= (uint64_t)c->row0 + c->nrows, PVW_ERR_INDEX_OUT_OF_BOUNDS,
+          fmt("rows [%u, %u) are outside this context's shard [%u, %u)", row, row + count, c->row0, c->row0 + c->nrows));
+}
+
+int pvw_pk_upload_rows(pvw_ctx* c, uint32_t row, uint32_t count, const uint64_t* B, uint32_t flags) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(B != nullptr, PVW_ERR_INVALID_PARAMETERS, "B is null");
+    check_rows(c, row, count);
+    ensure_B(c);
+    const uint32_t k = c->hp.k, ell = c->hp.ell;
+    upload_polys(c, B, (uint64_t)count * k, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, flags);
+    c->num_keys = std::max(c->num_keys, row + count);
+  });
+}
+int pvw_pk_download_rows(pvw_ctx* c, uint32_t row, uint32_t count, uint64_t* B) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    check_rows(c, row, count);
+    ensure_B(c);
+    const uint32_t k = c->hp.k, ell = c->hp.ell;
+    download_polys(c, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, (uint64_t)count * k, B);
+  });
+}
+int pvw_pk_num_keys(const pvw_ctx* c, uint32_t* num_keys) {
+  if (!c || !num_keys) return PVW_ERR_INVALID_PARAMETERS;
+  *num_keys = c->num_keys;
+  return PVW_OK;
+}
+
+int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk, const int64_t* e, uint32_t flags) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(sk && e, PVW_ERR_INVALID_PARAMETERS, "sk / e is null");
+    require(c->A_set, PVW_ERR_KEYGEN, "CRS has not been uploaded");
+    check_rows(c, row, count);
+    ensure_B(c);
+    ensure_At(c);
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+    const size_t small = (size_t)count * k * ell * 8;
+    const long long* d_sk = (const long long*)stage_in(c, c->in_small, sk, small, flags);
+    const long long* d_e = (const long long*)stage_in(c, c->in_small2, e, small, flags);
+    // s_hat[p][limb][j][ell]
+    c->rhat.ensure((size_t)count * L * k * ell * 8);
+    launch_ntt_small(c->T, d_sk, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, c->stream);
+    check_launch(c);
+    // B rows <- NTT(e): item idx = p*k + cidx lands at B[limb][row+p][cidx]
+    u64* Brow = c->B.as<u64>() + (size_t)(row - c->row0) * k * ell;
+    launch_ntt_small(c->T, d_e, nullptr, (uint64_t)count * k, (uint32_t)std::min<uint64_t>((uint64_t)count * k, 0xFFFFFFFFu), Brow, 0,
+                     (size_t)c->nrows * k * ell, c->stream);
+    check_launch(c);
+    GemmArgs g{};
+    g.M = c->At.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
+    g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell;
+    g.O = Brow; g.O_ls = (size_t)c->nrows * k * ell; g.O_ds = (size_t)k * ell;
+    g.rows = k; g.D = count; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
+    gemm(c, g);
+    c->num_keys = std::max(c->num_keys, row + count);
+    if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));  // host buffers may be reused by the caller
+  });
+}
+
+int pvw_crs_multiply_by_randomness(pvw_ctx* c, uint32_t D, const uint64_t* r_hat, uint64_t* out) {
+  return guarded(c, [&] {
+    if (D == 0) return;
+    require(r_hat && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    require(c->A_set, PVW_ERR_INVALID_PARAMETERS, "CRS has not been uploaded");
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+    const size_t per = (size_t)k * L * ell;  // words per dealer
+    c->stage.ensure((size_t)D * per * 8);
+    c->rhat.ensure((size_t)D * per * 8);
+    c->z.ensure((size_t)D * per * 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->stage.p, r_hat, (size_t)D * per * 8, cudaMemcpyHostToDevice, c->stream));
+    // [D][k][L][ell] -> [D][L][k][ell]
+    launch_permute(c->stage.as<u64>(), c->rhat.as<u64>(), D, k, L, ell, per, (size_t)L * ell, ell, per, ell, (size_t)k * ell, c->stream);
+    check_launch(c);
+    CUDA_CHECK(cudaMemsetAsync(c->z.p, 0, (size_t)D * per * 8, c->stream));
+    GemmArgs g{};
+    g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
+    g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = per;
+    g.O = c->z.as<u64>(); g.O_ls = (size_t)k * ell; g.O_ds = per;
+    g.rows = k; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
+    gemm(c, g);
+    launch_permute(c->z.as<u64>(), c->stage.as<u64>(), D, L, k, ell, per, (size_t)k * ell, ell, per, ell, (size_t)L * ell, c->stream);
+    check_launch(c);
+    CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)D * per * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_ct_reserve(pvw_ctx* c, uint32_t capacity) {
+  return guarded(c, [&] {
+    const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell, w2 = (size_t)c->hp.L * c->nrows * c->hp.ell;
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->c1s.release(); c->c2s.release();
+    c->cap = 0;
+    if (capacity == 0) return;
+    c->c1s.ensure((size_t)capacity * w1 * 8);
+    c->c2s.ensure((size_t)capacity * w2 * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->c1s.p, 0, (size_t)capacity * w1 * 8, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->c2s.p, 0, (size_t)capacity * w2 * 8, c->stream));
+    c->cap = capacity;
+  });
+}
+
+int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, uint32_t c1_hi, const uint64_t* m, const int64_t* r,
+                      const int64_t* e1, const int64_t* e2, uint32_t flags) {
+  return guarded(c, [&] {
+    if (D == 0) return;
+    const HostParams& hp = c->hp;
+    const uint32_t L = hp.L, k = hp.k, ell = hp.ell, nrows = c->nrows;
+    require(m && r && e2, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    require(c1_lo <= c1_hi && c1_hi <= D, PVW_ERR_INVALID_PARAMETERS, "bad c1 dealer range");
+    require(c1_lo == c1_hi || e1 != nullptr, PVW_ERR_INVALID_PARAMETERS, "e1 is null");
+    require(c->A_set, PVW_ERR_INVALID_PARAMETERS, "CRS has not been uploaded");
+    // encryption.rs:117-121: is_full() <=> num_keys >= n ; restricted to this shard: every local row below num_keys
+    require(c->num_keys >= c->row0 + nrows, PVW_ERR_INVALID_PARAMETERS, "Global public key is not complete (missing party keys)");
+    // encryption.rs:124-128
+    require(hp.correctness_condition(), PVW_ERR_INVALID_PARAMETERS,
+            "Parameters do not satisfy correctness condition - decryption may fail");
+    require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS,
+            fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
+    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const long long* d_r = (const long long*)stage_in(c, c->in_small, r, (size_t)D * k * ell * 8, flags);
+    // r_hat[d][limb][j][ell]   (encryption.rs:147-154)
+    c->rhat.ensure((size_t)D * w1 * 8);
+    launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream);
+    check_launch(c);
+    u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
+    u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
+    if (c1_hi > c1_lo) {
+      const uint32_t Dc = c1_hi - c1_lo;
+      const int64_t* e1p = e1 + (size_t)c1_lo * k * ell;
+      const long long* d_e1 = (const long long*)stage_in(c, c->in_small2, e1p, (size_t)Dc * k * ell * 8, flags);
+      // c1 <- NTT(e1)   (encryption.rs:161-167), then c1 += A r_hat   (crs.rs:187-199, encryption.rs:171-173)
+      launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)Dc * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream);
+      check_launch(c);
+      GemmArgs g{};
+      g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
+      g.V = c->rhat.as<u64>() + (size_t)c1_lo * w1; g.V_ls = (size_t)k * ell; g.V_ds = w1;
+      g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1;
+      g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
+      gemm(c, g);
+    }
+    {
+      // c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
+      const long long* d_e2 = (const long long*)stage_in(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags);
+      const u64* d_m = (const u64*)stage_in(c, c->in_m, m, (size_t)D * nrows * 8, flags);
+      launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream);
+      check_launch(c);
+      GemmArgs g{};
+      g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
+      g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
+      g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2;
+      g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
+      gemm(c, g);
+    }
+    if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_ct_download(pvw_ctx* c, uint32_t slot, uint64_t* c1, uint64_t* c2) {
+  return guarded(c, [&] {
+    require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+    if (c1) download_polys(c, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, k, c1);
+    if (c2) download_polys(c, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, nrows, c2);
+  });
+}
+int pvw_ct_upload(pvw_ctx* c, uint32_t slot, const uint64_t* c1, const uint64_t* c2) {
+  return guarded(c, [&] {
+    require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+    if (c1) upload_polys(c, c1, k, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, PVW_IO_HOST);
+    if (c2) upload_polys(c, c2, nrows, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, PVW_IO_HOST);
+  });
+}
+int pvw_ct_c1_device_ptr(pvw_ctx* c, uint32_t slot, void** ptr, uint64_t* slot_stride) {
+  return guarded(c, [&] {
+    require(ptr != nullptr, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
+    const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell;
+    *ptr = c->c1s.as<u64>() + (size_t)slot * w1;
+    if (slot_stride) *slot_stride = w1;
+  });
+}
+
+static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps) {
+  const uint64_t S = (uint64_t)Pc * D;
+  c->y.ensure(decode_scratch_words_y(c->T, S) * 8);
+  c->X.ensure(decode_scratch_words_X(c->T, S) * 8);
+  launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream);
+  check_launch(c);
+  launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream);
+  check_launch(c);
+  launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream);
+  check_launch(c);
+}
+
+int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint32_t P, const uint32_t* party_idx, const int64_t* sk,
+                      uint64_t* out, uint32_t flags) {
+  return guarded(c, [&] {
+    if (D == 0 || P == 0) return;
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+    require(party_idx && sk && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    if (dealer_slots) {
+      for (uint32_t d = 0; d < D; d++)
+        require(dealer_slots[d] < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", dealer_slots[d], c->cap));
+    } else {
+      require(D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("%u ciphertexts requested, %u reserved", D, c->cap));
+    }
+    std::vector<uint32_t> local(P);
+    for (uint32_t p = 0; p < P; p++) {
+      // decrypt_party_shares: party_index >= n, decryption.rs:303-309
+      if (party_idx[p] >= c->hp.n) throw PvwException(PVW_ERR_INVALID_PARAMETERS, fmt("Party index %u exceeds maximum %u", party_idx[p], c->hp.n - 1));
+      require(party_idx[p] >= c->row0 && party_idx[p] < c->row0 + nrows, PVW_ERR_INDEX_OUT_OF_BOUNDS,
+              fmt("party %u is outside this context's shard [%u, %u)", party_idx[p], c->row0, c->row0 + nrows));
+      local[p] = party_idx[p] - c->row0;
+    }
+    c->idxp.ensure((size_t)P * 4);
+    CUDA_CHECK(cudaMemcpyAsync(c->idxp.p, local.data(), (size_t)P * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t* d_slots = nullptr;
+    if (dealer_slots) {
+      c->idxd.ensure((size_t)D * 4);
+      CUDA_CHECK(cudaMemcpyAsync(c->idxd.p, dealer_slots, (size_t)D * 4, cudaMemcpyHostToDevice, c->stream));
+      d_slots = c->idxd.as<uint32_t>();
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // `local` goes out of scope below only after use; keep it simple and safe
+    const long long* d_sk = (const long long*)stage_in(c, c->in_small, sk, (size_t)P * k * ell * 8, flags);
+    u64* d_out = reinterpret_cast<u64*>(out);
+    if (!(flags & PVW_IO_DEVICE)) { c->outd.ensure((size_t)P * D * 8); d_out = c->outd.as<u64>(); }
+    uint32_t Pc_max = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(P, c->decrypt_chunk_shares / std::max<uint32_t>(D, 1)));
+    c->shat.ensure((size_t)L * Pc_max * k * ell * 8);
+    c->z.ensure((size_t)D * L * Pc_max * ell * 8);
+    for (uint32_t p0 = 0; p0 < P; p0 += Pc_max) {
+      const uint32_t Pc = std::min(Pc_max, P - p0);
+      // s_hat[limb][p][j][ell]   (SecretKey::get_polynomial, secret_key.rs:98-112 -- once per party, not per ciphertext)
+      launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream);
+      check_launch(c);
+      // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274)
+      GemmArgs g{};
+      g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;
+      g.V = c->c1s.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell; g.V_dmap = d_slots;
+      g.O = c->z.as<u64>(); g.O_ls = (size_t)Pc * ell; g.O_ds = (size_t)L * Pc * ell;
+      g.S = c->c2s.as<u64>(); g.S_ls = (size_t)nrows * ell; g.S_ds = (size_t)L * nrows * ell; g.S_rowmap = c->idxp.as<uint32_t>() + p0;
+      g.rows = Pc; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
+      gemm(c, g);
+      decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, D, d_out + (size_t)p0 * D, D);
+    }
+    if (!(flags & PVW_IO_DEVICE)) {
+      CUDA_CHECK(cudaMemcpyAsync(out, d_out, (size_t)P * D * 8, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+  });
+}
+
+int pvw_decode_batch(pvw_ctx* c, uint32_t count, const uint64_t* zhat, uint64_t* out) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(zhat && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    const size_t poly = c->poly();
+    c->z.ensure((size_t)count * poly * 8);
+    c->outd.ensure((size_t)count * 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->z.p, zhat, (size_t)count * poly * 8, cudaMemcpyHostToDevice, c->stream));
+    // host layout [count][L][ell] read in place: "dealer" = item, one party per dealer
+    decode_on_device(c, c->z.as<u64>(), c->hp.ell, poly, 1, count, c->outd.as<u64>(), 0);
+    CUDA_CHECK(cudaMemcpyAsync(out, c->outd.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_ntt_forward_small(pvw_ctx* c, uint32_t count, const int64_t* coeffs, uint64_t* out) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(coeffs && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    const size_t poly = c->poly();
+    c->in_small.ensure((size_t)count * c->hp.ell * 8);
+    c->stage.ensure((size_t)count * poly * 8);
+    CUDA_CHECK(cudaMemcpyAsync(c->in_small.p, coeffs, (size_t)count * c->hp.ell * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_ntt_small(c->T, c->in_small.as<long long>(), nullptr, count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream);
+    check_launch(c);
+    CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_encode_scalars(pvw_ctx* c, uint32_t count, const uint64_t* m, uint64_t* out) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(m && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    const size_t poly = c->poly();
+    c->in_small.ensure((size_t)count * c->hp.ell * 8);
+    c->in_m.ensure((size_t)count * 8);
+    c->stage.ensure((size_t)count * poly * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->in_small.p, 0, (size_t)count * c->hp.ell * 8, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->in_m.p, m, (size_t)count * 8, cudaMemcpyHostToDevice, c->stream));
+    launch_ntt_small(c->T, c->in_small.as<long long>(), c->in_m.as<u64>(), count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream);
+    check_launch(c);
+    CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_ctx_synchronize(pvw_ctx* c) {
+  return guarded(c, [&] { CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+}
+void* pvw_ctx_stream(pvw_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
+  return guarded(c, [&] {
+    require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");
+    std::string n(name);
+    if (n == "gemm_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0 or 1"); c->gemm_impl = (int)value; }
+    else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
+    else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }
+    else throw PvwException(PVW_ERR_INVALID_PARAMETERS, "unknown option " + n);
+  });
+}
+uint64_t pvw_ctx_launch_count(const pvw_ctx* c) { return c ? c->launches : 0; }
+const char* pvw_version(void) { return "pvw_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

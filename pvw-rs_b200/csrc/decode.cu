@@ -1,0 +1,333 @@
+// decode.cu -- K4: the l-redundant PVW decoding of the noisy message zhat = <s,c1> - c2 (src/crypto/decryption.rs:10-58
+// with its helpers :61-247), restated so that every step is either per-limb modular arithmetic or arithmetic on one
+// multi-precision integer.  The reference moves between representations ~4l times per share (clone,
+// inverse NTT, CRT lift of all l coefficients, BigInt op, re-encode, forward NTT); every one of those "constant
+// polynomial" operations is arithmetic on a scalar mod Q, so the same integers are obtained by:
+//
+//   (1) decode_rns  : one inverse NTT per limb, then IN RNS  tmp_i = z_i*D - z_{i+1}  (:19-27),
+//                     last = Horner(tmp, D) (:30-33), w = -z_0 (:51-52); pre-multiplied by (Q/q_j)^-1 for the lift;
+//   (2) crt_lift    : CRT lift of the l+1 values {tmp_0..tmp_{l-2}, last, w} to integers in [0,Q)
+//                     (Vec<BigUint>::from(&Poly), :118,:213 -- fhe-math RnsContext::lift);
+//   (3) decode_tail : centred remainder of `last` by D^(l-1) (:154-178), the back-substitution
+//                     noise_i = round((noise_{i+1} - tmp_i)/D) with truncated division (:44-48,:180-207),
+//                     plaintext = -z_0 - noise_0 (:51-53) and the u64 conversion rules (:226-247).
+//
+// Results are the reference's for every input, including shares whose noise is too large to decode correctly.
+#include "kernels.cuh"
+#include "ntt_regs.cuh"
+
+namespace pvw {
+
+// ---------------------------------------------------------------------------------------------------------------
+// (1) thread = (share, limb)
+// ---------------------------------------------------------------------------------------------------------------
+template <int ELL>
+__global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, uint32_t Pc, uint64_t S,
+                                                         u64* __restrict__ y, const LimbConst* __restrict__ lcs,
+                                                         const u64* __restrict__ twi, const u64* __restrict__ twi_sh) {
+  __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
+  const uint32_t limb = blockIdx.y;
+  if (threadIdx.x < ELL) {
+    s_tw[threadIdx.x] = twi[(size_t)limb * ELL + threadIdx.x];
+    s_tw_sh[threadIdx.x] = twi_sh[(size_t)limb * ELL + threadIdx.x];
+  }
+  __syncthreads();
+  const LimbConst lc = lcs[limb];
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const uint64_t d = s / Pc, p = s % Pc;
+  u64 a[ELL];
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(z + d * z_ds + (size_t)limb * z_ls + p * ELL);
+#pragma unroll
+  for (int t = 0; t < ELL / 2; t++) {
+    ulonglong2 v = src[t];
+    a[2 * t] = v.x;
+    a[2 * t + 1] = v.y;
+  }
+  ntt_inverse_regs<ELL>(a, s_tw, s_tw_sh, lc.ninv, lc.ninv_sh, lc.q);
+  const u64 q = lc.q;
+  u64* yo = y + ((size_t)limb * (ELL + 1)) * S + s;
+  u64 last = 0;
+#pragma unroll
+  for (int i = 0; i < ELL - 1; i++) {
+    u64 tmp = submod(mulmod_shoup(a[i], lc.delta, lc.delta_sh, q), a[i + 1], q);           // decryption.rs:25
+    last = (i == 0) ? tmp : addmod(mulmod_shoup(last, lc.delta, lc.delta_sh, q), tmp, q);  // decryption.rs:30-33
+    yo[(size_t)i * S] = mulmod_shoup(tmp, lc.qhinv, lc.qhinv_sh, q);
+  }
+  yo[(size_t)(ELL - 1) * S] = mulmod_shoup(last, lc.qhinv, lc.qhinv_sh, q);
+  yo[(size_t)ELL * S] = mulmod_shoup(negmod(a[0], q), lc.qhinv, lc.qhinv_sh, q);            // z_0 * (-1), :52
+}
+
+void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st) {
+  const uint64_t S = (uint64_t)Pc * D;
+  if (S == 0) return;
+  dim3 grid((unsigned)((S + 127) / 128), T.L);
+  switch (T.ell) {
+    case 8: decode_rns_kernel<8><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh); break;
+    case 16: decode_rns_kernel<16><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh); break;
+    case 32: decode_rns_kernel<32><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (2) thread = (share, value i): acc = sum_j y_j * (Q/q_j)  (< L*Q, NWT+1 words in registers), then mod Q by
+//     conditional subtraction of Q << b.  Q/q_j words are uniform across the warp (broadcast loads).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NWT>
+__global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y, u64* __restrict__ X, uint64_t S, uint32_t L, uint32_t ellp1,
+                                                       uint32_t NW, const u64* __restrict__ qhat, const u64* __restrict__ Qsh, uint32_t LB) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = blockIdx.y;
+  if (s >= S) return;
+  u64 acc[NWT + 1];
+#pragma unroll
+  for (int w = 0; w <= NWT; w++) acc[w] = 0;
+  for (uint32_t j = 0; j < L; j++) {
+    const u64 yv = y[((size_t)j * ellp1 + i) * S + s];
+    const u64* qh = qhat + (size_t)j * NWT;
+    u64 carry = 0;
+#pragma unroll
+    for (int w = 0; w < NWT; w++) {
+      const u64 qw = qh[w];
+      const u64 lo = yv * qw, hi = __umul64hi(yv, qw);
+      u64 t = acc[w] + carry;
+      const u64 c1 = t < carry;
+      t += lo;
+      const u64 c2 = t < lo;
+      acc[w] = t;
+      carry = hi + c1 + c2;  // hi <= 2^64 - 2, so no overflow
+    }
+    acc[NWT] += carry;
+  }
+  for (int b = (int)LB - 1; b >= 0; b--) {
+    const u64* qs = Qsh + (size_t)b * (NWT + 1);
+    bool ge = true;  // acc >= Q<<b ?
+#pragma unroll
+    for (int w = NWT; w >= 0; w--) {
+      const u64 qw = qs[w];
+      if (acc[w] != qw) { ge = acc[w] > qw; break; }
+    }
+    if (ge) {
+      u64 borrow = 0;
+#pragma unroll
+      for (int w = 0; w <= NWT; w++) {
+        const u64 qw = qs[w];
+        const u64 d1 = acc[w] - qw, b1 = acc[w] < qw;
+        const u64 d2 = d1 - borrow, b2 = d1 < borrow;
+        acc[w] = d2;
+        borrow = b1 | b2;
+      }
+    }
+  }
+  u64* xo = X + ((size_t)i * NW) * S + s;
+#pragma unroll
+  for (int w = 0; w < NWT; w++)
+    if (w < (int)NW) xo[(size_t)w * S] = acc[w];
+}
+
+void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st) {
+  if (S == 0) return;
+  dim3 grid((unsigned)((S + 127) / 128), T.ell + 1);
+#define PVW_LIFT_CASE(N)                                                                                     \
+  case N:                                                                                                    \
+    crt_lift_kernel<N><<<grid, 128, 0, st>>>(y, X, S, T.L, T.ell + 1, T.NW, T.qhat, T.Qsh, T.LB);          \
+    break;
+  switch (T.NWT) {
+    PVW_LIFT_CASE(2)
+    PVW_LIFT_CASE(4)
+    PVW_LIFT_CASE(8)
+    PVW_LIFT_CASE(17)
+    PVW_LIFT_CASE(33)
+    PVW_LIFT_CASE(64)
+  }
+#undef PVW_LIFT_CASE
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (3) thread = share; multi-precision integers as little-endian u64 arrays in local memory (runtime length).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MAXW = 68;
+
+PVW_DEV int big_cmp(const u64* a, const u64* b, int n) {
+  for (int i = n - 1; i >= 0; i--)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return 0;
+}
+PVW_DEV void big_sub(u64* r, const u64* a, const u64* b, int n) {  // r = a - b (mod 2^(64n))
+  u64 borrow = 0;
+  for (int i = 0; i < n; i++) {
+    const u64 d1 = a[i] - b[i], b1 = a[i] < b[i];
+    const u64 d2 = d1 - borrow, b2 = d1 < borrow;
+    r[i] = d2;
+    borrow = b1 | b2;
+  }
+}
+PVW_DEV bool big_is_zero(const u64* a, int n) {
+  for (int i = 0; i < n; i++)
+    if (a[i]) return false;
+  return true;
+}
+// (q, r) = (u1*2^64 + u0) / d, d normalised, u1 < d, v = floor((2^128-1)/d) - 2^64   (Moller-Granlund, Alg. 4)
+PVW_DEV u64 div_2by1(u64 u1, u64 u0, u64 d, u64 v, u64* rem) {
+  u64 q0 = v * u1, q1 = __umul64hi(v, u1);
+  q0 += u0;
+  q1 += u1 + (q0 < u0) + 1;
+  u64 r = u0 - q1 * d;
+  if (r > q0) { q1--; r += d; }
+  if (r >= d) { q1++; r -= d; }
+  *rem = r;
+  return q1;
+}
+// Knuth algorithm D.  u: dividend, nu words (any value); v: normalised divisor (n words, top bit set), `shift` = the
+// normalisation shift already applied to v.  q receives nq = nu_eff - n + 1 words (caller zero-fills q[0..qcap)),
+// r receives the n-word remainder.  un is scratch of nu+1 words.
+PVW_DEV void big_divrem(const u64* u, int nu, const u64* v, int n, int shift, u64 vinv, u64* q, u64* r, u64* un) {
+  while (nu > 0 && u[nu - 1] == 0) nu--;
+  if (nu < n) {  // |u| < |v|
+    for (int i = 0; i < n; i++) r[i] = i < nu ? u[i] : 0;
+    return;
+  }
+  un[nu] = shift ? u[nu - 1] >> (64 - shift) : 0;
+  for (int i = nu - 1; i > 0; i--) un[i] = shift ? (u[i] << shift) | (u[i - 1] >> (64 - shift)) : u[i];
+  un[0] = u[0] << shift;
+  const u64 vt = v[n - 1];
+  for (int j = nu - n; j >= 0; j--) {
+    const u64 u1 = un[j + n], u0 = un[j + n - 1];
+    u64 qhat, rhat;
+    bool rhat_ovf = false;
+    if (u1 >= vt) {  // only u1 == vt can occur; qhat = B - 1
+      qhat = ~0ull;
+      rhat = u0 + vt;
+      rhat_ovf = rhat < u0;
+    } else {
+      qhat = div_2by1(u1, u0, vt, vinv, &rhat);
+    }
+    if (n >= 2) {
+      const u64 v2 = v[n - 2], u2 = un[j + n - 2];
+      while (!rhat_ovf) {
+        const u64 ph = __umul64hi(qhat, v2), pl = qhat * v2;
+        if (ph > rhat || (ph == rhat && pl > u2)) {
+          qhat--;
+          const u64 nr = rhat + vt;
+          rhat_ovf = nr < rhat;
+          rhat = nr;
+        } else {
+          break;
+        }
+      }
+    }
+    // multiply and subtract qhat * v from un[j .. j+n]
+    u64 carry = 0, borrow = 0;
+    for (int i = 0; i < n; i++) {
+      const u64 pl = qhat * v[i], ph = __umul64hi(qhat, v[i]);
+      const u64 lo = pl + carry;
+      carry = ph + (lo < pl);
+      const u64 x = un[i + j];
+      const u64 d1 = x - lo, b1 = x < lo;
+      const u64 d2 = d1 - borrow, b2 = d1 < borrow;
+      un[i + j] = d2;
+      borrow = b1 | b2;
+    }
+    {
+      const u64 x = un[j + n];
+      const u64 d1 = x - carry, b1 = x < carry;
+      const u64 d2 = d1 - borrow, b2 = d1 < borrow;
+      un[j + n] = d2;
+      borrow = b1 | b2;
+    }
+    if (borrow) {  // add back
+      qhat--;
+      u64 c = 0;
+      for (int i = 0; i < n; i++) {
+        const u64 s1 = un[i + j] + v[i], c1 = s1 < v[i];
+        const u64 s2 = s1 + c, c2 = s2 < c;
+        un[i + j] = s2;
+        c = c1 | c2;
+      }
+      un[j + n] += c;
+    }
+    q[j] = qhat;
+  }
+  for (int i = 0; i < n; i++) r[i] = shift ? (un[i] >> shift) | (un[i + 1] << (64 - shift)) : un[i];
+}
+
+__global__ void __launch_bounds__(128) decode_tail_kernel(const u64* __restrict__ X, uint64_t S, uint32_t Pc, uint32_t ell, u64* __restrict__ out,
+                                                          size_t out_ps, const DevTables T) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int NW = (int)T.NW;
+  u64 noise[MAXW], cur[MAXW], num[MAXW], quo[MAXW], scratch[MAXW], rem[MAXW];
+  // ---- last component: centred remainder modulo M = D^(l-1)   (reduce_modulo_poly, decryption.rs:154-178)
+  for (int w = 0; w < NW; w++) cur[w] = X[((size_t)(ell - 1) * NW + w) * S + s];
+  bool neg = big_cmp(cur, T.halfQ, NW) > 0;                      // centre(): x > Q/2  -> x - Q
+  if (neg) big_sub(num, T.Qw, cur, NW); else for (int w = 0; w < NW; w++) num[w] = cur[w];
+  for (int w = 0; w < NW + 2; w++) quo[w] = 0;
+  for (int w = 0; w < NW; w++) rem[w] = 0;
+  big_divrem(num, NW, T.divM_v, (int)T.divM_n, (int)T.divM_shift, T.divM_vinv, quo, rem, scratch);  // |x| % M (truncated)
+  // `reduced > half_mod` / `reduced < -half_mod`: both mean |rem| > floor(M/2); the sign then flips
+  bool rneg = neg;
+  if (big_cmp(rem, T.halfM, NW) > 0) {
+    big_sub(rem, T.Mw, rem, NW);  // M - |rem|
+    rneg = !neg;
+  }
+  if (big_is_zero(rem, NW)) rneg = false;
+  // noise_{l-1} as an element of [0,Q): bigints_to_poly of a signed value, parameters.rs:437-452
+  if (rneg) big_sub(noise, T.Qw, rem, NW); else for (int w = 0; w < NW; w++) noise[w] = rem[w];
+  // ---- back-substitution  noise_i = round((noise_{i+1} - tmp_i) / D)   (decryption.rs:44-48, :180-207)
+  for (int i = (int)ell - 2; i >= 0; i--) {
+    for (int w = 0; w < NW; w++) cur[w] = X[((size_t)i * NW + w) * S + s];
+    // diff = (noise - tmp_i) mod Q
+    if (big_cmp(noise, cur, NW) >= 0) big_sub(num, noise, cur, NW);
+    else { big_sub(num, cur, noise, NW); big_sub(num, T.Qw, num, NW); }
+    const bool nneg = big_cmp(num, T.halfQ, NW) > 0;
+    if (nneg) big_sub(num, T.Qw, num, NW);                       // |centre(diff)|
+    // |quotient| = floor((2|num| + D) / (2D)) for either sign (truncated division of 2num -/+ D by 2D)
+    u64 c = 0;
+    for (int w = 0; w < NW; w++) { const u64 x = num[w]; num[w] = (x << 1) | c; c = x >> 63; }
+    num[NW] = c;
+    c = 0;
+    for (int w = 0; w <= NW; w++) {
+      const u64 dw = w < NW ? T.Dw[w] : 0;
+      const u64 s1 = num[w] + dw, c1 = s1 < dw;
+      const u64 s2 = s1 + c, c2 = s2 < c;
+      num[w] = s2;
+      c = c1 | c2;
+    }
+    for (int w = 0; w < NW + 2; w++) quo[w] = 0;
+    big_divrem(num, NW + 1, T.div2D_v, (int)T.div2D_n, (int)T.div2D_shift, T.div2D_vinv, quo, rem, scratch);
+    if (nneg && !big_is_zero(quo, NW)) big_sub(noise, T.Qw, quo, NW); else for (int w = 0; w < NW; w++) noise[w] = quo[w];
+  }
+  // ---- plaintext = (-z_0) - noise_0 mod Q, centred, then extract_constant_term_as_u64 (decryption.rs:226-247)
+  for (int w = 0; w < NW; w++) cur[w] = X[((size_t)ell * NW + w) * S + s];
+  if (big_cmp(cur, noise, NW) >= 0) big_sub(num, cur, noise, NW);
+  else { big_sub(num, noise, cur, NW); big_sub(num, T.Qw, num, NW); }
+  u64 result;
+  if (big_cmp(num, T.halfQ, NW) > 0) {           // negative: value = num - Q
+    big_sub(cur, T.Qw, num, NW);                 // |value|
+    bool small = cur[0] <= 1000;
+    for (int w = 1; w < NW; w++) small = small && cur[w] == 0;
+    if (small) result = 0;                       // "small negative values might be noise"
+    else {                                       // (value + Q) % Q = num ; to_u64().unwrap_or(0)
+      bool fits = true;
+      for (int w = 1; w < NW; w++) fits = fits && num[w] == 0;
+      result = fits ? num[0] : 0;
+    }
+  } else {
+    bool fits = true;
+    for (int w = 1; w < NW; w++) fits = fits && num[w] == 0;
+    result = fits ? num[0] : 0;
+  }
+  const uint64_t d = s / Pc, p = s % Pc;
+  out[p * out_ps + d] = result;
+}
+
+void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t D, u64* out, size_t out_ps, cudaStream_t st) {
+  const uint64_t S = (uint64_t)Pc * D;
+  if (S == 0) return;
+  decode_tail_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T);
+}
+
+size_t decode_scratch_words_y(const DevTables& T, uint64_t S) { return (size_t)T.L * (T.ell + 1) * S; }
+size_t decode_scratch_words_X(const DevTables& T, uint64_t S) { return (size_t)(T.ell + 1) * T.NW * S; }
+
+}  // namespace pvw

@@ -1,0 +1,74 @@
+// kernels.cuh -- launcher declarations shared by the .cu files of libpvw_b200.so.
+// Device layout ("limb-major"): a vector of polynomials is stored as [..][L][len][ell] so that, for one RNS limb,
+// the `len` polynomials' ell-slot blocks are contiguous (len*ell*8 bytes): the modulus is uniform per CTA and a
+// row of k polynomials is one contiguous 1D bulk-copy (TMA) source.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "modarith.cuh"
+
+namespace pvw {
+
+// device-resident per-context constant tables
+struct DevTables {
+  const LimbConst* lc;     // [L]
+  const u64* tw;           // [L][ell] psi^brv(i)                     (forward NTT, fhe-math NttOperator omegas)
+  const u64* tw_sh;        //          Shoup companions
+  const u64* twi;          // [L][ell] psi^-brv(i)                    (inverse NTT)
+  const u64* twi_sh;
+  const u64* gadget_hat;   // [L][ell] NTT([1, D, .., D^(l-1)] mod q) (parameters.rs:288-308)
+  // CRT lift
+  const u64* qhat;         // [L][NWT]   Q/q_j, zero padded to the template width
+  const u64* Qsh;          // [LB][NWT+1] Q << b
+  // decode tail (each NW words): Q, floor(Q/2), M = D^(l-1), floor(M/2), D; then the normalised divisors
+  const u64* Qw; const u64* halfQ; const u64* Mw; const u64* halfM; const u64* Dw;
+  const u64* divM_v; const u64* div2D_v;
+  uint32_t L, ell, NW, NWT, LB;
+  uint32_t divM_n, divM_shift, div2D_n, div2D_shift;
+  u64 divM_vinv, div2D_vinv;
+};
+
+// ---- ntt.cu -------------------------------------------------------------------------------------------------
+// small signed coefficients -> RNS -> forward NTT (+ optional message encoding), written in the device layout:
+//   item idx in [0,count): vec = idx / inner, j = idx % inner;  out[vec*vstride + limb*lstride + j*ell + c]
+//   value = NTT(rns(coef[idx]))[c] (+ (m[idx] as i64 mod q) * gadget_hat[limb][c] when m != nullptr)
+void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
+                      size_t vstride, size_t lstride, cudaStream_t st);
+// generic strided block copy:  out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c],  c < blk
+void launch_permute(const u64* in, u64* out, uint64_t Bn, uint64_t X, uint64_t Y, uint32_t blk, size_t ibs, size_t ixs, size_t iys,
+                    size_t obs, size_t oxs, size_t oys, cudaStream_t st);
+
+// ---- mac.cu -------------------------------------------------------------------------------------------------
+// NTT-domain polynomial matrix product for every limb and slot:
+//   acc[row][d][c] = sum_{j<k} M[limb][row][j][c] * V[d][limb][j][c]  mod q_limb
+//   mode 0: O = acc + O (in place: O was pre-loaded with NTT(e) (+ m*g))   -- c1, c2, keygen
+//   mode 1: O = acc - S                                                    -- decrypt (S = c2)
+struct GemmArgs {
+  const u64* M; size_t M_ls, M_rs;        // M[limb*M_ls + row*M_rs + j*ell + c]
+  const u64* V; size_t V_ls, V_ds;        // V[d*V_ds + limb*V_ls + j*ell + c]
+  u64* O; size_t O_ls, O_ds;              // O[d*O_ds + limb*O_ls + row*ell + c]
+  const u64* S; size_t S_ls, S_ds;        // S[d*S_ds + limb*S_ls + srow(row)*ell + c]
+  const uint32_t* S_rowmap;               // optional: srow(row) = S_rowmap[row] (party index list), else row
+  const uint32_t* V_dmap;                 // optional: dealer slot list, V/S dealer index = V_dmap[d], else d
+  uint32_t rows, D, k, L, ell;
+  int mode;
+  const LimbConst* lc;
+};
+// impl: 0 = synchronous shared-memory tiles, 1 = cp.async.bulk (TMA) + mbarrier pipeline with a producer warp
+void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st);
+size_t mac_gemm_launches(const GemmArgs& a);
+
+// ---- decode.cu ----------------------------------------------------------------------------------------------
+// share s' = d*Pc + p  (d < D, p < Pc).  z[d*z_ds + limb*z_ls + p*ell + c]  ->  y[(limb*(ell+1) + i)*S + s']
+void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st);
+// X[(i*NW + w)*S + s'] = CRT lift of y[.][i][s']
+void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st);
+// out[p*out_ps + d] for s' = d*Pc + p
+void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t D, u64* out, size_t out_ps, cudaStream_t st);
+size_t decode_scratch_words_y(const DevTables& T, uint64_t S);
+size_t decode_scratch_words_X(const DevTables& T, uint64_t S);
+
+}  // namespace pvw

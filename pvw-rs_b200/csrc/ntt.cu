@@ -1,0 +1,87 @@
+// ntt.cu -- K1: per-RNS-limb ell-point negacyclic NTT held entirely in registers, fused with the RNS reduction of
+// the small signed inputs and (for c2) the message encoding; plus the strided block copy used for layout changes.
+//
+// Replaces, on the device: Poly::from_coefficients + change_representation(Ntt) (src/crypto/encryption.rs:147-154,
+// src/keys/secret_key.rs:98-112), sample_error_1/2's bigints_to_poly + NTT (src/params/parameters.rs:264-284,
+// 420-474) and encode_scalar (parameters.rs:346-367).  Convention (fhe-math NttOperator): natural
+// order in, bit-reversed order out, slot i = evaluation at psi^(2*brv(i)+1).
+#include "kernels.cuh"
+#include "ntt_regs.cuh"
+
+namespace pvw {
+
+template <int ELL>
+__global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
+                                                        uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
+                                                        const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
+                                                        const u64* __restrict__ tw_sh, const u64* __restrict__ gadget_hat) {
+  __shared__ u64 s_tw[ELL], s_tw_sh[ELL], s_g[ELL];
+  const uint32_t limb = blockIdx.y;
+  if (threadIdx.x < ELL) {
+    s_tw[threadIdx.x] = tw[(size_t)limb * ELL + threadIdx.x];
+    s_tw_sh[threadIdx.x] = tw_sh[(size_t)limb * ELL + threadIdx.x];
+    s_g[threadIdx.x] = gadget_hat[(size_t)limb * ELL + threadIdx.x];
+  }
+  __syncthreads();
+  const LimbConst lc = lcs[limb];
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  u64 a[ELL];
+  const longlong2* src = reinterpret_cast<const longlong2*>(coef + idx * ELL);
+#pragma unroll
+  for (int t = 0; t < ELL / 2; t++) {
+    longlong2 v = src[t];
+    a[2 * t] = reduce_i64(v.x, lc);
+    a[2 * t + 1] = reduce_i64(v.y, lc);
+  }
+  ntt_forward_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
+  if (m != nullptr) {
+    u64 mr = reduce_i64((long long)m[idx], lc);  // `scalars[p] as i64`, encryption.rs:195
+#pragma unroll
+    for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], mulmod(mr, s_g[t], lc), lc.q);
+  }
+  uint64_t vec = idx / inner, j = idx % inner;
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
+#pragma unroll
+  for (int t = 0; t < ELL / 2; t++) dst[t] = make_ulonglong2(a[2 * t], a[2 * t + 1]);
+}
+
+void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
+                      size_t vstride, size_t lstride, cudaStream_t st) {
+  if (count == 0) return;
+  dim3 grid((unsigned)((count + 127) / 128), T.L);
+#define PVW_NTT_CASE(E)                                                                                                       \
+  case E:                                                                                                                     \
+    ntt_small_kernel<E><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat); \
+    break;
+  switch (T.ell) {
+    PVW_NTT_CASE(8)
+    PVW_NTT_CASE(16)
+    PVW_NTT_CASE(32)
+  }
+#undef PVW_NTT_CASE
+}
+
+// out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c]; one thread per 16 bytes (blk is a multiple of 2)
+__global__ void __launch_bounds__(256) permute_kernel(const ulonglong2* __restrict__ in, ulonglong2* __restrict__ out, uint64_t total,
+                                                      uint64_t X, uint64_t Y, uint32_t blk2, size_t ibs, size_t ixs, size_t iys, size_t obs,
+                                                      size_t oxs, size_t oys) {
+  uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  uint32_t c = (uint32_t)(e % blk2);
+  uint64_t r = e / blk2;
+  uint64_t x = r % X; r /= X;   // x fastest: consecutive threads walk the output's contiguous axis when oxs == blk
+  uint64_t y = r % Y;
+  uint64_t b = r / Y;
+  out[(b * obs + x * oxs + y * oys) / 2 + c] = in[(b * ibs + x * ixs + y * iys) / 2 + c];
+}
+
+void launch_permute(const u64* in, u64* out, uint64_t Bn, uint64_t X, uint64_t Y, uint32_t blk, size_t ibs, size_t ixs, size_t iys,
+                    size_t obs, size_t oxs, size_t oys, cudaStream_t st) {
+  uint64_t total = Bn * X * Y * (blk / 2);
+  if (total == 0) return;
+  permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(in), reinterpret_cast<ulonglong2*>(out),
+                                                                  total, X, Y, blk / 2, ibs, ixs, iys, obs, oxs, oys);
+}
+
+}  // namespace pvw

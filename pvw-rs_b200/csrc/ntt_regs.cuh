@@ -1,0 +1,54 @@
+// ntt_regs.cuh -- ell-point negacyclic NTT on a register array (ell in {8,16,32}); loops fully unrolled so that every
+// index is a compile-time constant.  Forward: Cooley-Tukey, natural in / bit-reversed out, twiddle tw[m+i] =
+// psi^brv(m+i).  Inverse: Gentleman-Sande with twi[h+i] = psi^-brv(h+i) and a final scale by ell^-1.
+// Canonical residues in and out (fhe-math NttOperator::forward/backward produce fully reduced outputs).
+#pragma once
+#include "modarith.cuh"
+
+namespace pvw {
+
+template <int ELL>
+PVW_DEV void ntt_forward_regs(u64 (&a)[ELL], const u64* tw, const u64* tw_sh, u64 q) {
+  int t = ELL;
+#pragma unroll
+  for (int m = 1; m < ELL; m <<= 1) {
+    t >>= 1;
+#pragma unroll
+    for (int i = 0; i < m; i++) {
+      const u64 s = tw[m + i], s_sh = tw_sh[m + i];
+      const int j1 = 2 * i * t;
+#pragma unroll
+      for (int j = j1; j < j1 + t; j++) {
+        u64 u = a[j], v = mulmod_shoup(a[j + t], s, s_sh, q);
+        a[j] = addmod(u, v, q);
+        a[j + t] = submod(u, v, q);
+      }
+    }
+  }
+}
+
+template <int ELL>
+PVW_DEV void ntt_inverse_regs(u64 (&a)[ELL], const u64* twi, const u64* twi_sh, u64 ninv, u64 ninv_sh, u64 q) {
+  int t = 1;
+#pragma unroll
+  for (int m = ELL; m > 1; m >>= 1) {
+    const int h = m >> 1;
+    int j1 = 0;
+#pragma unroll
+    for (int i = 0; i < h; i++) {
+      const u64 s = twi[h + i], s_sh = twi_sh[h + i];
+#pragma unroll
+      for (int j = j1; j < j1 + t; j++) {
+        u64 u = a[j], v = a[j + t];
+        a[j] = addmod(u, v, q);
+        a[j + t] = mulmod_shoup(submod(u, v, q), s, s_sh, q);
+      }
+      j1 += 2 * t;
+    }
+    t <<= 1;
+  }
+#pragma unroll
+  for (int j = 0; j < ELL; j++) a[j] = mulmod_shoup(a[j], ninv, ninv_sh, q);
+}
+
+}  // namespace pvw

@@ -1,0 +1,271 @@
+"""Engine: one `pvw_ctx` (one CUDA device, one shard of parties) behind an object, speaking numpy on the host
+side and torch CUDA tensors / raw device pointers on the device side.  No arithmetic happens here: every method
+is one call into the C ABI (include/pvw_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from .errors import PvwError
+
+
+def _is_device_tensor(x) -> bool:
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+class _Arg:
+    """pointer + keep-alive for one call argument (numpy host array or torch CUDA tensor)"""
+
+    def __init__(self, x, dtype, shape: Optional[Sequence[int]] = None, name: str = "argument"):
+        self.device = _is_device_tensor(x)
+        if self.device:
+            import torch
+            want = {np.uint64: (torch.uint64, torch.int64), np.int64: (torch.int64,), np.uint32: (torch.uint32, torch.int32)}[dtype]
+            if x.dtype not in want or not x.is_contiguous():
+                raise PvwError("InvalidParameters", f"{name}: need a contiguous CUDA tensor of dtype {want[0]}")
+            self.keep = x
+            self.ptr = x.data_ptr()
+            got = tuple(x.shape)
+        else:
+            a = np.ascontiguousarray(x, dtype=dtype)
+            self.keep = a
+            self.ptr = a.ctypes.data
+            got = a.shape
+        if shape is not None and tuple(got) != tuple(shape):
+            raise PvwError("DimensionMismatch", f"{name}: expected shape {tuple(shape)}, got {tuple(got)}")
+
+
+class Engine:
+    """Owns a pvw_ctx.  `row0`/`nrows` select the shard of parties (rows of B) this context holds."""
+
+    def __init__(self, n: int, k: int, l: int, moduli: Sequence[int], psi: Optional[Sequence[int]] = None,
+                 secret_variance: float = 0.5, error_bound_1: int = 100, error_bound_2: int = 200,
+                 row0: int = 0, nrows: int = 0, device: int = 0):
+        self.lib = _ffi.load()
+        for name, v in (("n", n), ("k", k), ("l", l), ("row0", row0), ("nrows", nrows)):
+            if not 0 <= int(v) < 2 ** 32:
+                raise PvwError("InvalidParameters", f"{name} out of range")
+        for name, v in (("error_bound_1", error_bound_1), ("error_bound_2", error_bound_2)):
+            if not 0 <= int(v) < 2 ** 63:
+                # the reference type is BigInt (parameters.rs:31-33); every call site uses <= u32 (parameters.rs:110-114)
+                raise PvwError("InvalidParameters", f"{name} must be in [0, 2^63)")
+        mods = [int(q) for q in moduli]
+        if any(q < 0 or q >= 2 ** 64 for q in mods):
+            raise PvwError("InvalidParameters", "Context creation failed: modulus does not fit 64 bits")
+        self._mods = (C.c_uint64 * max(1, len(mods)))(*mods)
+        self._psi = (C.c_uint64 * len(mods))(*[int(p) for p in psi]) if psi is not None else None
+        desc = _ffi.PvwParamsDesc(int(n), int(k), int(l), len(mods), self._mods if mods else None, self._psi,
+                                  float(secret_variance), int(error_bound_1), int(error_bound_2), int(row0), int(nrows), int(device))
+        h = C.c_void_p()
+        rc = self.lib.pvw_ctx_create(C.byref(h), C.byref(desc))
+        if rc != 0:
+            raise PvwError(_ffi.STATUS_NAMES.get(rc, "InternalError"), (self.lib.pvw_last_error(None) or b"").decode())
+        self.h = h
+        self.n, self.k, self.l, self.L = int(n), int(k), int(l), len(mods)
+        self.moduli = mods
+        self.row0 = int(row0)
+        self.nrows = int(nrows) if nrows else self.n - self.row0
+        self.device = int(device)
+        self.poly = (self.L, self.l)
+        self.capacity = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PvwError(_ffi.STATUS_NAMES.get(rc, "InternalError"), (self.lib.pvw_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pvw_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self.lib.pvw_ctx_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.pvw_ctx_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pvw_ctx_launch_count(self.h))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.pvw_ctx_set_option(self.h, name.encode(), int(value)))
+
+    # -- parameters ------------------------------------------------------------------------------
+    def _bigint(self, which: int) -> int:
+        nw = C.c_uint32()
+        self._check(self.lib.pvw_params_bigint(self.h, which, None, 0, C.byref(nw)))
+        buf = np.zeros(max(1, nw.value), dtype=np.uint64)
+        self._check(self.lib.pvw_params_bigint(self.h, which, buf.ctypes.data, len(buf), C.byref(nw)))
+        return sum(int(w) << (64 * i) for i, w in enumerate(buf[:nw.value]))
+
+    @property
+    def q_total(self) -> int:
+        return self._bigint(0)
+
+    @property
+    def delta(self) -> int:
+        return self._bigint(1)
+
+    @property
+    def delta_power_l_minus_1(self) -> int:
+        return self._bigint(2)
+
+    @property
+    def psi(self):
+        out = np.zeros(self.L, dtype=np.uint64)
+        self._check(self.lib.pvw_params_psi(self.h, out.ctypes.data))
+        return [int(x) for x in out]
+
+    def verify_correctness_condition(self) -> bool:
+        ok = C.c_int()
+        self._check(self.lib.pvw_params_correctness_condition(self.h, C.byref(ok)))
+        return bool(ok.value)
+
+    # -- CRS / public key residency --------------------------------------------------------------
+    def crs_upload(self, A):
+        a = _Arg(A, np.uint64, (self.k, self.k) + self.poly, "A")
+        self._check(self.lib.pvw_crs_upload(self.h, a.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+
+    def crs_download(self) -> np.ndarray:
+        out = np.empty((self.k, self.k) + self.poly, dtype=np.uint64)
+        self._check(self.lib.pvw_crs_download(self.h, out.ctypes.data))
+        return out
+
+    def pk_upload_rows(self, row: int, B):
+        count = int(B.shape[0])
+        a = _Arg(B, np.uint64, (count, self.k) + self.poly, "B rows")
+        self._check(self.lib.pvw_pk_upload_rows(self.h, row, count, a.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+
+    def pk_download_rows(self, row: int, count: int) -> np.ndarray:
+        out = np.empty((count, self.k) + self.poly, dtype=np.uint64)
+        self._check(self.lib.pvw_pk_download_rows(self.h, row, count, out.ctypes.data))
+        return out
+
+    @property
+    def num_keys(self) -> int:
+        v = C.c_uint32()
+        self._check(self.lib.pvw_pk_num_keys(self.h, C.byref(v)))
+        return v.value
+
+    def keygen_batch(self, row: int, sk, e):
+        count = int(sk.shape[0])
+        a = _Arg(sk, np.int64, (count, self.k, self.l), "sk")
+        b = _Arg(e, np.int64, (count, self.k, self.l), "e")
+        if a.device != b.device:
+            raise PvwError("InvalidParameters", "sk and e must both be host or both be device arrays")
+        self._check(self.lib.pvw_keygen_batch(self.h, row, count, a.ptr, b.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+
+    def crs_multiply_by_randomness(self, r_hat) -> np.ndarray:
+        r = np.ascontiguousarray(r_hat, dtype=np.uint64)
+        D = r.shape[0]
+        if r.shape != (D, self.k) + self.poly:
+            raise PvwError("DimensionMismatch", f"expected {self.k} polynomials, got shape {r.shape}")
+        out = np.empty_like(r)
+        self._check(self.lib.pvw_crs_multiply_by_randomness(self.h, D, r.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- ciphertext store ------------------------------------------------------------------------
+    def ct_reserve(self, capacity: int):
+        self._check(self.lib.pvw_ct_reserve(self.h, capacity))
+        self.capacity = capacity
+
+    def encrypt_batch(self, slot0: int, m, r, e1, e2, c1_range=None):
+        """m [D][nrows] u64; r, e1 [D][k][l] i64; e2 [D][nrows][l] i64 -- all host or all device"""
+        D = int(m.shape[0])
+        lo, hi = (0, D) if c1_range is None else c1_range
+        am = _Arg(m, np.uint64, (D, self.nrows), "m")
+        ar = _Arg(r, np.int64, (D, self.k, self.l), "r")
+        ae2 = _Arg(e2, np.int64, (D, self.nrows, self.l), "e2")
+        ae1 = _Arg(e1, np.int64, (D, self.k, self.l), "e1") if e1 is not None else None
+        devs = {a.device for a in (am, ar, ae2, ae1) if a is not None}
+        if len(devs) != 1:
+            raise PvwError("InvalidParameters", "inputs must be all host or all device arrays")
+        self._check(self.lib.pvw_encrypt_batch(self.h, slot0, D, lo, hi, am.ptr, ar.ptr, ae1.ptr if ae1 else None, ae2.ptr,
+                                               _ffi.PVW_IO_DEVICE if devs.pop() else 0))
+
+    def ct_download(self, slot: int, want_c1=True, want_c2=True):
+        c1 = np.empty((self.k,) + self.poly, dtype=np.uint64) if want_c1 else None
+        c2 = np.empty((self.nrows,) + self.poly, dtype=np.uint64) if want_c2 else None
+        self._check(self.lib.pvw_ct_download(self.h, slot, c1.ctypes.data if want_c1 else None, c2.ctypes.data if want_c2 else None))
+        return c1, c2
+
+    def ct_upload(self, slot: int, c1=None, c2=None):
+        a1 = _Arg(c1, np.uint64, (self.k,) + self.poly, "c1") if c1 is not None else None
+        a2 = _Arg(c2, np.uint64, (self.nrows,) + self.poly, "c2") if c2 is not None else None
+        self._check(self.lib.pvw_ct_upload(self.h, slot, a1.ptr if a1 else None, a2.ptr if a2 else None))
+
+    def c1_device_ptr(self, slot: int = 0):
+        p, stride = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.pvw_ct_c1_device_ptr(self.h, slot, C.byref(p), C.byref(stride)))
+        return int(p.value), int(stride.value)
+
+    def c1_store_tensor(self, slot0: int, count: int):
+        """torch view [count][L*k*l] (int64 reinterpretation) of the device-resident c1 of slots [slot0, slot0+count),
+        for collectives issued by the host layer (NCCL all-gather over dealers)."""
+        import torch
+        ptr, stride = self.c1_device_ptr(slot0)
+
+        class _Holder:
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (count, stride), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+        return torch.as_tensor(h, device=f"cuda:{self.device}")
+
+    def decrypt_batch(self, party_idx, sk, dealer_slots=None, D: Optional[int] = None, out=None):
+        """out[p][d] for P parties (global indices inside the shard) x D stored ciphertexts"""
+        pidx = np.ascontiguousarray(party_idx, dtype=np.uint32)
+        P = len(pidx)
+        if dealer_slots is not None:
+            ds = np.ascontiguousarray(dealer_slots, dtype=np.uint32)
+            D = len(ds)
+        else:
+            ds = None
+            D = self.capacity if D is None else D
+        a = _Arg(sk, np.int64, (P, self.k, self.l), "sk")
+        if a.device:
+            if out is None:
+                import torch
+                out = torch.empty((P, D), dtype=torch.int64, device=sk.device)
+            o = _Arg(out, np.uint64, (P, D), "out")
+            self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr, o.ptr,
+                                                   _ffi.PVW_IO_DEVICE))
+            return out
+        res = np.empty((P, D), dtype=np.uint64)
+        self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr,
+                                               res.ctypes.data, 0))
+        return res
+
+    def decode_batch(self, zhat) -> np.ndarray:
+        z = np.ascontiguousarray(zhat, dtype=np.uint64)
+        count = z.size // (self.L * self.l)
+        out = np.empty(count, dtype=np.uint64)
+        self._check(self.lib.pvw_decode_batch(self.h, count, z.ctypes.data, out.ctypes.data))
+        return out
+
+    def encode_scalars(self, scalars) -> np.ndarray:
+        m = np.ascontiguousarray(scalars, dtype=np.uint64)
+        out = np.empty(m.shape + self.poly, dtype=np.uint64)
+        self._check(self.lib.pvw_encode_scalars(self.h, m.size, m.ctypes.data, out.ctypes.data))
+        return out
+
+    def ntt_forward_small(self, coeffs) -> np.ndarray:
+        c = np.ascontiguousarray(coeffs, dtype=np.int64)
+        if c.shape[-1] != self.l:
+            raise PvwError("InvalidParameters", f"Expected {self.l} coefficients, got {c.shape[-1]}")
+        lead = c.shape[:-1]
+        out = np.empty(lead + self.poly, dtype=np.uint64)
+        self._check(self.lib.pvw_ntt_forward_small(self.h, int(np.prod(lead, dtype=np.int64)), c.ctypes.data, out.ctypes.data))
+        return out

@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- party-shares encrypted + decrypted per second on the 128-bit parameter set (BASELINE.json).
+
+A "step" is one pass of the hot path over one batch of synthetic dealers:
+    encrypt (c1 = A r + e1, c2 = B r + e2 + m g) for the step's dealers x all local parties, then
+    decrypt (<s, c1> - c2, l-redundant decode) of every local party x every dealer of the step.
+Workload C3 of SURVEY.md 8(d): k=256, l=8, 17 x 62-bit moduli (Q 1054 bit), n=4096 parties.
+Multi-GPU (one process per GPU, torchrun): rows of B / parties are sharded across ranks, A is broadcast once over
+NCCL, every rank computes c1 for its slice of the step's dealers and the slices are all-gathered over NCCL; the
+number of dealers per step grows with the rank count so that the per-GPU work is fixed ("weak").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dealers D_per_gpu] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same through the host-buffer C-ABI
+calls (H2D of r/e1/e2/m/sk and D2H of the plaintexts inside the timed region), `roofline` = the MAC kernel against
+the measured HBM peak on algorithmic bytes, `cpu_baseline` = the oracle port on the host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "party-shares encrypted+decrypted/sec"
+UNIT = "shares/s"
+N_PARTIES, K_DIM, ELL, N_LIMBS = 4096, 256, 8, 17
+SEED = 0x5056572D42323030
+
+
+def p128_moduli():
+    import pvw_oracle as O          # parameter-set definition only (prime search), not on any timed path
+    return O.largest_ntt_primes(N_LIMBS)
+
+
+def workload_name(n=N_PARTIES):
+    return f"C3 P128: n={n} parties, k={K_DIM}, l={ELL}, L={N_LIMBS}x62-bit (Q 1054 bit); encrypt + all-party decrypt"
+
+
+def bytes_per_share(n=N_PARTIES):
+    """algorithmic bytes per encrypted + decrypted share."""
+    poly = 8 * N_LIMBS * ELL
+    enc = ((K_DIM * K_DIM + n * K_DIM) * poly + (K_DIM + n) * poly + 8 * (2 * K_DIM * ELL + n * ELL + n)) / n
+    dec = K_DIM * poly + poly + 8
+    return enc + dec
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port (the reference itself is Rust + un-vendored fhe-math: not buildable here)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_inputs(P, D, B=None):
+    import c_oracle as CO
+    import pvw_oracle as O
+    A = CO.synth_crs_np(P)
+    if B is None:   # uniform rows: identical arithmetic and memory traffic, plaintexts are not recovered
+        u = CO.stream_np(SEED, O.TAG_B, 0, P.n * P.k * P.L * P.l).reshape(P.n, P.k, P.L, P.l)
+        B = CO._mulhi_np(u, np.broadcast_to(np.array(P.moduli, dtype=np.uint64).reshape(1, 1, P.L, 1), u.shape))
+    sk = CO.synth_small_np(P, O.TAG_SK, P.n, P.k, "cbd")
+    m = CO.synth_messages_np(P, D, "u63")
+    r = CO.synth_small_np(P, O.TAG_R, D, P.k, "cbd")
+    e1 = CO.synth_small_np(P, O.TAG_E1, D, P.k, "uniform", P.error_bound_1)
+    e2 = CO.synth_small_np(P, O.TAG_E2, D, P.n, "uniform", P.error_bound_2)
+    return A, B, sk, m, r, e1, e2
+
+
+def cpu_step(co, A, B, sk, m, r, e1, e2):
+    c1, c2 = co.encrypt(A, B, m, r, e1, e2)
+    return co.decrypt(sk, c1, c2)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import c_oracle as CO
+    import pvw_oracle as O
+    n = args.parties
+    P = O.Params(n, K_DIM, ELL, p128_moduli())
+    co = CO.COracle(P)
+    D = args.cpu_dealers
+    A, B, sk, m, r, e1, e2 = cpu_inputs(P, D)
+    for _ in range(args.warmup):
+        cpu_step(co, A, B, sk, m[:1], r[:1], e1[:1], e2[:1])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(co, A, B, sk, m, r, e1, e2)
+    dt = time.perf_counter() - t0
+    val = args.steps * D * n / dt
+    sample = f"{D} dealers x {n} parties per step (encrypt + all-party decrypt), uniform synthetic B, {co.threads} OpenMP threads"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "dealers_per_step": D, "note": "CPU port of the reference path (oracle/pvw_oracle.c); "
+                       "the Rust crate and its fhe-math dependency cannot be built in this image"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": co.threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def synth_device(torch, dev, gen, shape, kind, bound=None):
+    if kind == "cbd":        # CBD(0.5): {-1, 0, 1}
+        b = torch.randint(0, 4, shape, device=dev, generator=gen, dtype=torch.int64)
+        return (b & 1) - ((b >> 1) & 1)
+    if kind == "uniform":
+        return torch.randint(-bound, bound + 1, shape, device=dev, generator=gen, dtype=torch.int64)
+    if kind == "u63":
+        return torch.randint(0, 2 ** 62, shape, device=dev, generator=gen, dtype=torch.int64)
+    raise ValueError(kind)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import pvw_rs_b200 as pvw
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n, k, l, L = args.parties, K_DIM, ELL, N_LIMBS
+    assert n % world == 0, "parties must divide evenly over the ranks"
+    nrows, row0 = n // world, rank * (n // world)
+    Dg = args.dealers                 # dealers per GPU per step (this rank's c1 slice)
+    D = Dg * world                    # dealers per step
+    moduli = p128_moduli()
+
+    eng = pvw.Engine(n, k, l, moduli, row0=row0, nrows=nrows, device=local)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    # ---- setup (untimed): CRS broadcast over NCCL, genuine public keys generated on the device ----------------
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED & 0x7FFFFFFF)
+    A = torch.empty((k, k, L, l), dtype=torch.int64, device=dev)
+    if rank == 0:
+        for j, q in enumerate(moduli):
+            A[:, :, j, :] = torch.randint(0, q, (k, k, l), device=dev, generator=gen, dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(A, 0)
+    torch.cuda.synchronize()
+    eng.crs_upload(A)
+    gen.manual_seed((SEED >> 8) & 0x7FFFFFFF)       # identical key material on every rank; each keeps its slice
+    sk_all = synth_device(torch, dev, gen, (n, k, l), "cbd")
+    sk = sk_all[row0:row0 + nrows].contiguous()
+    del sk_all
+    gen.manual_seed(1000 + rank)
+    for p0 in range(0, nrows, 512):
+        cnt = min(512, nrows - p0)
+        ke = synth_device(torch, dev, gen, (cnt, k, l), "uniform", 100)
+        eng.keygen_batch(row0 + p0, sk[p0:p0 + cnt].contiguous(), ke)
+    eng.synchronize()
+    eng.ct_reserve(D)
+
+    # ---- the step's synthetic inputs: same dealers on every rank (r, e1), local columns of m / e2 ---------------
+    gen.manual_seed(77)
+    r = synth_device(torch, dev, gen, (D, k, l), "cbd")
+    e1 = synth_device(torch, dev, gen, (D, k, l), "uniform", 100)
+    gen.manual_seed(78 + rank)
+    m = synth_device(torch, dev, gen, (D, nrows), "u63")
+    e2 = synth_device(torch, dev, gen, (D, nrows, l), "uniform", 200)
+    out = torch.empty((nrows, D), dtype=torch.int64, device=dev)
+    parties = np.arange(row0, row0 + nrows, dtype=np.uint32)
+    c1_view = eng.c1_store_tensor(0, D) if world > 1 else None
+
+    def gather_c1():
+        if world > 1:
+            with torch.cuda.stream(ext):
+                dist.all_gather_into_tensor(c1_view, c1_view[rank * Dg:(rank + 1) * Dg])
+
+    def step_device():
+        eng.encrypt_batch(0, m, r, e1, e2, c1_range=(rank * Dg, (rank + 1) * Dg))
+        gather_c1()
+        eng.decrypt_batch(parties, sk, D=D, out=out)
+
+    # host-buffer path (e2e): pinned host inputs, H2D inside the library calls, plaintexts read back to the host
+    pin = lambda t: t.cpu().pin_memory()
+    h_m, h_r, h_e1, h_e2, h_sk = pin(m), pin(r), pin(e1), pin(e2), pin(sk)
+    n_m, n_r, n_e1, n_e2, n_sk = (t.numpy() for t in (h_m, h_r, h_e1, h_e2, h_sk))
+    n_m = n_m.view(np.uint64)
+
+    def step_host():
+        eng.encrypt_batch(0, n_m, n_r, n_e1, n_e2, c1_range=(rank * Dg, (rank + 1) * Dg))
+        gather_c1()
+        return eng.decrypt_batch(parties, n_sk, D=D)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(ext)
+        for _ in range(steps):
+            fn()
+        b.record(ext)
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- correctness guard: the plaintexts of the step are the messages (genuine keys) -------------------------
+    step_device()
+    eng.synchronize()
+    ok = bool((out.t() == m).all().item())
+    res_host = step_host()
+    ok = ok and bool((res_host.view(np.int64).T == n_m.view(np.int64)).all())
+    if not ok:
+        raise SystemExit("bench: decrypted shares differ from the messages -- refusing to report a number")
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3) - 1):
+        step_device()
+    eng.set_option("profile", 2)
+    l0 = eng.launch_count
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total = timed(step_device, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    launches = eng.launch_count - l0
+    prof = eng.profile()
+    eng.set_option("profile", 0)
+    shares_per_step = D * n
+    value = shares_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI calls ------------------------------------------------------------------
+    for _ in range(2):
+        step_host()
+    ms_e2e = timed(step_host, args.steps)
+    e2e_value = shares_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(a.nbytes for a in (n_m, n_r, n_e2, n_sk)) + n_e1[rank * Dg:(rank + 1) * Dg].nbytes + parties.nbytes
+    d2h = nrows * D * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (mac_gemm) ------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    mac_ms, mac_n, mac_bytes = prof["mac_gemm"]
+    achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    kernel_ms = {kname: round(v[0] / args.steps, 4) for kname, v in prof.items()}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "mac_gemm_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "mac_gemm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback", "traffic": traffic,
+                "launches_per_step": mac_n / args.steps, "avg_launch_ms": mac_ms / max(mac_n, 1),
+                "algorithmic_bytes_per_launch": mac_bytes / max(mac_n, 1),
+                "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": round(mac_ms / ms_total, 4),
+                "modmuladds_per_s": (mac_bytes / ((k + 1.0) * 8)) * k / (mac_ms * 1e-3) if mac_ms > 0 else 0.0,
+                "note": "dealer tiling re-uses each B / c1 tile from shared memory for several dealers, so the kernel is bound by the "
+                        "integer pipe (4 IMAD.WIDE per 62-bit multiply-accumulate) and moves fewer DRAM bytes than the algorithmic "
+                        "figure; frac > 1 is therefore possible (DESIGN.md)"}
+
+    # ---- CPU baseline: oracle port on the host cores, bounded sample -------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import c_oracle as CO
+        import pvw_oracle as O
+        P = O.Params(n, k, l, moduli, psi=eng.psi)
+        co = CO.COracle(P)
+        Dc = args.cpu_dealers
+        A_h = eng.crs_download()
+        B_h = eng.pk_download_rows(0, n)
+        r_h, e1_h, e2_h, m_h, sk_h = n_r[:Dc], n_e1[:Dc], n_e2[:Dc], n_m[:Dc], n_sk
+        t0 = time.perf_counter()
+        c1_h, c2_h = co.encrypt(A_h, B_h, m_h, r_h, e1_h, e2_h)
+        dec_h = co.decrypt(sk_h, c1_h, c2_h)
+        dt = time.perf_counter() - t0
+        # the CPU port and the GPU agree on this sample (same keys, same randomness): plaintexts and ciphertext of dealer 0
+        g1, g2 = eng.ct_download(0)
+        same = bool((dec_h == res_host[:, :Dc]).all() and (g1 == c1_h[0]).all() and (g2 == c2_h[0]).all())
+        cpu = {"value": Dc * n / dt, "unit": UNIT, "cores": co.threads, "kind": "port",
+               "sample": f"{Dc} dealers x {n} parties (encrypt + all-party decrypt) of the same workload, {dt:.1f} s; "
+                         f"bit-identical to the GPU result: {same}"}
+        if not same:
+            raise SystemExit("bench: CPU port and GPU disagree on the sample")
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "dealers_per_step": D, "dealers_per_gpu_per_step": Dg, "shares_per_step": shares_per_step,
+                       "parallelism": f"B rows / parties sharded x{world}; c1 dealer slices all-gathered (NCCL)" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (B shard %.0f MB, ciphertext store %.0f MB per step vs 126 MB L2)" % (
+                           nrows * k * L * l * 8 / 1e6, D * (nrows + k) * L * l * 8 / 1e6),
+                       "keys": "genuine (device keygen); every decrypted share checked == message before timing"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "hbm_roof_shares_per_s": peak * 1e9 / bytes_per_share(n) * world}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dealers", type=int, default=256, help="dealers per GPU per step")
+    ap.add_argument("--parties", type=int, default=N_PARTIES)
+    ap.add_argument("--cpu-dealers", type=int, default=16, help="dealers in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "b200" and world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,8 +144,15 @@ int pvw_encode_scalars(pvw_ctx *ctx, uint32_t count, const uint64_t *m /* [count
 int pvw_ctx_synchronize(pvw_ctx *ctx);
 /* the CUDA stream (cudaStream_t) all work of the context is ordered on, for CUDA-event timing by the caller */
 void *pvw_ctx_stream(pvw_ctx *ctx);
-/* tuning / introspection: "gemm_impl" (0 = synchronous tiles, 1 = TMA bulk-copy pipeline), "dealer_tile" ... */
+/* tuning / introspection: "gemm_impl" (0 = synchronous tiles, 1 = TMA bulk-copy pipeline), "decrypt_chunk_shares",
+ * "upload_chunk_bytes", "profile" */
 int pvw_ctx_set_option(pvw_ctx *ctx, const char *name, int64_t value);
+/* per-kernel-kind device timing, measured with CUDA events on the context's stream around every launch while the
+ * option "profile" is 1 (2 = enable and reset, 0 = disable and reset): total milliseconds, launches and algorithmic
+ * bytes accumulated since the last reset.  Synchronises the stream. */
+enum { PVW_KERNEL_NTT = 0, PVW_KERNEL_MAC = 1, PVW_KERNEL_DECODE_RNS = 2, PVW_KERNEL_CRT_LIFT = 3, PVW_KERNEL_DECODE_TAIL = 4,
+       PVW_KERNEL_PERMUTE = 5, PVW_KERNEL_KINDS = 6 };
+int pvw_ctx_profile(pvw_ctx *ctx, int kind, double *ms_total, uint64_t *launches, double *algorithmic_bytes);
 /* number of kernels launched by this context so far */
 uint64_t pvw_ctx_launch_count(const pvw_ctx *ctx);
 const char *pvw_version(void);

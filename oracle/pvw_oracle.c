@@ -48,6 +48,23 @@ typedef struct {
 /* modular arithmetic (fhe-math zq::Modulus semantics: canonical results)                            */
 /* ------------------------------------------------------------------------------------------------ */
 static inline uint64_t mulmod(uint64_t a, uint64_t b, uint64_t q) { return (uint64_t)((u128)a * b % q); }
+/* Barrett form of the same product for a, b < q < 2^62 (fhe-math zq::Modulus::mul = 128-bit product + Barrett
+ * `reduce_u128`): mu = floor(2^128 / q) as (mu_hi, mu_lo); the quotient estimate is short by at most 3. */
+typedef struct { uint64_t q, mu_hi, mu_lo; } bmod;
+static inline bmod bmod_init(uint64_t q) {
+  bmod m; m.q = q;
+  u128 mu = (~(u128)0) / q; /* q odd prime: floor((2^128-1)/q) == floor(2^128/q) */
+  m.mu_hi = (uint64_t)(mu >> 64); m.mu_lo = (uint64_t)mu;
+  return m;
+}
+static inline uint64_t mulmod_b(uint64_t a, uint64_t b, const bmod *m) {
+  u128 x = (u128)a * b;
+  uint64_t h = (uint64_t)(x >> 64), lo = (uint64_t)x;
+  uint64_t qh = h * m->mu_hi + (uint64_t)(((u128)h * m->mu_lo) >> 64) + (uint64_t)(((u128)lo * m->mu_hi) >> 64);
+  uint64_t r = lo - qh * m->q;
+  while (r >= m->q) r -= m->q;
+  return r;
+}
 static inline uint64_t addmod(uint64_t a, uint64_t b, uint64_t q) { uint64_t s = a + b; return s >= q ? s - q : s; }
 static inline uint64_t submod(uint64_t a, uint64_t b, uint64_t q) { return a >= b ? a - b : a + q - b; }
 static uint64_t powmod(uint64_t a, uint64_t e, uint64_t q) {
@@ -81,6 +98,7 @@ static void ntt_tab_init(ntt_tab *t, uint64_t q, uint64_t psi, uint32_t ell) {
   t->ninv = powmod(ell, q - 2, q);
 }
 static void ntt_fwd(uint64_t *a, const ntt_tab *tb, uint64_t q, uint32_t ell) {
+  const bmod bm = bmod_init(q);
   uint32_t t = ell;
   for (uint32_t m = 1; m < ell; m <<= 1) {
     t >>= 1;
@@ -88,7 +106,7 @@ static void ntt_fwd(uint64_t *a, const ntt_tab *tb, uint64_t q, uint32_t ell) {
       uint64_t s = tb->w[m + i];
       uint32_t j1 = 2 * i * t;
       for (uint32_t j = j1; j < j1 + t; j++) {
-        uint64_t u = a[j], v = mulmod(a[j + t], s, q);
+        uint64_t u = a[j], v = mulmod_b(a[j + t], s, &bm);
         a[j] = addmod(u, v, q);
         a[j + t] = submod(u, v, q);
       }
@@ -96,6 +114,7 @@ static void ntt_fwd(uint64_t *a, const ntt_tab *tb, uint64_t q, uint32_t ell) {
   }
 }
 static void ntt_inv(uint64_t *a, const ntt_tab *tb, uint64_t q, uint32_t ell) {
+  const bmod bm = bmod_init(q);
   uint32_t t = 1;
   for (uint32_t m = ell; m > 1; m >>= 1) {
     uint32_t h = m >> 1, j1 = 0;
@@ -104,19 +123,19 @@ static void ntt_inv(uint64_t *a, const ntt_tab *tb, uint64_t q, uint32_t ell) {
       for (uint32_t j = j1; j < j1 + t; j++) {
         uint64_t u = a[j], v = a[j + t];
         a[j] = addmod(u, v, q);
-        a[j + t] = mulmod(submod(u, v, q), s, q);
+        a[j + t] = mulmod_b(submod(u, v, q), s, &bm);
       }
       j1 += 2 * t;
     }
     t <<= 1;
   }
-  for (uint32_t j = 0; j < ell; j++) a[j] = mulmod(a[j], tb->ninv, q);
+  for (uint32_t j = 0; j < ell; j++) a[j] = mulmod_b(a[j], tb->ninv, &bm);
 }
 
-typedef struct { const pvwo_params *p; ntt_tab tab[PVWO_MAX_L]; } octx;
+typedef struct { const pvwo_params *p; ntt_tab tab[PVWO_MAX_L]; bmod bm[PVWO_MAX_L]; } octx;
 static void octx_init(octx *c, const pvwo_params *p) {
   c->p = p;
-  for (uint32_t j = 0; j < p->L; j++) ntt_tab_init(&c->tab[j], p->moduli[j], p->psi[j], p->ell);
+  for (uint32_t j = 0; j < p->L; j++) { ntt_tab_init(&c->tab[j], p->moduli[j], p->psi[j], p->ell); c->bm[j] = bmod_init(p->moduli[j]); }
 }
 
 /* small signed coefficients (ell) -> RNS -> NTT, out u64[L][ell]
@@ -136,18 +155,19 @@ static void encode_scalar(const octx *c, uint64_t m, uint64_t *out) {
   int64_t ms = (int64_t)m; /* `scalars[p] as i64`, encryption.rs:195 */
   for (uint32_t j = 0; j < p->L; j++) {
     uint64_t q = p->moduli[j], *row = out + (size_t)j * p->ell, mr = reduce_i64(ms, q);
-    for (uint32_t t = 0; t < p->ell; t++) row[t] = mulmod(mr, p->gadget_rns[(size_t)j * p->ell + t], q);
+    for (uint32_t t = 0; t < p->ell; t++) row[t] = mulmod_b(mr, p->gadget_rns[(size_t)j * p->ell + t], &c->bm[j]);
     ntt_fwd(row, &c->tab[j], q, p->ell);
   }
 }
 
 /* acc[L][ell] += a[L][ell] (.) b[L][ell]  -- Poly Mul then Poly Add, slot-wise (crs.rs:197-198) */
-static inline void poly_mac(const pvwo_params *p, uint64_t *acc, const uint64_t *a, const uint64_t *b) {
+static inline void poly_mac(const octx *c, uint64_t *acc, const uint64_t *a, const uint64_t *b) {
+  const pvwo_params *p = c->p;
   for (uint32_t j = 0; j < p->L; j++) {
-    uint64_t q = p->moduli[j];
+    const bmod *bm = &c->bm[j];
     for (uint32_t t = 0; t < p->ell; t++) {
       size_t o = (size_t)j * p->ell + t;
-      acc[o] = addmod(acc[o], mulmod(a[o], b[o], q), q);
+      acc[o] = addmod(acc[o], mulmod_b(a[o], b[o], bm), bm->q);
     }
   }
 }
@@ -398,7 +418,7 @@ void pvwo_keygen(const pvwo_params *p, uint64_t nparties, const uint64_t *A, con
       for (uint32_t ci = 0; ci < k; ci++) {
         uint64_t *b = out + ((size_t)pi * k + ci) * poly;
         memset(b, 0, poly * 8);
-        for (uint32_t j = 0; j < k; j++) poly_mac(p, b, shat + (size_t)j * poly, A + ((size_t)j * k + ci) * poly);
+        for (uint32_t j = 0; j < k; j++) poly_mac(&c, b, shat + (size_t)j * poly, A + ((size_t)j * k + ci) * poly);
         small_to_ntt(&c, e + ((size_t)pi * k + ci) * p->ell, tmp);
         poly_add(p, b, tmp);
       }
@@ -426,7 +446,7 @@ void pvwo_encrypt(const pvwo_params *p, uint64_t D, uint64_t nrows, const uint64
         for (int64_t i = 0; i < (int64_t)k; i++) {                              /* crs.rs:187-199 */
           uint64_t *o = c1 + ((size_t)d * k + i) * poly;
           memset(o, 0, poly * 8);
-          for (uint32_t j = 0; j < k; j++) poly_mac(p, o, A + ((size_t)i * k + j) * poly, rhat + ((size_t)d * k + j) * poly);
+          for (uint32_t j = 0; j < k; j++) poly_mac(&c, o, A + ((size_t)i * k + j) * poly, rhat + ((size_t)d * k + j) * poly);
           small_to_ntt(&c, e1 + ((size_t)d * k + i) * p->ell, tmp);             /* :161-173 */
           poly_add(p, o, tmp);
         }
@@ -442,7 +462,7 @@ void pvwo_encrypt(const pvwo_params *p, uint64_t D, uint64_t nrows, const uint64
         for (int64_t pi = 0; pi < (int64_t)nrows; pi++) {                       /* :177-200 */
           uint64_t *o = c2 + ((size_t)d * nrows + pi) * poly;
           memset(o, 0, poly * 8);
-          for (uint32_t j = 0; j < k; j++) poly_mac(p, o, B + ((size_t)pi * k + j) * poly, rhat + ((size_t)d * k + j) * poly);
+          for (uint32_t j = 0; j < k; j++) poly_mac(&c, o, B + ((size_t)pi * k + j) * poly, rhat + ((size_t)d * k + j) * poly);
           encode_scalar(&c, m[(size_t)d * nrows + pi], tmp); poly_add(p, o, tmp);
           small_to_ntt(&c, e2 + ((size_t)d * nrows + pi) * p->ell, tmp); poly_add(p, o, tmp);
         }
@@ -456,7 +476,7 @@ void pvwo_encrypt(const pvwo_params *p, uint64_t D, uint64_t nrows, const uint64
 static void noisy_message(const octx *c, const uint64_t *shat, const uint64_t *c1, const uint64_t *c2p, uint64_t *z) {
   const pvwo_params *p = c->p; size_t poly = (size_t)p->L * p->ell;
   memset(z, 0, poly * 8);
-  for (uint32_t j = 0; j < p->k; j++) poly_mac(p, z, shat + (size_t)j * poly, c1 + (size_t)j * poly);
+  for (uint32_t j = 0; j < p->k; j++) poly_mac(c, z, shat + (size_t)j * poly, c1 + (size_t)j * poly);
   poly_sub(p, z, c2p);
 }
 

@@ -55,9 +55,12 @@ SIGNATURES = {
     "pvw_ctx_synchronize": (C.c_int, [_vp]),
     "pvw_ctx_stream": (_vp, [_vp]),
     "pvw_ctx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
+    "pvw_ctx_profile": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_u64), C.POINTER(C.c_double)]),
     "pvw_ctx_launch_count": (_u64, [_vp]),
     "pvw_version": (C.c_char_p, []),
 }
+
+KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute"]
 
 _lib = None
 

@@ -75,6 +75,14 @@ struct pvw_ctx {
   DevBuf stage, rhat, in_small, in_small2, in_m, shat, z, y, X, outd, idxd, idxp;
   std::string err;
   uint64_t launches = 0;
+  // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg): events bracket each launch on `stream`
+  bool profile = false;
+  struct ProfRec { int kind; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[PVW_KERNEL_KINDS] = {0};
+  uint64_t prof_n[PVW_KERNEL_KINDS] = {0};
+  double prof_bytes[PVW_KERNEL_KINDS] = {0};
   int gemm_impl = 1;
   int64_t decrypt_chunk_shares = 1 << 19;
   int64_t upload_chunk_bytes = 256ll << 20;
@@ -132,6 +140,38 @@ void check_launch(pvw_ctx* c, size_t n = 1) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+cudaEvent_t prof_event(pvw_ctx* c) {
+  if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+void prof_drain(pvw_ctx* c) {
+  if (c->prof_pending.empty()) return;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_pending) {
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    c->prof_ms[r.kind] += ms;
+    c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+  }
+  c->prof_pending.clear();
+}
+// run one kernel launch `f`, counting it and (when profiling) bracketing it with events; `bytes` = algorithmic bytes
+template <class F>
+void launch(pvw_ctx* c, int kind, double bytes, F&& f) {
+  if (!c->profile) { f(); check_launch(c); return; }
+  cudaEvent_t a = prof_event(c), b = prof_event(c);
+  CUDA_CHECK(cudaEventRecord(a, c->stream));
+  f();
+  check_launch(c);
+  CUDA_CHECK(cudaEventRecord(b, c->stream));
+  c->prof_pending.push_back({kind, a, b});
+  c->prof_n[kind]++;
+  c->prof_bytes[kind] += bytes;
+  if (c->prof_pending.size() >= 4096) prof_drain(c);
+}
+
 // copy `bytes` from a caller pointer (host or device, per flags) into a device scratch buffer
 const void* stage_in(pvw_ctx* c, DevBuf& buf, const void* src, size_t bytes, uint32_t flags) {
   if (flags & PVW_IO_DEVICE) return src;
@@ -143,14 +183,12 @@ const void* stage_in(pvw_ctx* c, DevBuf& buf, const void* src, size_t bytes, uin
 // host-layout polynomials [count][L][ell]  <->  limb-major [L][count][ell] slice inside a bigger array
 void to_limb_major(pvw_ctx* c, const u64* in_host_layout, uint64_t count, u64* out, size_t out_limb_stride) {
   const uint32_t L = c->hp.L, ell = c->hp.ell;
-  launch_permute(in_host_layout, out, 1, count, L, ell, 0, (size_t)L * ell, ell, 0, ell, out_limb_stride, c->stream);
-  check_launch(c);
+  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(in_host_layout, out, 1, count, L, ell, 0, (size_t)L * ell, ell, 0, ell, out_limb_stride, c->stream); });
 }
 void from_limb_major(pvw_ctx* c, const u64* in, size_t in_limb_stride, uint64_t count, u64* out_host_layout) {
   const uint32_t L = c->hp.L, ell = c->hp.ell;
   // x = limb is the fastest thread axis here so that the host-layout side (the output) is written contiguously
-  launch_permute(in, out_host_layout, 1, L, count, ell, 0, in_limb_stride, ell, 0, ell, (size_t)L * ell, c->stream);
-  check_launch(c);
+  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(in, out_host_layout, 1, L, count, ell, 0, in_limb_stride, ell, 0, ell, (size_t)L * ell, c->stream); });
 }
 
 // upload `count` polynomials given in host layout (host or device memory) into limb-major dst (+ offset handled by caller)
@@ -181,8 +219,9 @@ void download_polys(pvw_ctx* c, const u64* src, size_t src_limb_stride, uint64_t
 void require(bool cond, int code, const std::string& msg) { if (!cond) throw PvwException(code, msg); }
 
 void gemm(pvw_ctx* c, const GemmArgs& a) {
-  launch_mac_gemm(a, c->gemm_impl, c->stream);
-  check_launch(c, mac_gemm_launches(a));
+  // algorithmic bytes: per (dealer, row) one k-polynomial operand row read + one polynomial written
+  const double bytes = (double)a.D * a.rows * (a.k + 1.0) * a.L * a.ell * 8.0;
+  launch(c, PVW_KERNEL_MAC, bytes, [&] { launch_mac_gemm(a, c->gemm_impl, c->stream); });
 }
 
 void ensure_At(pvw_ctx* c) {
@@ -191,8 +230,7 @@ void ensure_At(pvw_ctx* c) {
   const size_t kk = (size_t)k * k * ell;
   c->At.ensure((size_t)L * kk * 8);
   // At[limb][cidx][j] = A[limb][j][cidx]; x = j walks the output's contiguous axis
-  launch_permute(c->A.as<u64>(), c->At.as<u64>(), L, k, k, ell, kk, (size_t)k * ell, ell, kk, ell, (size_t)k * ell, c->stream);
-  check_launch(c);
+  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(c->A.as<u64>(), c->At.as<u64>(), L, k, k, ell, kk, (size_t)k * ell, ell, kk, ell, (size_t)k * ell, c->stream); });
   c->At_valid = true;
 }
 
@@ -258,6 +296,8 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
                     &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp})
     b->release();
@@ -360,13 +400,11 @@ int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk
     const long long* d_e = (const long long*)stage_in(c, c->in_small2, e, small, flags);
     // s_hat[p][limb][j][ell]
     c->rhat.ensure((size_t)count * L * k * ell * 8);
-    launch_ntt_small(c->T, d_sk, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, c->stream); });
     // B rows <- NTT(e): item idx = p*k + cidx lands at B[limb][row+p][cidx]
     u64* Brow = c->B.as<u64>() + (size_t)(row - c->row0) * k * ell;
-    launch_ntt_small(c->T, d_e, nullptr, (uint64_t)count * k, (uint32_t)std::min<uint64_t>((uint64_t)count * k, 0xFFFFFFFFu), Brow, 0,
-                     (size_t)c->nrows * k * ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e, nullptr, (uint64_t)count * k, (uint32_t)std::min<uint64_t>((uint64_t)count * k, 0xFFFFFFFFu), Brow, 0,
+                     (size_t)c->nrows * k * ell, c->stream); });
     GemmArgs g{};
     g.M = c->At.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
     g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell;
@@ -390,8 +428,7 @@ int pvw_crs_multiply_by_randomness(pvw_ctx* c, uint32_t D, const uint64_t* r_hat
     c->z.ensure((size_t)D * per * 8);
     CUDA_CHECK(cudaMemcpyAsync(c->stage.p, r_hat, (size_t)D * per * 8, cudaMemcpyHostToDevice, c->stream));
     // [D][k][L][ell] -> [D][L][k][ell]
-    launch_permute(c->stage.as<u64>(), c->rhat.as<u64>(), D, k, L, ell, per, (size_t)L * ell, ell, per, ell, (size_t)k * ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(c->stage.as<u64>(), c->rhat.as<u64>(), D, k, L, ell, per, (size_t)L * ell, ell, per, ell, (size_t)k * ell, c->stream); });
     CUDA_CHECK(cudaMemsetAsync(c->z.p, 0, (size_t)D * per * 8, c->stream));
     GemmArgs g{};
     g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
@@ -399,8 +436,7 @@ int pvw_crs_multiply_by_randomness(pvw_ctx* c, uint32_t D, const uint64_t* r_hat
     g.O = c->z.as<u64>(); g.O_ls = (size_t)k * ell; g.O_ds = per;
     g.rows = k; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
     gemm(c, g);
-    launch_permute(c->z.as<u64>(), c->stage.as<u64>(), D, L, k, ell, per, (size_t)k * ell, ell, per, ell, (size_t)L * ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(c->z.as<u64>(), c->stage.as<u64>(), D, L, k, ell, per, (size_t)k * ell, ell, per, ell, (size_t)L * ell, c->stream); });
     CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)D * per * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -442,8 +478,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     const long long* d_r = (const long long*)stage_in(c, c->in_small, r, (size_t)D * k * ell * 8, flags);
     // r_hat[d][limb][j][ell]   (encryption.rs:147-154)
     c->rhat.ensure((size_t)D * w1 * 8);
-    launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream); });
     u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
     if (c1_hi > c1_lo) {
@@ -451,8 +486,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       const int64_t* e1p = e1 + (size_t)c1_lo * k * ell;
       const long long* d_e1 = (const long long*)stage_in(c, c->in_small2, e1p, (size_t)Dc * k * ell * 8, flags);
       // c1 <- NTT(e1)   (encryption.rs:161-167), then c1 += A r_hat   (crs.rs:187-199, encryption.rs:171-173)
-      launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)Dc * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream);
-      check_launch(c);
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)Dc * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream); });
       GemmArgs g{};
       g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
       g.V = c->rhat.as<u64>() + (size_t)c1_lo * w1; g.V_ls = (size_t)k * ell; g.V_ds = w1;
@@ -464,8 +498,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       // c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
       const long long* d_e2 = (const long long*)stage_in(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags);
       const u64* d_m = (const u64*)stage_in(c, c->in_m, m, (size_t)D * nrows * 8, flags);
-      launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream);
-      check_launch(c);
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream); });
       GemmArgs g{};
       g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
       g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
@@ -507,12 +540,9 @@ static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds,
   const uint64_t S = (uint64_t)Pc * D;
   c->y.ensure(decode_scratch_words_y(c->T, S) * 8);
   c->X.ensure(decode_scratch_words_X(c->T, S) * 8);
-  launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream);
-  check_launch(c);
-  launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream);
-  check_launch(c);
-  launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream);
-  check_launch(c);
+  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream); });
+  launch(c, PVW_KERNEL_CRT_LIFT, 0.0, [&] { launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream); });
+  launch(c, PVW_KERNEL_DECODE_TAIL, 0.0, [&] { launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream); });
 }
 
 int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint32_t P, const uint32_t* party_idx, const int64_t* sk,
@@ -553,8 +583,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     for (uint32_t p0 = 0; p0 < P; p0 += Pc_max) {
       const uint32_t Pc = std::min(Pc_max, P - p0);
       // s_hat[limb][p][j][ell]   (SecretKey::get_polynomial, secret_key.rs:98-112 -- once per party, not per ciphertext)
-      launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream);
-      check_launch(c);
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream); });
       // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274)
       GemmArgs g{};
       g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;
@@ -595,8 +624,7 @@ int pvw_ntt_forward_small(pvw_ctx* c, uint32_t count, const int64_t* coeffs, uin
     c->in_small.ensure((size_t)count * c->hp.ell * 8);
     c->stage.ensure((size_t)count * poly * 8);
     CUDA_CHECK(cudaMemcpyAsync(c->in_small.p, coeffs, (size_t)count * c->hp.ell * 8, cudaMemcpyHostToDevice, c->stream));
-    launch_ntt_small(c->T, c->in_small.as<long long>(), nullptr, count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, c->in_small.as<long long>(), nullptr, count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream); });
     CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -612,8 +640,7 @@ int pvw_encode_scalars(pvw_ctx* c, uint32_t count, const uint64_t* m, uint64_t* 
     c->stage.ensure((size_t)count * poly * 8);
     CUDA_CHECK(cudaMemsetAsync(c->in_small.p, 0, (size_t)count * c->hp.ell * 8, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->in_m.p, m, (size_t)count * 8, cudaMemcpyHostToDevice, c->stream));
-    launch_ntt_small(c->T, c->in_small.as<long long>(), c->in_m.as<u64>(), count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream);
-    check_launch(c);
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, c->in_small.as<long long>(), c->in_m.as<u64>(), count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream); });
     CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -631,7 +658,21 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     if (n == "gemm_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0 or 1"); c->gemm_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }
+    else if (n == "profile") {
+      prof_drain(c);
+      c->profile = value != 0;
+      if (value == 2 || value == 0) for (int i = 0; i < PVW_KERNEL_KINDS; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; c->prof_bytes[i] = 0; }
+    }
     else throw PvwException(PVW_ERR_INVALID_PARAMETERS, "unknown option " + n);
+  });
+}
+int pvw_ctx_profile(pvw_ctx* c, int kind, double* ms_total, uint64_t* launches, double* algorithmic_bytes) {
+  return guarded(c, [&] {
+    require(kind >= 0 && kind < PVW_KERNEL_KINDS, PVW_ERR_INVALID_PARAMETERS, "unknown kernel kind");
+    prof_drain(c);
+    if (ms_total) *ms_total = c->prof_ms[kind];
+    if (launches) *launches = c->prof_n[kind];
+    if (algorithmic_bytes) *algorithmic_bytes = c->prof_bytes[kind];
   });
 }
 uint64_t pvw_ctx_launch_count(const pvw_ctx* c) { return c ? c->launches : 0; }

@@ -55,6 +55,8 @@ class Engine:
         mods = [int(q) for q in moduli]
         if any(q < 0 or q >= 2 ** 64 for q in mods):
             raise PvwError("InvalidParameters", "Context creation failed: modulus does not fit 64 bits")
+        if psi is not None and len(psi) != len(mods):
+            raise PvwError("InvalidParameters", f"{len(psi)} roots given for {len(mods)} moduli")
         self._mods = (C.c_uint64 * max(1, len(mods)))(*mods)
         self._psi = (C.c_uint64 * len(mods))(*[int(p) for p in psi]) if psi is not None else None
         desc = _ffi.PvwParamsDesc(int(n), int(k), int(l), len(mods), self._mods if mods else None, self._psi,
@@ -101,6 +103,15 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.pvw_ctx_set_option(self.h, name.encode(), int(value)))
+
+    def profile(self) -> dict:
+        """{kernel kind: (ms_total, launches, algorithmic_bytes)} since profiling was last reset (option "profile")"""
+        out = {}
+        for i, name in enumerate(_ffi.KERNEL_KINDS):
+            ms, n, b = C.c_double(), C.c_uint64(), C.c_double()
+            self._check(self.lib.pvw_ctx_profile(self.h, i, C.byref(ms), C.byref(n), C.byref(b)))
+            out[name] = (ms.value, n.value, b.value)
+        return out
 
     # -- parameters ------------------------------------------------------------------------------
     def _bigint(self, which: int) -> int:

@@ -204,8 +204,8 @@ def test_ciphertext_upload_roundtrip_and_row_sharding(pkg):
 def test_error_paths_of_the_boundary(pkg):
     P = params("EX")
     S = System(P, 2, "example")
-    for bad in (dict(n=0), dict(k=0), dict(l=4), dict(l=12), dict(moduli=[0xFFFFEE001, 0xFFFFEE001]), dict(moduli=[15]),
-                dict(error_bound_1=0)):
+    for bad in (dict(n=0), dict(k=0), dict(l=4), dict(l=12), dict(moduli=[0xFFFFEE001, 0xFFFFEE001], psi=None),
+                dict(moduli=[15], psi=None), dict(moduli=[], psi=None), dict(psi=[1, 1]), dict(psi=[3]), dict(error_bound_1=0)):
         with pytest.raises(pkg.PvwError) as ei:
             pkg.Engine(**engine_kwargs(P, **bad))
         assert ei.value.variant == "InvalidParameters"

@@ -10,12 +10,14 @@
 //
 // B200 mapping.  The reference calls this once per (dealer, party); batched over D dealers it is a modular GEMM per
 // slot, so each M row tile fetched from HBM/L2 is reused for DT dealers and each V tile for RT rows.  The bound then
-// is the integer pipe, not HBM: a 62x62-bit product is 4 IMAD.WIDE.U32; products are accumulated unreduced in 160
-// bits (modarith.cuh) and reduced once per k terms.  No tensor cores: exact modular integer arithmetic.
+// is the integer pipe, not HBM: a 62x62-bit product is 3 IMAD.WIDE.U32 (Karatsuba on 31-bit halves); the three partial
+// sums are accumulated unreduced in 96 bits each (modarith.cuh, AccK) and reduced once per k terms.  Measured on
+// B200 (tools/int_peaks.cu): an IMAD.WIDE with a 64-bit addend issues every 4 cycles per SM sub-partition, so the
+// ceiling is 12 cycles per warp-wide multiply-accumulate = 2.8e12 MAC/s.  No tensor cores: exact modular arithmetic.
 //   * thread = one NTT slot c of a TR x TD (row, dealer) sub-tile -> TR*TD independent carry chains (ILP);
 //     a warp's lanes sweep the ell slots of (32/ell) sub-tiles, so shared-memory reads are conflict-free 8-byte
 //     accesses, broadcast across the sub-tiles that share a row.
-//   * operand rows are contiguous in the limb-major layout (kc*ell*8 bytes): a producer warp streams them with
+//   * operand rows are contiguous in the limb-major layout (kc*ell*8 bytes): the compute warps stream them with
 //     cp.async.bulk (TMA, SASS UBLKCP) into a 4-stage shared-memory ring guarded by mbarriers (impl 1);
 //     impl 0 is the same tile with synchronous loads (bring-up / cross-check path).
 //   * D == 1 (a single `encrypt` call) degenerates to the HBM-bound matrix-vector product with DT = 1.
@@ -68,7 +70,7 @@ template <int ELL, int TR, int TD, int GD, int KC>
 struct Worker {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
   int c, gr, gd;
-  Acc160 acc[TR][TD];
+  AccK acc[TR][TD];
   __device__ __forceinline__ void init(int tid) {
     const int lane = tid & 31, w = tid >> 5;
     c = lane % ELL;
@@ -78,25 +80,52 @@ struct Worker {
 #pragma unroll
     for (int t = 0; t < TR; t++)
 #pragma unroll
-      for (int u = 0; u < TD; u++) acc_zero(acc[t][u]);
+      for (int u = 0; u < TD; u++) acck_zero(acc[t][u]);
+  }
+  // NJ consecutive polynomials starting at jj0: the TD dealer operands are split once and reused for the TR rows
+  template <int NJ>
+  __device__ __forceinline__ void block(const unsigned char* ms, const unsigned char* vs, int jj0) {
+    u32 b0[TD][NJ], b1[TD][NJ];  // 31-bit halves; the Karatsuba sum is formed at the use (alu pipe has slack, registers do not)
+#pragma unroll
+    for (int u = 0; u < TD; u++)
+#pragma unroll
+      for (int i = 0; i < NJ; i++) {
+        const u64 x = *reinterpret_cast<const u64*>(vs + u * C::ROWB + (jj0 + i) * ELL * 8);
+        b0[u][i] = (u32)x & 0x7fffffffu;
+        b1[u][i] = (u32)(x >> 31);
+      }
+#pragma unroll
+    for (int t = 0; t < TR; t++) {
+      SplitOp a[NJ];
+#pragma unroll
+      for (int i = 0; i < NJ; i++) a[i] = split_op(*reinterpret_cast<const u64*>(ms + t * C::ROWB + (jj0 + i) * ELL * 8));
+#pragma unroll
+      for (int u = 0; u < TD; u++)
+#pragma unroll
+        for (int i = 0; i < NJ; i++) {
+          SplitOp b;
+          b.x0 = b0[u][i]; b.x1 = b1[u][i]; b.xs = b0[u][i] + b1[u][i];
+          acck_mac(acc[t][u], a[i], b);
+        }
+    }
   }
   // one staged chunk: kc polynomials of every row / dealer of the tile
   template <bool FULL>
   __device__ __forceinline__ void chunk(const unsigned char* stage, int kc) {
     const unsigned char* ms = stage + (size_t)(gr * TR) * C::ROWB + c * 8;
     const unsigned char* vs = stage + (size_t)(C::RT + gd * TD) * C::ROWB + c * 8;
+    constexpr int NJ = KC % 4 == 0 ? 4 : (KC % 2 == 0 ? 2 : 1);
+    if (FULL) {
+      // straight-line blocks of NJ polynomials; the compiler barrier keeps ptxas from hoisting the next block's
+      // shared-memory loads above this block's arithmetic (which costs registers and then spills)
 #pragma unroll
-    for (int jj = 0; jj < KC; jj++) {
-      if (!FULL && jj >= kc) break;
-      u64 a[TR], b[TD];
-#pragma unroll
-      for (int t = 0; t < TR; t++) a[t] = *reinterpret_cast<const u64*>(ms + t * C::ROWB + jj * ELL * 8);
-#pragma unroll
-      for (int u = 0; u < TD; u++) b[u] = *reinterpret_cast<const u64*>(vs + u * C::ROWB + jj * ELL * 8);
-#pragma unroll
-      for (int t = 0; t < TR; t++)
-#pragma unroll
-        for (int u = 0; u < TD; u++) acc_mac(acc[t][u], a[t], b[u]);
+      for (int jj = 0; jj < KC; jj += NJ) {
+        block<NJ>(ms, vs, jj);
+        asm volatile("" ::: "memory");
+      }
+    } else {
+#pragma unroll 1
+      for (int jj = 0; jj < kc; jj++) block<1>(ms, vs, jj);
     }
   }
   __device__ __forceinline__ void epilogue(const GemmArgs& g, uint32_t limb, uint32_t r0, uint32_t d0) {
@@ -110,7 +139,7 @@ struct Worker {
       for (int t = 0; t < TR; t++) {
         const uint32_t row = r0 + gr * TR + t;
         if (row >= g.rows) continue;
-        u64 v = acc_reduce(acc[t][u], lc);
+        u64 v = acck_reduce(acc[t][u], lc);
         u64* o = g.O + (size_t)d * g.O_ds + (size_t)limb * g.O_ls + (size_t)row * ELL + c;
         if (g.mode == 0) {
           v = addmod(v, *o, lc.q);
@@ -160,62 +189,60 @@ __global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_sync_kernel(const
   wk.epilogue(g, limb, r0, d0);
 }
 
-// ---- impl 1: TMA bulk-copy producer warp + mbarrier ring ---------------------------------------------------------
+// ---- impl 1: TMA bulk copies + mbarrier ring, no dedicated producer warp ---------------------------------------------
+// Nine warps would cap the kernel at 168 registers (three warps on one sub-partition share 16 K registers), so the
+// eight compute warps feed themselves: warp w owns rows {w, w+8, ...} of the staged tile; before it starts chunk i it
+// refills the stage that chunk i-1 used (everybody has left it: `empty` barrier) with chunk i-1+NS.
 template <int ELL, int TR, int TD, int GD, int KC>
-__global__ void __launch_bounds__(kComputeThreads + 32, 1) mac_gemm_tma_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_tma_kernel(const GemmArgs g) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
+  constexpr int NW = kComputeThreads / 32;
+  constexpr int ROWS = C::RT + C::DT;
+  constexpr int RPW = (ROWS + NW - 1) / NW;  // staged rows per warp
+  static_assert(RPW <= 32, "one lane per staged row");
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bars[2 * NS];  // full[NS], empty[NS]
   const uint32_t limb = blockIdx.z, r0 = blockIdx.x * C::RT, d0 = blockIdx.y * C::DT;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar0 = smem_u32(bars);
   if (tid == 0) {
     for (int s = 0; s < NS; s++) {
-      mbar_init(bar0 + 8 * s, 1);                            // full: one arrive.expect_tx by the producer
-      mbar_init(bar0 + 8 * (NS + s), kComputeThreads / 32);  // empty: one arrive per consumer warp
+      mbar_init(bar0 + 8 * s, NW);         // full: one arrive.expect_tx per warp (its rows' bytes)
+      mbar_init(bar0 + 8 * (NS + s), NW);  // empty: one arrive per warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const uint32_t nchunks = (g.k + KC - 1) / KC;
-  if (tid >= kComputeThreads) {
-    // ===== producer warp: one 1D bulk copy per staged row =====
-    const int lane = tid & 31;
-    const u64* src[(C::RT + C::DT + 31) / 32];
-#pragma unroll
-    for (int i = 0; i < (C::RT + C::DT + 31) / 32; i++) {
-      const int rr = lane + 32 * i;
-      src[i] = rr < C::RT + C::DT ? row_src<C>(g, limb, r0, d0, rr, ELL) : nullptr;
-    }
-    for (uint32_t it = 0; it < nchunks; it++) {
-      const int s = it % NS;
-      const uint32_t n = it / NS;
-      mbar_wait(bar0 + 8 * (NS + s), (n & 1) ^ 1);  // consumers released the previous use of this stage
-      const uint32_t kc = min((uint32_t)KC, g.k - it * KC);
-      const uint32_t row_bytes = kc * ELL * 8;
-      if (lane == 0) mbar_expect_tx(bar0 + 8 * s, (C::RT + C::DT) * row_bytes);
-      __syncwarp();
-      const uint32_t dst0 = smem_u32(smem) + s * C::STAGE;
-#pragma unroll
-      for (int i = 0; i < (C::RT + C::DT + 31) / 32; i++) {
-        const int rr = lane + 32 * i;
-        if (rr < C::RT + C::DT) bulk_g2s(dst0 + rr * C::ROWB, src[i] + (size_t)it * KC * ELL, row_bytes, bar0 + 8 * s);
-      }
-    }
-    return;
-  }
-  // ===== consumer warps =====
+  // this lane's staged row (rows first, then dealers)
+  const int my_row = warp + NW * lane;
+  const bool issuer = lane < RPW && my_row < ROWS;
+  const int my_nrows = (ROWS - warp + NW - 1) / NW;  // rows owned by this warp
+  const u64* my_src = issuer ? row_src<C>(g, limb, r0, d0, my_row, ELL) : nullptr;
+  auto refill = [&](uint32_t chunk) {
+    const int s = chunk % NS;
+    const uint32_t kc = min((uint32_t)KC, g.k - chunk * KC);
+    const uint32_t row_bytes = kc * ELL * 8;
+    if (lane == 0) mbar_expect_tx(bar0 + 8 * s, my_nrows * row_bytes);
+    __syncwarp();
+    if (issuer) bulk_g2s(smem_u32(smem) + s * C::STAGE + my_row * C::ROWB, my_src + (size_t)chunk * KC * ELL, row_bytes, bar0 + 8 * s);
+  };
+  for (uint32_t ch = 0; ch < nchunks && ch < (uint32_t)NS; ch++) refill(ch);
   Worker<ELL, TR, TD, GD, KC> wk;
   wk.init(tid);
   for (uint32_t it = 0; it < nchunks; it++) {
+    if (it >= 1 && it - 1 + NS < nchunks) {
+      const int sp = (it - 1) % NS;
+      mbar_wait(bar0 + 8 * (NS + sp), ((it - 1) / NS) & 1);  // every warp has finished chunk it-1
+      refill(it - 1 + NS);
+    }
     const int s = it % NS;
-    const uint32_t n = it / NS;
-    mbar_wait(bar0 + 8 * s, n & 1);
+    mbar_wait(bar0 + 8 * s, (it / NS) & 1);
     const int kc = min((uint32_t)KC, g.k - it * KC);
     const unsigned char* stage = smem + (size_t)s * C::STAGE;
     if (kc == KC) wk.template chunk<true>(stage, kc); else wk.template chunk<false>(stage, kc);
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(bar0 + 8 * (NS + s));
+    if (lane == 0) mbar_arrive(bar0 + 8 * (NS + s));
   }
   wk.epilogue(g, limb, r0, d0);
 }
@@ -233,7 +260,7 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
     auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC>;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * C::STAGE); attr = true; }
-    kern<<<grid, kComputeThreads + 32, NS * C::STAGE, st>>>(a);
+    kern<<<grid, kComputeThreads, NS * C::STAGE, st>>>(a);
   }
 }
 

@@ -111,4 +111,134 @@ PVW_DEV u64 acc_reduce(const Acc160& c, const LimbConst& lc) {
   return addmod(t, u, lc.q);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Three-multiply lazy accumulator (Karatsuba on 31-bit halves).  x = x1*2^31 + x0 with x0, x1 < 2^31 (x < 2^62) and
+// xs = x0 + x1 < 2^32, so all three partial products are single 32x32->64 IMAD.WIDE.U32:
+//     a*b = H*2^62 + (K - L - H)*2^31 + L,   L = a0*b0,  H = a1*b1,  K = as*bs.
+// L, H and K are summed unreduced over the whole inner dimension in 96 bits each (k < 2^32 terms); the subtraction,
+// the recombination and the single modular reduction happen once per output.  3 IMAD.WIDE.U32 (fma pipe) + 3 IADD3.X
+// (alu pipe) per multiply-accumulate instead of 4 + 3.
+// ---------------------------------------------------------------------------------------------------------------
+struct SplitOp {
+  u32 x0, x1, xs;
+};
+PVW_DEV SplitOp split_op(u64 x) {
+  SplitOp s;
+  s.x0 = (u32)x & 0x7fffffffu;
+  s.x1 = (u32)(x >> 31);
+  s.xs = s.x0 + s.x1;
+  return s;
+}
+struct AccK {
+  u32 l0, l1, l2, h0, h1, h2, k0, k1, k2;
+};
+PVW_DEV void acck_zero(AccK& c) { c.l0 = c.l1 = c.l2 = c.h0 = c.h1 = c.h2 = c.k0 = c.k1 = c.k2 = 0; }
+PVW_DEV void acck_mac(AccK& c, const SplitOp& a, const SplitOp& b) {
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      : "+r"(c.l0), "+r"(c.l1), "+r"(c.l2)
+      : "r"(a.x0), "r"(b.x0));
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      : "+r"(c.h0), "+r"(c.h1), "+r"(c.h2)
+      : "r"(a.x1), "r"(b.x1));
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      : "+r"(c.k0), "+r"(c.k1), "+r"(c.k2)
+      : "r"(a.xs), "r"(b.xs));
+}
+// canonical value of the accumulator mod q
+PVW_DEV u64 acck_reduce(const AccK& c, const LimbConst& lc) {
+  const u64 L = reduce128(reduce64((u64)c.l2, lc), ((u64)c.l1 << 32) | c.l0, lc);
+  const u64 H = reduce128(reduce64((u64)c.h2, lc), ((u64)c.h1 << 32) | c.h0, lc);
+  const u64 K = reduce128(reduce64((u64)c.k2, lc), ((u64)c.k1 << 32) | c.k0, lc);
+  const u64 mid = submod(submod(K, L, lc.q), H, lc.q);
+  const u64 p31 = reduce64(1ull << 31, lc), p62 = reduce64(1ull << 62, lc);
+  return addmod(addmod(mulmod(H, p62, lc), mulmod(mid, p31, lc), lc.q), L, lc.q);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Carry-free lazy accumulator (the production path of mac.cu).  Measured on B200 (tools/int_peaks.cu): a plain
+// IMAD.WIDE.U32 issues at 64 lanes/clk/SM, one that produces or consumes a carry at half that.  So operands are kept
+// as 31-bit halves packed in one word, x = x1*2^31 + x0 -> (x1 << 32) | x0, every partial product is < 2^62, and
+// four consecutive terms are summed in plain 64-bit IMAD.WIDE accumulators (no carry possible) before being folded
+// into 96-bit sums on the alu pipe:  4 IMAD.WIDE (fma pipe) + ~2.5 IADD3 (alu pipe) per multiply-accumulate.
+//     a*b = H*2^62 + (M01 + M10)*2^31 + L,   L = a0*b0, M01 = a0*b1, M10 = a1*b0, H = a1*b1
+// ---------------------------------------------------------------------------------------------------------------
+PVW_DEV u64 pack_halves(u64 x) { return ((x >> 31) << 32) | (x & 0x7fffffffull); }       // x < 2^62
+PVW_DEV u64 unpack_halves(u64 p) { return ((p >> 32) << 31) + (p & 0xffffffffull); }
+PVW_DEV u64 mul_wide(u32 a, u32 b) { u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
+PVW_DEV u64 mad_wide(u32 a, u32 b, u64 c) { u64 r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+struct AccW {
+  u32 l0, l1, l2, m0, m1, m2, h0, h1, h2;
+};
+PVW_DEV void accw_zero(AccW& c) { c.l0 = c.l1 = c.l2 = c.m0 = c.m1 = c.m2 = c.h0 = c.h1 = c.h2 = 0; }
+PVW_DEV u32 lo32(u64 p) { u32 lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p)); return lo; }
+PVW_DEV u32 hi32(u64 p) { u32 lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p)); return hi; }
+PVW_DEV void fold96(u32& w0, u32& w1, u32& w2, u64 p) {
+  asm("add.cc.u32 %0, %0, %3;\n\t"
+      "addc.cc.u32 %1, %1, %4;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      : "+r"(w0), "+r"(w1), "+r"(w2)
+      : "r"(lo32(p)), "r"(hi32(p)));
+}
+// N <= 4 consecutive terms: a[i], b[i] are packed halves
+template <int N>
+PVW_DEV void accw_mac(AccW& c, const u64 (&a)[N], const u64 (&b)[N]) {
+  static_assert(N >= 1 && N <= 4, "at most four 62-bit products fit a 64-bit partial sum");
+  u64 pl, ph, p01, p10;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const u32 a0 = (u32)a[i], a1 = (u32)(a[i] >> 32), b0 = (u32)b[i], b1 = (u32)(b[i] >> 32);
+    if (i == 0) {
+      pl = mul_wide(a0, b0); p01 = mul_wide(a0, b1); p10 = mul_wide(a1, b0); ph = mul_wide(a1, b1);
+    } else {
+      pl = mad_wide(a0, b0, pl); p01 = mad_wide(a0, b1, p01); p10 = mad_wide(a1, b0, p10); ph = mad_wide(a1, b1, ph);
+    }
+  }
+  fold96(c.l0, c.l1, c.l2, pl);
+  fold96(c.m0, c.m1, c.m2, p01);
+  fold96(c.m0, c.m1, c.m2, p10);
+  fold96(c.h0, c.h1, c.h2, ph);
+}
+// canonical value of the accumulator mod q
+PVW_DEV u64 accw_reduce(const AccW& c, const LimbConst& lc) {
+  const u64 L = reduce128(reduce64((u64)c.l2, lc), ((u64)c.l1 << 32) | c.l0, lc);
+  const u64 M = reduce128(reduce64((u64)c.m2, lc), ((u64)c.m1 << 32) | c.m0, lc);
+  const u64 H = reduce128(reduce64((u64)c.h2, lc), ((u64)c.h1 << 32) | c.h0, lc);
+  const u64 p31 = reduce64(1ull << 31, lc), p62 = reduce64(1ull << 62, lc);
+  return addmod(addmod(mulmod(H, p62, lc), mulmod(M, p31, lc), lc.q), L, lc.q);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hybrid: Karatsuba with the two small products (L = a0*b0, H = a1*b1 < 2^62) summed carry-free four at a time and
+// the cross term K = (a0+a1)*(b0+b1) < 2^64 accumulated with carry.  Packed operand word: (x1 << 32) | x0.
+// ---------------------------------------------------------------------------------------------------------------
+struct AccH {
+  u32 l0, l1, l2, h0, h1, h2, k0, k1, k2;
+};
+PVW_DEV void acch_zero(AccH& c) { c.l0 = c.l1 = c.l2 = c.h0 = c.h1 = c.h2 = c.k0 = c.k1 = c.k2 = 0; }
+template <int N>
+PVW_DEV void acch_mac(AccH& c, const u64 (&a)[N], const u64 (&b)[N]) {
+  static_assert(N >= 1 && N <= 4, "at most four 62-bit products fit a 64-bit partial sum");
+  u64 pl, ph;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const u32 a0 = (u32)a[i], a1 = (u32)(a[i] >> 32), b0 = (u32)b[i], b1 = (u32)(b[i] >> 32);
+    const u32 as = a0 + a1, bs = b0 + b1;
+    if (i == 0) { pl = mul_wide(a0, b0); ph = mul_wide(a1, b1); }
+    else { pl = mad_wide(a0, b0, pl); ph = mad_wide(a1, b1, ph); }
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;\n\t"
+        : "+r"(c.k0), "+r"(c.k1), "+r"(c.k2)
+        : "r"(as), "r"(bs));
+  }
+  fold96(c.l0, c.l1, c.l2, pl);
+  fold96(c.h0, c.h1, c.h2, ph);
+}
+
 }  // namespace pvw

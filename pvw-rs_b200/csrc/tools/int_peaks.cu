@@ -1,0 +1,344 @@
+// int_peaks.cu -- measures the integer-pipe ceilings the PVW kernels are judged against ("integer-modmul
+// peak is not in MEASURED_PEAKS.json -- measure it once on the box with a register-resident modmul loop").
+// Register-resident loops, no memory traffic: IMAD.WIDE.U32 issue rate, the 160-bit lazy multiply-accumulate of
+// modarith.cuh, the 3-multiply (Karatsuba, 31-bit halves) variant, and Barrett / Shoup modular multiplies.
+// Prints one JSON object.  Usage: int_peaks [iters]
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../modarith.cuh"
+
+using namespace pvw;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("{\"error\": \"%s\"}\n", cudaGetErrorString(e)); return 1; } } while (0)
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_imad_wide(u64* out, const u32* in, int iters) {
+  u64 acc[CH];
+  u32 a[CH];
+  u32 b = in[threadIdx.x & 31];
+#pragma unroll
+  for (int i = 0; i < CH; i++) { acc[i] = in[i + 32]; a[i] = in[i + 64] + threadIdx.x; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CH; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a[i]), "r"(b));
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) s ^= acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// IMAD.WIDE with carry-out + IADD3.X: 96-bit accumulate of 32x32 products
+template <int CH>
+__global__ void __launch_bounds__(256) k_imad_wide_cc(u64* out, const u32* in, int iters) {
+  u32 lo[CH], hi[CH], top[CH], a[CH];
+  u32 b = in[threadIdx.x & 31];
+#pragma unroll
+  for (int i = 0; i < CH; i++) { lo[i] = in[i + 32]; hi[i] = in[i + 40]; top[i] = 0; a[i] = in[i + 64] + threadIdx.x; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CH; i++)
+      asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                   : "+r"(lo[i]), "+r"(hi[i]), "+r"(top[i]) : "r"(a[i]), "r"(b));
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) s ^= ((u64)hi[i] << 32 | lo[i]) + top[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_mac160(u64* out, const u64* in, int iters) {
+  Acc160 acc[CH];
+  u64 a[CH];
+  u64 b = in[threadIdx.x & 31];
+#pragma unroll
+  for (int i = 0; i < CH; i++) { acc_zero(acc[i]); a[i] = in[i + 32] + threadIdx.x; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CH; i++) acc_mac(acc[i], a[i], b);
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) s ^= ((u64)acc[i].e1 << 32 | acc[i].e0) + acc[i].e2 + acc[i].e3 + acc[i].e4 + acc[i].o0 + acc[i].o1 + acc[i].o2;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_mack(u64* out, const u64* in, int iters) {
+  AccK acc[CH];
+  SplitOp a[CH];
+  SplitOp b = split_op(in[threadIdx.x & 31] >> 2);
+#pragma unroll
+  for (int i = 0; i < CH; i++) { acck_zero(acc[i]); a[i] = split_op((in[i + 32] >> 2) + threadIdx.x); }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < CH; i++) acck_mac(acc[i], a[i], b);
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) s ^= acc[i].l0 + acc[i].l1 + acc[i].l2 + acc[i].h0 + acc[i].h1 + acc[i].h2 + acc[i].k0 + acc[i].k1 + acc[i].k2;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// candidate production inner loops in isolation: 4x4 register tile, groups of 4 terms, operands from shared memory.
+// MODE 0: Acc160 (4 carry IMAD.WIDE), 1: AccK (3 carry IMAD.WIDE), 2: AccW (4 plain IMAD.WIDE + folds), 3: AccH (hybrid)
+template <int MODE> struct TileAcc;
+template <> struct TileAcc<0> { typedef Acc160 T; };
+template <> struct TileAcc<1> { typedef AccK T; };
+template <> struct TileAcc<2> { typedef AccW T; };
+template <> struct TileAcc<3> { typedef AccH T; };
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) k_tile(u64* out, const u64* in, int iters) {
+  typedef typename TileAcc<MODE>::T Acc;
+  __shared__ u64 sm[2][16][8 * 8 + 2];  // [M|V][row][j*8 + c]
+  for (int i = threadIdx.x; i < 2 * 16 * 66; i += blockDim.x)
+    (&sm[0][0][0])[i] = MODE == 0 ? (in[i % 1024] >> 2) : pack_halves(in[i % 1024] >> 2);
+  __syncthreads();
+  Acc acc[4][4];
+  memset(acc, 0, sizeof(acc));
+  const int c = threadIdx.x & 7, g = threadIdx.x >> 3, gr = (g >> 2) & 3, gd = g & 3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 1
+    for (int grp = 0; grp < 2; grp++) {
+      u64 b[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) b[u][i] = sm[1][gd * 4 + u][(grp * 4 + i) * 8 + c];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        u64 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = sm[0][gr * 4 + t][(grp * 4 + i) * 8 + c];
+        if constexpr (MODE == 1) {
+          SplitOp as[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) { as[i].x0 = (u32)a[i]; as[i].x1 = (u32)(a[i] >> 32); as[i].xs = as[i].x0 + as[i].x1; }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              SplitOp bs; bs.x0 = (u32)b[u][i]; bs.x1 = (u32)(b[u][i] >> 32); bs.xs = bs.x0 + bs.x1;
+              acck_mac(acc[t][u], as[i], bs);
+            }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if constexpr (MODE == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) acc_mac(acc[t][u], a[i], b[u][i]);
+            } else if constexpr (MODE == 2) {
+              accw_mac<4>(acc[t][u], a, b[u]);
+            } else {
+              acch_mac<4>(acc[t][u], a, b[u]);
+            }
+          }
+        }
+      }
+    }
+  }
+  u64 s = 0;
+  const u32* w = reinterpret_cast<const u32*>(&acc[0][0]);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(acc) / 4); i++) s += w[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// carry-free accumulation with the 4-term partial sums carried across a REAL (not unrolled) loop so that ptxas keeps
+// every IMAD.WIDE as an in-place accumulate (in straight-line code it re-associates the chains into adds)
+__device__ __forceinline__ void mad_wide_ip(u64& acc, u32 a, u32 b) { asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b)); }
+template <int TR, int TD, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_tile_loop(u64* out, const u64* in, int iters) {
+  __shared__ u64 sm[2][16][8 * 8 + 2];
+  for (int i = threadIdx.x; i < 2 * 16 * 66; i += blockDim.x) (&sm[0][0][0])[i] = pack_halves(in[i % 1024] >> 2);
+  __syncthreads();
+  AccW acc[TR][TD];
+  memset(acc, 0, sizeof(acc));
+  const int c = threadIdx.x & 7, g = threadIdx.x >> 3, gr = (g >> 2) % (16 / TR), gd = g % (16 / TD);
+  const u64* ma = &sm[0][gr * TR][c];
+  const u64* mb = &sm[1][gd * TD][c];
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 1
+    for (int grp = 0; grp < 2; grp++) {
+      u64 pl[TR][TD], p01[TR][TD], p10[TR][TD], ph[TR][TD];
+      {
+        u64 a[TR], b[TD];
+#pragma unroll
+        for (int t = 0; t < TR; t++) a[t] = ma[t * 66 + grp * 32];
+#pragma unroll
+        for (int u = 0; u < TD; u++) b[u] = mb[u * 66 + grp * 32];
+#pragma unroll
+        for (int t = 0; t < TR; t++)
+#pragma unroll
+          for (int u = 0; u < TD; u++) {
+            const u32 a0 = (u32)a[t], a1 = (u32)(a[t] >> 32), b0 = (u32)b[u], b1 = (u32)(b[u] >> 32);
+            pl[t][u] = mul_wide(a0, b0); p01[t][u] = mul_wide(a0, b1); p10[t][u] = mul_wide(a1, b0); ph[t][u] = mul_wide(a1, b1);
+          }
+      }
+#pragma unroll 1
+      for (int jj = 1; jj < 4; jj++) {
+        u64 a[TR], b[TD];
+#pragma unroll
+        for (int t = 0; t < TR; t++) a[t] = ma[t * 66 + grp * 32 + jj * 8];
+#pragma unroll
+        for (int u = 0; u < TD; u++) b[u] = mb[u * 66 + grp * 32 + jj * 8];
+#pragma unroll
+        for (int t = 0; t < TR; t++)
+#pragma unroll
+          for (int u = 0; u < TD; u++) {
+            const u32 a0 = (u32)a[t], a1 = (u32)(a[t] >> 32), b0 = (u32)b[u], b1 = (u32)(b[u] >> 32);
+            mad_wide_ip(pl[t][u], a0, b0); mad_wide_ip(p01[t][u], a0, b1); mad_wide_ip(p10[t][u], a1, b0); mad_wide_ip(ph[t][u], a1, b1);
+          }
+      }
+#pragma unroll
+      for (int t = 0; t < TR; t++)
+#pragma unroll
+        for (int u = 0; u < TD; u++) {
+          AccW& w = acc[t][u];
+          fold96(w.l0, w.l1, w.l2, pl[t][u]);
+          fold96(w.m0, w.m1, w.m2, p01[t][u]);
+          fold96(w.m0, w.m1, w.m2, p10[t][u]);
+          fold96(w.h0, w.h1, w.h2, ph[t][u]);
+        }
+    }
+  }
+  u64 s = 0;
+  const u32* w = reinterpret_cast<const u32*>(&acc[0][0]);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(acc) / 4); i++) s += w[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// Karatsuba (AccK) tile with configurable register tile / occupancy
+template <int TR, int TD, int NB>
+__global__ void __launch_bounds__(256, NB) k_tile_k(u64* out, const u64* in, int iters) {
+  __shared__ u64 sm[2][16][8 * 8 + 2];
+  for (int i = threadIdx.x; i < 2 * 16 * 66; i += blockDim.x) (&sm[0][0][0])[i] = pack_halves(in[i % 1024] >> 2);
+  __syncthreads();
+  AccK acc[TR][TD];
+  memset(acc, 0, sizeof(acc));
+  const int c = threadIdx.x & 7, g = threadIdx.x >> 3, gr = (g >> 2) % (16 / TR), gd = g % (16 / TD);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll 2
+    for (int jj = 0; jj < 8; jj++) {
+      SplitOp a[TR], b[TD];
+#pragma unroll
+      for (int t = 0; t < TR; t++) { u64 v = sm[0][gr * TR + t][jj * 8 + c]; a[t].x0 = (u32)v; a[t].x1 = (u32)(v >> 32); a[t].xs = a[t].x0 + a[t].x1; }
+#pragma unroll
+      for (int u = 0; u < TD; u++) { u64 v = sm[1][gd * TD + u][jj * 8 + c]; b[u].x0 = (u32)v; b[u].x1 = (u32)(v >> 32); b[u].xs = b[u].x0 + b[u].x1; }
+#pragma unroll
+      for (int t = 0; t < TR; t++)
+#pragma unroll
+        for (int u = 0; u < TD; u++) acck_mac(acc[t][u], a[t], b[u]);
+    }
+  }
+  u64 s = 0;
+  const u32* w = reinterpret_cast<const u32*>(&acc[0][0]);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(acc) / 4); i++) s += w[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_mulmod(u64* out, const u64* in, const LimbConst* lcp, int iters, int shoup) {
+  const LimbConst lc = lcp[0];
+  u64 x[CH];
+  u64 w = in[threadIdx.x & 31] % lc.q, wsh = lc.ninv_sh;
+#pragma unroll
+  for (int i = 0; i < CH; i++) x[i] = (in[i + 32] + threadIdx.x) % lc.q;
+  if (shoup) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < CH; i++) x[i] = mulmod_shoup(x[i], lc.ninv, wsh, lc.q);
+    }
+  } else {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < CH; i++) x[i] = mulmod(x[i], w, lc);
+    }
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < CH; i++) s ^= x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <class F>
+static double time_ms(F&& launch, int reps = 5) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  launch();
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int r = 0; r < reps; r++) {
+    cudaEventRecord(a);
+    launch();
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  return best;
+}
+
+int main(int argc, char** argv) {
+  int iters = argc > 1 ? atoi(argv[1]) : 4096;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount, blocks = sms * 8, threads = 256;
+  u64 *out, *in; LimbConst* lc;
+  CK(cudaMalloc(&out, (size_t)blocks * threads * 8));
+  CK(cudaMalloc(&in, 1024 * 8));
+  CK(cudaMalloc(&lc, sizeof(LimbConst)));
+  u64 h[1024];
+  for (int i = 0; i < 1024; i++) h[i] = 0x9E3779B97F4A7C15ull * (i + 1) ^ (0xBF58476D1CE4E5B9ull >> (i % 13));
+  CK(cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice));
+  LimbConst hl{};
+  hl.q = 0x3ffffffffffffdc1ull;
+  unsigned __int128 mu = (~(unsigned __int128)0) / hl.q;
+  hl.mu_hi = (u64)(mu >> 64); hl.mu_lo = (u64)mu; hl.mu64 = (u64)((((unsigned __int128)1) << 64) / hl.q);
+  hl.ninv = 0x123456789abcdefull % hl.q; hl.ninv_sh = (u64)((((unsigned __int128)hl.ninv) << 64) / hl.q);
+  CK(cudaMemcpy(lc, &hl, sizeof(hl), cudaMemcpyHostToDevice));
+  const double thr = (double)blocks * threads;
+  constexpr int CH = 8;
+  double t1 = time_ms([&] { k_imad_wide<CH><<<blocks, threads>>>(out, (const u32*)in, iters); });
+  double t2 = time_ms([&] { k_imad_wide_cc<CH><<<blocks, threads>>>(out, (const u32*)in, iters); });
+  double t3 = time_ms([&] { k_mac160<CH><<<blocks, threads>>>(out, in, iters); });
+  double t4 = time_ms([&] { k_mack<CH><<<blocks, threads>>>(out, in, iters); });
+  double tt[4];
+  tt[0] = time_ms([&] { k_tile<0><<<sms, 256>>>(out, in, iters / 4); });
+  tt[1] = time_ms([&] { k_tile<1><<<sms, 256>>>(out, in, iters / 4); });
+  tt[2] = time_ms([&] { k_tile<2><<<sms, 256>>>(out, in, iters / 4); });
+  tt[3] = time_ms([&] { k_tile<3><<<sms, 256>>>(out, in, iters / 4); });
+  double tl1 = time_ms([&] { k_tile_loop<2, 4, 256><<<sms, 256>>>(out, in, iters / 4); });
+  double tl2 = time_ms([&] { k_tile_loop<2, 4, 384><<<sms, 384>>>(out, in, iters / 4); });
+  double tl3 = time_ms([&] { k_tile_loop<2, 2, 512><<<sms, 512>>>(out, in, iters / 4); });
+  printf("{\"tile_loop_2x4_256\": %.4g, \"tile_loop_2x4_384\": %.4g, \"tile_loop_2x2_512\": %.4g}\n",
+         (double)sms * 256 * 8 * 8 * (iters / 4) / (tl1 * 1e-3), (double)sms * 384 * 8 * 8 * (iters / 4) / (tl2 * 1e-3),
+         (double)sms * 512 * 4 * 8 * (iters / 4) / (tl3 * 1e-3));
+  {
+    double a1 = time_ms([&] { k_tile_k<4, 4, 1><<<sms, 256>>>(out, in, iters / 4); });
+    double a2 = time_ms([&] { k_tile_k<4, 2, 2><<<sms * 2, 256>>>(out, in, iters / 4); });
+    double a3 = time_ms([&] { k_tile_k<2, 2, 3><<<sms * 3, 256>>>(out, in, iters / 4); });
+    double a4 = time_ms([&] { k_tile_k<4, 3, 1><<<sms, 256>>>(out, in, iters / 4); });
+    printf("{\"tilek_4x4_1cta\": %.4g, \"tilek_4x2_2cta\": %.4g, \"tilek_2x2_3cta\": %.4g, \"tilek_4x3_1cta\": %.4g}\n",
+           (double)sms * 256 * 16 * 8 * (iters / 4) / (a1 * 1e-3), (double)sms * 2 * 256 * 8 * 8 * (iters / 4) / (a2 * 1e-3),
+           (double)sms * 3 * 256 * 4 * 8 * (iters / 4) / (a3 * 1e-3), (double)sms * 256 * 12 * 8 * (iters / 4) / (a4 * 1e-3));
+  }
+  auto trate = [&](double ms) { return (double)sms * 256 * 16 * 8 * (iters / 4) / (ms * 1e-3); };
+  double t5 = time_ms([&] { k_mulmod<CH><<<blocks, threads>>>(out, in, lc, iters, 0); });
+  double t6 = time_ms([&] { k_mulmod<CH><<<blocks, threads>>>(out, in, lc, iters, 1); });
+  CK(cudaGetLastError());
+  auto rate = [&](double ms) { return thr * CH * iters / (ms * 1e-3); };
+  int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  printf("{\"sms\": %d, \"max_clock_khz\": %d, \"imad_wide_per_s\": %.4g, \"imad_wide_cc_per_s\": %.4g, \"mac160_per_s\": %.4g, "
+         "\"mac_karatsuba_per_s\": %.4g, \"tile_mac160_per_s\": %.4g, \"tile_karatsuba_per_s\": %.4g, \"tile_carryfree_per_s\": %.4g, \"tile_hybrid_per_s\": %.4g, \"mulmod_barrett_per_s\": %.4g, \"mulmod_shoup_per_s\": %.4g, "
+         "\"imad_wide_per_clk_per_sm_at_max_clock\": %.3f}\n",
+         sms, clk, rate(t1), rate(t2), rate(t3), rate(t4), trate(tt[0]), trate(tt[1]), trate(tt[2]), trate(tt[3]), rate(t5), rate(t6), rate(t1) / ((double)clk * 1e3) / sms);
+  return 0;
+}

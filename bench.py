@@ -182,10 +182,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     n, k, l, L = args.parties, K_DIM, ELL, N_LIMBS
-    assert n % world == 0, "parties must divide evenly over the ranks"
-    nrows, row0 = n // world, rank * (n // world)
+    plan = pvw.sharding.ShardPlan(n, world, rank)
+    nrows, row0 = plan.nrows, plan.row0
     Dg = args.dealers                 # dealers per GPU per step (this rank's c1 slice)
     D = Dg * world                    # dealers per step
+    c1_lo, c1_hi = plan.dealer_slice(D)
     moduli = p128_moduli()
 
     eng = pvw.Engine(n, k, l, moduli, row0=row0, nrows=nrows, device=local)
@@ -227,11 +228,11 @@ def run_b200(args):
 
     def gather_c1():
         if world > 1:
-            with torch.cuda.stream(ext):
-                dist.all_gather_into_tensor(c1_view, c1_view[rank * Dg:(rank + 1) * Dg])
+            with torch.cuda.stream(ext):     # ordered on the library's stream, between encrypt and decrypt
+                pvw.sharding.all_gather_c1(c1_view, plan)
 
     def step_device():
-        eng.encrypt_batch(0, m, r, e1, e2, c1_range=(rank * Dg, (rank + 1) * Dg))
+        eng.encrypt_batch(0, m, r, e1, e2, c1_range=(c1_lo, c1_hi))
         gather_c1()
         eng.decrypt_batch(parties, sk, D=D, out=out)
 
@@ -242,7 +243,7 @@ def run_b200(args):
     n_m = n_m.view(np.uint64)
 
     def step_host():
-        eng.encrypt_batch(0, n_m, n_r, n_e1, n_e2, c1_range=(rank * Dg, (rank + 1) * Dg))
+        eng.encrypt_batch(0, n_m, n_r, n_e1, n_e2, c1_range=(c1_lo, c1_hi))
         gather_c1()
         return eng.decrypt_batch(parties, n_sk, D=D)
 
@@ -294,7 +295,7 @@ def run_b200(args):
         step_host()
     ms_e2e = timed(step_host, args.steps)
     e2e_value = shares_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(a.nbytes for a in (n_m, n_r, n_e2, n_sk)) + n_e1[rank * Dg:(rank + 1) * Dg].nbytes + parties.nbytes
+    h2d = sum(a.nbytes for a in (n_m, n_r, n_e2, n_sk)) + n_e1[c1_lo:c1_hi].nbytes + parties.nbytes
     d2h = nrows * D * 8
 
     if rank != 0:

@@ -191,6 +191,9 @@ def run_b200(args):
 
     eng = pvw.Engine(n, k, l, moduli, row0=row0, nrows=nrows, device=local)
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    for kv in filter(None, os.environ.get("PVW_OPTS", "").split(",")):     # tuning knobs, e.g. PVW_OPTS=gemm_tile=0,refill_lag=1
+        name, val = kv.split("=")
+        eng.set_option(name.strip(), int(val))
 
     # ---- setup (untimed): CRS broadcast over NCCL, genuine public keys generated on the device ----------------
     gen = torch.Generator(device=dev)
@@ -268,11 +271,15 @@ def run_b200(args):
     # ---- correctness guard: the plaintexts of the step are the messages (genuine keys) -------------------------
     step_device()
     eng.synchronize()
-    ok = bool((out.t() == m).all().item())
+    bad_dev = (out.t() != m)
     res_host = step_host()
-    ok = ok and bool((res_host.view(np.int64).T == n_m.view(np.int64)).all())
-    if not ok:
-        raise SystemExit("bench: decrypted shares differ from the messages -- refusing to report a number")
+    bad_host = torch.from_numpy(res_host.view(np.int64).T != n_m.view(np.int64))
+    for name, bad in (("device-resident", bad_dev), ("host-buffer", bad_host)):
+        if bool(bad.any().item()):
+            idx = bad.nonzero()
+            raise SystemExit(f"bench: rank {rank}: {idx.shape[0]} decrypted shares differ from the messages on the {name} path "
+                             f"(first (dealer, party) = {idx[0].tolist()}, dealers hit: {idx[:, 0].unique().numel()}, parties hit: "
+                             f"{idx[:, 1].unique().numel()}) -- refusing to report a number")
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3) - 1):

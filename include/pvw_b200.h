@@ -16,6 +16,8 @@
  *    pvw_ct_c1_device_ptr() exposes.  A context is not thread-safe; guard it with a mutex (the Rust shim does).
  *  - `PVW_IO_DEVICE` in `flags` means the data pointers of that call are CUDA device pointers on the context's
  *    device (inputs already resident in HBM); otherwise they are host pointers and the call performs the copies.
+ *    Device-pointer calls are asynchronous: they are queued on pvw_ctx_stream() and return at once, so the caller must
+ *    order its own producers / consumers of those buffers against that stream (events, or pvw_ctx_synchronize()).
  *  - there is no CPU fallback: without a CUDA device pvw_ctx_create fails with PVW_ERR_INTERNAL.
  */
 #ifndef PVW_B200_H

@@ -83,7 +83,7 @@ struct pvw_ctx {
   double prof_ms[PVW_KERNEL_KINDS] = {0};
   uint64_t prof_n[PVW_KERNEL_KINDS] = {0};
   double prof_bytes[PVW_KERNEL_KINDS] = {0};
-  int gemm_impl = 1;
+  int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
   int64_t decrypt_chunk_shares = 1 << 19;
   int64_t upload_chunk_bytes = 256ll << 20;
 
@@ -218,7 +218,9 @@ void download_polys(pvw_ctx* c, const u64* src, size_t src_limb_stride, uint64_t
 
 void require(bool cond, int code, const std::string& msg) { if (!cond) throw PvwException(code, msg); }
 
-void gemm(pvw_ctx* c, const GemmArgs& a) {
+void gemm(pvw_ctx* c, GemmArgs a) {
+  a.tile = c->gemm_tile;
+  a.refill_lag = c->refill_lag;
   // algorithmic bytes: per (dealer, row) one k-polynomial operand row read + one polynomial written
   const double bytes = (double)a.D * a.rows * (a.k + 1.0) * a.L * a.ell * 8.0;
   launch(c, PVW_KERNEL_MAC, bytes, [&] { launch_mac_gemm(a, c->gemm_impl, c->stream); });
@@ -656,6 +658,8 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");
     std::string n(name);
     if (n == "gemm_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0 or 1"); c->gemm_impl = (int)value; }
+    else if (n == "gemm_tile") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0 or 1"); c->gemm_tile = (int)value; }
+    else if (n == "refill_lag") { require(value >= 1 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..3"); c->refill_lag = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }
     else if (n == "profile") {

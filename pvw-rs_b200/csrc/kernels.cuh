@@ -56,6 +56,8 @@ struct GemmArgs {
   uint32_t rows, D, k, L, ell;
   int mode;
   const LimbConst* lc;
+  int tile;        // register-tile / occupancy variant (mac.cu launch_mac_gemm)
+  int refill_lag;  // chunks between a stage's last use and its refill (1 .. NS-1)
 };
 // impl: 0 = synchronous shared-memory tiles, 1 = cp.async.bulk (TMA) + mbarrier pipeline with a producer warp
 void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st);

@@ -24,23 +24,9 @@
 #include <cstdio>
 
 #include "kernels.cuh"
+#include "mac_worker.cuh"
 
 namespace pvw {
-
-constexpr int kComputeThreads = 256;
-constexpr int NS = 4;  // pipeline stages
-
-template <int ELL, int TR, int TD, int GD, int KC>
-struct TileCfg {
-  // KC = polynomials (j indices) per pipeline stage
-  static constexpr int G = kComputeThreads / ELL;  // (row-group, dealer-group) pairs per CTA
-  static constexpr int GR = G / GD;
-  static constexpr int RT = GR * TR;               // rows per CTA
-  static constexpr int DT = GD * TD;               // dealers per CTA
-  static constexpr int ROWB = KC * ELL * 8 + 16;   // bytes per staged row (+16: dealer sub-tiles land on distinct banks)
-  static constexpr int STAGE = (RT + DT) * ROWB;
-  static_assert(G % GD == 0, "bad tile");
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -66,93 +52,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int ELL, int TR, int TD, int GD, int KC>
-struct Worker {
-  using C = TileCfg<ELL, TR, TD, GD, KC>;
-  int c, gr, gd;
-  AccK acc[TR][TD];
-  __device__ __forceinline__ void init(int tid) {
-    const int lane = tid & 31, w = tid >> 5;
-    c = lane % ELL;
-    const int g = w * (32 / ELL) + lane / ELL;
-    gd = g % GD;
-    gr = g / GD;
-#pragma unroll
-    for (int t = 0; t < TR; t++)
-#pragma unroll
-      for (int u = 0; u < TD; u++) acck_zero(acc[t][u]);
-  }
-  // NJ consecutive polynomials starting at jj0: the TD dealer operands are split once and reused for the TR rows
-  template <int NJ>
-  __device__ __forceinline__ void block(const unsigned char* ms, const unsigned char* vs, int jj0) {
-    u32 b0[TD][NJ], b1[TD][NJ];  // 31-bit halves; the Karatsuba sum is formed at the use (alu pipe has slack, registers do not)
-#pragma unroll
-    for (int u = 0; u < TD; u++)
-#pragma unroll
-      for (int i = 0; i < NJ; i++) {
-        const u64 x = *reinterpret_cast<const u64*>(vs + u * C::ROWB + (jj0 + i) * ELL * 8);
-        b0[u][i] = (u32)x & 0x7fffffffu;
-        b1[u][i] = (u32)(x >> 31);
-      }
-#pragma unroll
-    for (int t = 0; t < TR; t++) {
-      SplitOp a[NJ];
-#pragma unroll
-      for (int i = 0; i < NJ; i++) a[i] = split_op(*reinterpret_cast<const u64*>(ms + t * C::ROWB + (jj0 + i) * ELL * 8));
-#pragma unroll
-      for (int u = 0; u < TD; u++)
-#pragma unroll
-        for (int i = 0; i < NJ; i++) {
-          SplitOp b;
-          b.x0 = b0[u][i]; b.x1 = b1[u][i]; b.xs = b0[u][i] + b1[u][i];
-          acck_mac(acc[t][u], a[i], b);
-        }
-    }
-  }
-  // one staged chunk: kc polynomials of every row / dealer of the tile
-  template <bool FULL>
-  __device__ __forceinline__ void chunk(const unsigned char* stage, int kc) {
-    const unsigned char* ms = stage + (size_t)(gr * TR) * C::ROWB + c * 8;
-    const unsigned char* vs = stage + (size_t)(C::RT + gd * TD) * C::ROWB + c * 8;
-    constexpr int NJ = KC % 4 == 0 ? 4 : (KC % 2 == 0 ? 2 : 1);
-    if (FULL) {
-      // straight-line blocks of NJ polynomials; the compiler barrier keeps ptxas from hoisting the next block's
-      // shared-memory loads above this block's arithmetic (which costs registers and then spills)
-#pragma unroll
-      for (int jj = 0; jj < KC; jj += NJ) {
-        block<NJ>(ms, vs, jj);
-        asm volatile("" ::: "memory");
-      }
-    } else {
-#pragma unroll 1
-      for (int jj = 0; jj < kc; jj++) block<1>(ms, vs, jj);
-    }
-  }
-  __device__ __forceinline__ void epilogue(const GemmArgs& g, uint32_t limb, uint32_t r0, uint32_t d0) {
-    const LimbConst lc = g.lc[limb];
-#pragma unroll
-    for (int u = 0; u < TD; u++) {
-      const uint32_t d = d0 + gd * TD + u;
-      if (d >= g.D) continue;
-      const uint32_t ds = g.V_dmap ? g.V_dmap[d] : d;
-#pragma unroll
-      for (int t = 0; t < TR; t++) {
-        const uint32_t row = r0 + gr * TR + t;
-        if (row >= g.rows) continue;
-        u64 v = acck_reduce(acc[t][u], lc);
-        u64* o = g.O + (size_t)d * g.O_ds + (size_t)limb * g.O_ls + (size_t)row * ELL + c;
-        if (g.mode == 0) {
-          v = addmod(v, *o, lc.q);
-        } else {
-          const uint32_t srow = g.S_rowmap ? g.S_rowmap[row] : row;
-          v = submod(v, g.S[(size_t)ds * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * ELL + c], lc.q);
-        }
-        *o = v;
-      }
-    }
-  }
-};
-
 // source address of staged row `rr` of the tile (rows first, then dealers); out-of-range indices are clamped to the
 // last valid one (their products are computed and discarded), so every copy is in bounds and full width.
 template <class C>
@@ -167,8 +66,8 @@ __device__ __forceinline__ const u64* row_src(const GemmArgs& g, uint32_t limb, 
 }
 
 // ---- impl 0: synchronous tiles ------------------------------------------------------------------------------------
-template <int ELL, int TR, int TD, int GD, int KC>
-__global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_sync_kernel(const GemmArgs g) {
+template <int ELL, int TR, int TD, int GD, int KC, int NB>
+__global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_sync_kernel(const GemmArgs g) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t limb = blockIdx.z, r0 = blockIdx.x * C::RT, d0 = blockIdx.y * C::DT;
@@ -193,8 +92,8 @@ __global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_sync_kernel(const
 // Nine warps would cap the kernel at 168 registers (three warps on one sub-partition share 16 K registers), so the
 // eight compute warps feed themselves: warp w owns rows {w, w+8, ...} of the staged tile; before it starts chunk i it
 // refills the stage that chunk i-1 used (everybody has left it: `empty` barrier) with chunk i-1+NS.
-template <int ELL, int TR, int TD, int GD, int KC>
-__global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_tma_kernel(const GemmArgs g) {
+template <int ELL, int TR, int TD, int GD, int KC, int NB>
+__global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tma_kernel(const GemmArgs g) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
   constexpr int NW = kComputeThreads / 32;
   constexpr int ROWS = C::RT + C::DT;
@@ -228,13 +127,16 @@ __global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_tma_kernel(const 
     if (issuer) bulk_g2s(smem_u32(smem) + s * C::STAGE + my_row * C::ROWB, my_src + (size_t)chunk * KC * ELL, row_bytes, bar0 + 8 * s);
   };
   for (uint32_t ch = 0; ch < nchunks && ch < (uint32_t)NS; ch++) refill(ch);
+  // the stage of chunk i-lag is refilled when chunk i starts: lag 1 = deepest prefetch but the wait on `empty` acts as
+  // a per-chunk barrier between the warps; lag 2 leaves a chunk of slack
+  const uint32_t lag = g.refill_lag >= 1 && g.refill_lag < NS ? g.refill_lag : 1;
   Worker<ELL, TR, TD, GD, KC> wk;
   wk.init(tid);
   for (uint32_t it = 0; it < nchunks; it++) {
-    if (it >= 1 && it - 1 + NS < nchunks) {
-      const int sp = (it - 1) % NS;
-      mbar_wait(bar0 + 8 * (NS + sp), ((it - 1) / NS) & 1);  // every warp has finished chunk it-1
-      refill(it - 1 + NS);
+    if (it >= lag && it - lag + NS < nchunks) {
+      const uint32_t prev = it - lag;
+      mbar_wait(bar0 + 8 * (NS + prev % NS), (prev / NS) & 1);  // every warp has finished chunk it-lag
+      refill(prev + NS);
     }
     const int s = it % NS;
     mbar_wait(bar0 + 8 * s, (it / NS) & 1);
@@ -247,17 +149,17 @@ __global__ void __launch_bounds__(kComputeThreads, 1) mac_gemm_tma_kernel(const 
   wk.epilogue(g, limb, r0, d0);
 }
 
-template <int ELL, int TR, int TD, int GD, int KC>
+template <int ELL, int TR, int TD, int GD, int KC, int NB>
 static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
   dim3 grid((a.rows + C::RT - 1) / C::RT, (a.D + C::DT - 1) / C::DT, a.L);
   if (impl == 0) {
-    auto kern = mac_gemm_sync_kernel<ELL, TR, TD, GD, KC>;
+    auto kern = mac_gemm_sync_kernel<ELL, TR, TD, GD, KC, NB>;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::STAGE); attr = true; }
     kern<<<grid, kComputeThreads, C::STAGE, st>>>(a);
   } else {
-    auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC>;
+    auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC, NB>;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * C::STAGE); attr = true; }
     kern<<<grid, kComputeThreads, NS * C::STAGE, st>>>(a);
@@ -267,15 +169,24 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
 void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
   if (a.rows == 0 || a.D == 0) return;
   const bool matvec = a.D == 1;
+  // tile 0: 4x4 register tile, one CTA per SM (255 registers); tile 1: 4x2, two CTAs per SM (<= 128 registers) so that
+  // one CTA's prologue / epilogue overlaps the other's main loop
+  const int tile = a.tile;
   switch (a.ell) {
     case 8:
-      if (matvec) launch_cfg<8, 4, 1, 1, 4>(a, impl, st); else launch_cfg<8, 4, 4, 4, 8>(a, impl, st);
+      if (matvec) launch_cfg<8, 4, 1, 1, 4, 2>(a, impl, st);
+      else if (tile == 0) launch_cfg<8, 4, 4, 4, 8, 1>(a, impl, st);
+      else launch_cfg<8, 4, 2, 4, 8, 2>(a, impl, st);
       break;
     case 16:
-      if (matvec) launch_cfg<16, 4, 1, 1, 4>(a, impl, st); else launch_cfg<16, 4, 4, 4, 8>(a, impl, st);
+      if (matvec) launch_cfg<16, 4, 1, 1, 4, 2>(a, impl, st);
+      else if (tile == 0) launch_cfg<16, 4, 4, 4, 8, 1>(a, impl, st);
+      else launch_cfg<16, 4, 2, 4, 8, 2>(a, impl, st);
       break;
     case 32:
-      if (matvec) launch_cfg<32, 4, 1, 1, 4>(a, impl, st); else launch_cfg<32, 4, 4, 2, 4>(a, impl, st);
+      if (matvec) launch_cfg<32, 4, 1, 1, 4, 2>(a, impl, st);
+      else if (tile == 0) launch_cfg<32, 4, 4, 2, 4, 1>(a, impl, st);
+      else launch_cfg<32, 4, 2, 2, 4, 2>(a, impl, st);
       break;
   }
 }

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "../modarith.cuh"
+#include "../mac_worker.cuh"
 
 using namespace pvw;
 
@@ -244,6 +245,43 @@ __global__ void __launch_bounds__(256, NB) k_tile_k(u64* out, const u64* in, int
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// the production inner loop (mac_worker.cuh) on a synthetic staged tile: no copy pipeline, no epilogue
+template <class W, int NB>
+__global__ void __launch_bounds__(W::THREADS, NB) k_worker(u64* out, const u64* in, int iters, int packed) {
+  extern __shared__ __align__(128) unsigned char wsm[];
+  u64* w64 = reinterpret_cast<u64*>(wsm);
+  for (int i = threadIdx.x; i < W::C::STAGE / 8; i += blockDim.x) w64[i] = packed ? pack_halves(in[i % 1024] >> 2) : (in[i % 1024] >> 2);
+  __syncthreads();
+  W wk;
+  wk.init(threadIdx.x);
+  for (int it = 0; it < iters; it++) wk.template chunk<true>(wsm, 0);
+  u64 s = 0;
+  const u32* w = reinterpret_cast<const u32*>(&wk.acc[0][0]);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(wk.acc) / 4); i++) s += w[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <class W, int NB>
+static double worker_rate(const char* name, u64* out, const u64* in, int sms, int iters, int packed) {
+  auto kern = k_worker<W, NB>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, W::C::STAGE);
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+  int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W::THREADS, W::C::STAGE);
+  float best = 1e30f;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(a);
+    kern<<<sms * NB, W::THREADS, W::C::STAGE>>>(out, in, iters, packed);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (r > 0 && ms < best) best = ms;
+  }
+  const double macs = (double)sms * NB * W::C::RT * W::C::DT * 8 /*ell*/ * 8 /*KC*/ * iters;
+  printf("{\"worker\": \"%s\", \"regs\": %d, \"ctas_per_sm\": %d, \"mac_per_s\": %.4g, \"err\": \"%s\"}\n", name, fa.numRegs, occ,
+         macs / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
+  return macs / (best * 1e-3);
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256) k_mulmod(u64* out, const u64* in, const LimbConst* lcp, int iters, int shoup) {
   const LimbConst lc = lcp[0];
@@ -310,6 +348,22 @@ int main(int argc, char** argv) {
   double t2 = time_ms([&] { k_imad_wide_cc<CH><<<blocks, threads>>>(out, (const u32*)in, iters); });
   double t3 = time_ms([&] { k_mac160<CH><<<blocks, threads>>>(out, in, iters); });
   double t4 = time_ms([&] { k_mack<CH><<<blocks, threads>>>(out, in, iters); });
+  {
+    const int wi = iters / 8;
+    worker_rate<Worker<8, 4, 4, 4, 8, 4, false, false, 256>, 1>("4x4 nj4 unrolled canonical (production)", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 4, 4, 8, 4, true, false, 256>, 1>("4x4 nj4 rolled canonical", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 4, 4, 8, 4, false, true, 256>, 1>("4x4 nj4 unrolled packed", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 4, 4, 8, 4, true, true, 256>, 1>("4x4 nj4 rolled packed", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 4, 4, 8, 2, false, true, 256>, 1>("4x4 nj2 unrolled packed", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 4, 4, 8, 8, false, true, 256>, 1>("4x4 nj8 unrolled packed", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, true, 256>, 2>("4x2 nj4 unrolled packed 2cta", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, true, true, 256>, 2>("4x2 nj4 rolled packed 2cta", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 256>, 2>("4x2 nj4 unrolled canonical 2cta", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 8, 8, 4, false, true, 512>, 1>("4x2 nj4 unrolled packed 512thr", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 2, 4, 4, 8, 4, false, true, 256>, 2>("2x4 nj4 unrolled packed 2cta", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 3, 4, 8, 4, false, true, 256>, 1>("4x3 nj4 unrolled packed", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 2, 2, 4, 8, 4, false, true, 256>, 3>("2x2 nj4 unrolled packed 3cta", out, in, sms, wi, 1);
+  }
   double tt[4];
   tt[0] = time_ms([&] { k_tile<0><<<sms, 256>>>(out, in, iters / 4); });
   tt[1] = time_ms([&] { k_tile<1><<<sms, 256>>>(out, in, iters / 4); });

@@ -75,6 +75,26 @@ class Engine:
         self.capacity = 0
 
     # -- plumbing ---------------------------------------------------------------------------------
+    def _torch_streams(self):
+        import torch
+        if getattr(self, "_ext", None) is None:
+            self._ext = torch.cuda.ExternalStream(self.stream, device=torch.device(f"cuda:{self.device}"))
+        return self._ext, torch.cuda.current_stream(torch.device(f"cuda:{self.device}"))
+
+    def _before_device_call(self):
+        """CUDA tensors handed to the library were produced on torch's current stream; the library works on its own
+        stream (pvw_ctx_stream).  Order the library's stream after torch's so that it never reads unfinished inputs."""
+        ext, cur = self._torch_streams()
+        if ext.cuda_stream != cur.cuda_stream:
+            ext.wait_stream(cur)
+
+    def _after_device_call(self):
+        """... and torch's current stream after the library's, so that torch ops see finished outputs and do not recycle
+        input buffers the library is still reading."""
+        ext, cur = self._torch_streams()
+        if ext.cuda_stream != cur.cuda_stream:
+            cur.wait_stream(ext)
+
     def _check(self, rc: int):
         if rc != 0:
             raise PvwError(_ffi.STATUS_NAMES.get(rc, "InternalError"), (self.lib.pvw_last_error(self.h) or b"").decode())
@@ -147,7 +167,11 @@ class Engine:
     # -- CRS / public key residency --------------------------------------------------------------
     def crs_upload(self, A):
         a = _Arg(A, np.uint64, (self.k, self.k) + self.poly, "A")
+        if a.device:
+            self._before_device_call()
         self._check(self.lib.pvw_crs_upload(self.h, a.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+        if a.device:
+            self._after_device_call()
 
     def crs_download(self) -> np.ndarray:
         out = np.empty((self.k, self.k) + self.poly, dtype=np.uint64)
@@ -157,7 +181,11 @@ class Engine:
     def pk_upload_rows(self, row: int, B):
         count = int(B.shape[0])
         a = _Arg(B, np.uint64, (count, self.k) + self.poly, "B rows")
+        if a.device:
+            self._before_device_call()
         self._check(self.lib.pvw_pk_upload_rows(self.h, row, count, a.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+        if a.device:
+            self._after_device_call()
 
     def pk_download_rows(self, row: int, count: int) -> np.ndarray:
         out = np.empty((count, self.k) + self.poly, dtype=np.uint64)
@@ -176,7 +204,11 @@ class Engine:
         b = _Arg(e, np.int64, (count, self.k, self.l), "e")
         if a.device != b.device:
             raise PvwError("InvalidParameters", "sk and e must both be host or both be device arrays")
+        if a.device:
+            self._before_device_call()
         self._check(self.lib.pvw_keygen_batch(self.h, row, count, a.ptr, b.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+        if a.device:
+            self._after_device_call()
 
     def crs_multiply_by_randomness(self, r_hat) -> np.ndarray:
         r = np.ascontiguousarray(r_hat, dtype=np.uint64)
@@ -203,8 +235,13 @@ class Engine:
         devs = {a.device for a in (am, ar, ae2, ae1) if a is not None}
         if len(devs) != 1:
             raise PvwError("InvalidParameters", "inputs must be all host or all device arrays")
+        on_device = devs.pop()
+        if on_device:
+            self._before_device_call()
         self._check(self.lib.pvw_encrypt_batch(self.h, slot0, D, lo, hi, am.ptr, ar.ptr, ae1.ptr if ae1 else None, ae2.ptr,
-                                               _ffi.PVW_IO_DEVICE if devs.pop() else 0))
+                                               _ffi.PVW_IO_DEVICE if on_device else 0))
+        if on_device:
+            self._after_device_call()
 
     def ct_download(self, slot: int, want_c1=True, want_c2=True):
         c1 = np.empty((self.k,) + self.poly, dtype=np.uint64) if want_c1 else None
@@ -251,8 +288,10 @@ class Engine:
                 import torch
                 out = torch.empty((P, D), dtype=torch.int64, device=sk.device)
             o = _Arg(out, np.uint64, (P, D), "out")
+            self._before_device_call()
             self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr, o.ptr,
                                                    _ffi.PVW_IO_DEVICE))
+            self._after_device_call()
             return out
         res = np.empty((P, D), dtype=np.uint64)
         self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr,

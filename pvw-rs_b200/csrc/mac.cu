@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_sync_kernel(cons
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t limb = blockIdx.z, r0 = blockIdx.x * C::RT, d0 = blockIdx.y * C::DT;
   Worker<ELL, TR, TD, GD, KC> wk;
-  wk.init(threadIdx.x);
+  wk.init(threadIdx.x, (u32)g.lc[limb].pad);
   for (uint32_t j0 = 0; j0 < g.k; j0 += KC) {
     const int kc = min((uint32_t)KC, g.k - j0);
     const int vec_per_row = kc * ELL / 2;  // 16-byte vectors
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tma_kernel(const
   // a per-chunk barrier between the warps; lag 2 leaves a chunk of slack
   const uint32_t lag = g.refill_lag >= 1 && g.refill_lag < NS ? g.refill_lag : 1;
   Worker<ELL, TR, TD, GD, KC> wk;
-  wk.init(tid);
+  wk.init(tid, (u32)g.lc[limb].pad);
   for (uint32_t it = 0; it < nchunks; it++) {
     if (it >= lag && it - lag + NS < nchunks) {
       const uint32_t prev = it - lag;

@@ -27,8 +27,10 @@ struct Worker {
   using C = TileCfg<ELL, TR, TD, GD, KC, THREADS_>;
   static constexpr int THREADS = THREADS_;
   int c, gr, gd;
+  u32 zero;  // run-time 0 (see add_alu)
   AccK acc[TR][TD];
-  __device__ __forceinline__ void init(int tid) {
+  __device__ __forceinline__ void init(int tid, u32 opaque_zero = 0) {
+    zero = opaque_zero;
     const int lane = tid & 31, w = tid >> 5;
     c = lane % ELL;
     const int g = w * (32 / ELL) + lane / ELL;
@@ -57,15 +59,15 @@ struct Worker {
 #pragma unroll
       for (int i = 0; i < NJ; i++) {
         const u64 x = *reinterpret_cast<const u64*>(ms + t * C::ROWB + (jj0 + i) * ELL * 8);
-        if (PACKED) { a[i].x0 = (u32)x; a[i].x1 = (u32)(x >> 32); a[i].xs = a[i].x0 + a[i].x1; }
-        else a[i] = split_op(x);
+        if (PACKED) { a[i].x0 = (u32)x; a[i].x1 = (u32)(x >> 32); a[i].xs = add_alu(a[i].x0, a[i].x1, zero); }
+        else a[i] = split_op(x, zero);
       }
 #pragma unroll
       for (int u = 0; u < TD; u++)
 #pragma unroll
         for (int i = 0; i < NJ; i++) {
           SplitOp b;
-          b.x0 = b0[u][i]; b.x1 = b1[u][i]; b.xs = b0[u][i] + b1[u][i];
+          b.x0 = b0[u][i]; b.x1 = b1[u][i]; b.xs = add_alu(b0[u][i], b1[u][i], zero);
           acck_mac(acc[t][u], a[i], b);
         }
     }

@@ -122,23 +122,44 @@ PVW_DEV u64 acc_reduce(const Acc160& c, const LimbConst& lc) {
 struct SplitOp {
   u32 x0, x1, xs;
 };
-PVW_DEV SplitOp split_op(u64 x) {
+// 32-bit add pinned to the alu pipe: a plain `+` is often emitted as IMAD.IADD on the fma pipe, which the
+// multiply-accumulate loop saturates.  A three-input add can only be an IADD3; `z` is a run-time zero the compiler
+// cannot see through (LimbConst::pad).
+PVW_DEV u32 add_alu(u32 a, u32 b, u32 z) { return a + b + z; }
+PVW_DEV SplitOp split_op(u64 x, u32 z = 0) {
   SplitOp s;
   s.x0 = (u32)x & 0x7fffffffu;
   s.x1 = (u32)(x >> 31);
-  s.xs = s.x0 + s.x1;
+  s.xs = add_alu(s.x0, s.x1, z);
   return s;
 }
 struct AccK {
   u32 l0, l1, l2, h0, h1, h2, k0, k1, k2;
 };
 PVW_DEV void acck_zero(AccK& c) { c.l0 = c.l1 = c.l2 = c.h0 = c.h1 = c.h2 = c.k0 = c.k1 = c.k2 = 0; }
+// SPLIT_L: form L = a0*b0 with a plain IMAD.WIDE (no addend: 2 fma-pipe cycles instead of 4) and add it into the 96-bit
+// sum with three IADD3 on the otherwise idle alu pipe -- balances the two pipes (integer-pipe model)
+#ifndef PVW_SPLIT_L
+#define PVW_SPLIT_L 0
+#endif
 PVW_DEV void acck_mac(AccK& c, const SplitOp& a, const SplitOp& b) {
+#if PVW_SPLIT_L
+  {
+    u32 plo, phi;
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(plo), "=r"(phi) : "r"(a.x0), "r"(b.x0));
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, 0;\n\t"
+        : "+r"(c.l0), "+r"(c.l1), "+r"(c.l2)
+        : "r"(plo), "r"(phi));
+  }
+#else
   asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
       "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
       "addc.u32 %2, %2, 0;\n\t"
       : "+r"(c.l0), "+r"(c.l1), "+r"(c.l2)
       : "r"(a.x0), "r"(b.x0));
+#endif
   asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
       "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
       "addc.u32 %2, %2, 0;\n\t"
@@ -150,14 +171,35 @@ PVW_DEV void acck_mac(AccK& c, const SplitOp& a, const SplitOp& b) {
       : "+r"(c.k0), "+r"(c.k1), "+r"(c.k2)
       : "r"(a.xs), "r"(b.xs));
 }
-// canonical value of the accumulator mod q
+// canonical value of the accumulator mod q: recombine the three 96-bit sums into one 160-bit integer
+//   T = L + (K - L - H) * 2^31 + H * 2^62      (K - L - H = sum of the cross products >= 0)
+// with shifts and word adds, then two Barrett steps (10 wide multiplies instead of 34 for reducing L, H, K separately)
 PVW_DEV u64 acck_reduce(const AccK& c, const LimbConst& lc) {
-  const u64 L = reduce128(reduce64((u64)c.l2, lc), ((u64)c.l1 << 32) | c.l0, lc);
-  const u64 H = reduce128(reduce64((u64)c.h2, lc), ((u64)c.h1 << 32) | c.h0, lc);
-  const u64 K = reduce128(reduce64((u64)c.k2, lc), ((u64)c.k1 << 32) | c.k0, lc);
-  const u64 mid = submod(submod(K, L, lc.q), H, lc.q);
-  const u64 p31 = reduce64(1ull << 31, lc), p62 = reduce64(1ull << 62, lc);
-  return addmod(addmod(mulmod(H, p62, lc), mulmod(mid, p31, lc), lc.q), L, lc.q);
+  // mid = K - L - H, 96 bits
+  u32 m0, m1, m2;
+  asm("sub.cc.u32 %0, %3, %6;\n\t"
+      "subc.cc.u32 %1, %4, %7;\n\t"
+      "subc.u32 %2, %5, %8;\n\t"
+      "sub.cc.u32 %0, %0, %9;\n\t"
+      "subc.cc.u32 %1, %1, %10;\n\t"
+      "subc.u32 %2, %2, %11;\n\t"
+      : "=&r"(m0), "=&r"(m1), "=&r"(m2)
+      : "r"(c.k0), "r"(c.k1), "r"(c.k2), "r"(c.l0), "r"(c.l1), "r"(c.l2), "r"(c.h0), "r"(c.h1), "r"(c.h2));
+  // mid << 31 -> words s0..s3 ; H << 62 -> words t1..t4 (62 = 32 + 30)
+  const u32 s0 = m0 << 31, s1 = __funnelshift_l(m0, m1, 31), s2 = __funnelshift_l(m1, m2, 31), s3 = m2 >> 1;
+  const u32 t1 = c.h0 << 30, t2 = __funnelshift_l(c.h0, c.h1, 30), t3 = __funnelshift_l(c.h1, c.h2, 30), t4 = c.h2 >> 2;
+  u64 a = (u64)c.l0 + s0;
+  const u32 T0 = (u32)a; a >>= 32;
+  a += (u64)c.l1 + s1 + t1;
+  const u32 T1 = (u32)a; a >>= 32;
+  a += (u64)c.l2 + s2 + t2;
+  const u32 T2 = (u32)a; a >>= 32;
+  a += (u64)s3 + t3;
+  const u32 T3 = (u32)a; a >>= 32;
+  a += t4;  // < 2^32: T < 2^32 terms * 2^124
+  const u64 lo = ((u64)T1 << 32) | T0, hi = ((u64)T3 << 32) | T2;
+  const u64 h = reduce128(reduce64(a, lc), hi, lc);
+  return reduce128(h, lo, lc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

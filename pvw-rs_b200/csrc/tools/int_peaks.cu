@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(W::THREADS, NB) k_worker(u64* out, const u64* 
   for (int i = threadIdx.x; i < W::C::STAGE / 8; i += blockDim.x) w64[i] = packed ? pack_halves(in[i % 1024] >> 2) : (in[i % 1024] >> 2);
   __syncthreads();
   W wk;
-  wk.init(threadIdx.x);
+  wk.init(threadIdx.x, (u32)(in[1023] >> 63) & (u32)packed & 2u);
   for (int it = 0; it < iters; it++) wk.template chunk<true>(wsm, 0);
   u64 s = 0;
   const u32* w = reinterpret_cast<const u32*>(&wk.acc[0][0]);

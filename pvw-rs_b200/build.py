@@ -22,9 +22,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 def _digest() -> str:
     h = hashlib.sha256(" ".join(FLAGS).encode())
-    for root in (CSRC, os.path.join(HERE, "..", "include")):
+    for root in (CSRC, os.path.join(HERE, "..", "include"), os.path.join(HERE, "..", "examples")):
         for fn in sorted(os.listdir(root)):
-            if fn.endswith((".cu", ".cuh", ".hpp", ".h")):
+            if fn.endswith((".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 with open(os.path.join(root, fn), "rb") as f:
                     h.update(fn.encode())
                     h.update(f.read())
@@ -51,6 +51,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with cf.ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
     subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    # the C++ host-mirror example (include/pvw_b200.hpp) -- plain g++ against the C ABI
+    example = os.path.join(HERE, "..", "examples", "pvw.cpp")
+    if os.path.exists(example):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"), example, "-o",
+                               os.path.join(OBJ, "pvw_example"), "-L", HERE, "-lpvw_b200", "-Wl,-rpath," + HERE, "-pthread"])
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

@@ -15,7 +15,17 @@ struct TileCfg {
   static constexpr int GR = G / GD;
   static constexpr int RT = GR * TR;               // rows per CTA
   static constexpr int DT = GD * TD;               // dealers per CTA
-  static constexpr int ROWB = KC * ELL * 8 + 16;   // bytes per staged row (+16: dealer sub-tiles land on distinct banks)
+  // bytes per staged row: the pad staggers the (32/ELL) sub-tiles of a warp that read DIFFERENT rows (dealer sub-tiles
+  // when GD > 1, row sub-tiles otherwise) onto disjoint banks: a half-warp of 8-byte loads covers 128 bytes, so two
+  // neighbouring sub-tiles must sit 64 bytes apart modulo 128
+  static constexpr int STEP = GD > 1 ? TD : TR;  // staged rows between neighbouring sub-tiles of a warp
+  static constexpr int pick_pad() {
+    if (ELL != 8) return 16;
+    for (int pad = 16; pad <= 128; pad += 16)
+      if ((STEP * (KC * ELL * 8 + pad)) % 128 == 64) return pad;
+    return 16;
+  }
+  static constexpr int ROWB = KC * ELL * 8 + pick_pad();
   static constexpr int STAGE = (RT + DT) * ROWB;
   static_assert(G % GD == 0, "bad tile");
 };

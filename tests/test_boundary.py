@@ -64,3 +64,12 @@ def test_no_cpu_fallback(lib_path):
     assert ei.value.variant == "InvalidParameters"
     null = ctypes.c_void_p()
     assert pvw_rs_b200._ffi.load().pvw_ctx_synchronize(null) != 0
+
+
+def test_cpp_host_mirror_compiles(lib_path):
+    exe = os.path.join(ROOT, "pvw-rs_b200", "build", "pvw_example")
+    assert os.path.exists(exe)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout      # fails loudly without a device

@@ -140,3 +140,16 @@ def test_public_key_generation_matches_crs_product(pvw):
     with pytest.raises(pvw.PvwError) as ei:
         crs.multiply_by_randomness(r[:-1])
     assert ei.value.variant == "DimensionMismatch"
+
+
+def test_cpp_host_mirror_runs_the_reference_example():
+    """examples/pvw.cpp = examples/pvw.rs on include/pvw_b200.hpp (the compiled-code host layer over the C ABI)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "pvw-rs_b200", "build", "pvw_example")
+    assert os.path.exists(exe), "run python pvw-rs_b200/build.py"
+    for args in ([], ["10", "4", "16"], ["13", "5", "8"]):      # example default; tests/crypto.rs:236-305 shape; ragged
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "ALL CHECKS PASSED" in r.stdout and "(100.0 %)" in r.stdout

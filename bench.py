@@ -327,15 +327,25 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    int_peak = None
+    try:
+        int_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")))["mac_karatsuba_per_s"])
+    except Exception:
+        pass
+    mac_rate = (mac_bytes / ((k + 1.0) * 8)) * k / (mac_ms * 1e-3) if mac_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "mac_gemm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback", "traffic": traffic,
                 "launches_per_step": mac_n / args.steps, "avg_launch_ms": mac_ms / max(mac_n, 1),
                 "algorithmic_bytes_per_launch": mac_bytes / max(mac_n, 1),
                 "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": round(mac_ms / ms_total, 4),
-                "modmuladds_per_s": (mac_bytes / ((k + 1.0) * 8)) * k / (mac_ms * 1e-3) if mac_ms > 0 else 0.0,
+                "modmuladds_per_s": mac_rate,
+                "integer_pipe": {"achieved": mac_rate, "peak": int_peak, "unit": "62-bit modular multiply-accumulates/s",
+                                 "frac": (mac_rate / int_peak) if int_peak else None,
+                                 "peak_source": "measured on B200 with csrc/tools/int_peaks.cu (3 IMAD.WIDE + carries per MAC, register "
+                                                "resident; profiles/r01_int_peaks.json)"},
                 "note": "dealer tiling re-uses each B / c1 tile from shared memory for several dealers, so the kernel is bound by the "
-                        "integer pipe (4 IMAD.WIDE per 62-bit multiply-accumulate) and moves fewer DRAM bytes than the algorithmic "
-                        "figure; frac > 1 is therefore possible (DESIGN.md)"}
+                        "fma-heavy integer pipe (3 IMAD.WIDE per 62-bit multiply-accumulate, ncu sm__pipe_fmaheavy 75 %) and moves far "
+                        "fewer DRAM bytes (`traffic`) than the algorithmic figure; frac > 1 is therefore possible (DESIGN.md 4)"}
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample -------------------------------------------------
     cpu = None

@@ -70,68 +70,86 @@ void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_d
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// (2) thread = (share, value i): acc = sum_j y_j * (Q/q_j)  (< L*Q, NWT+1 words in registers), then mod Q by
-//     conditional subtraction of Q << b.  Q/q_j words are uniform across the warp (broadcast loads).
+// (2) thread = (share, value i): acc = sum_j y_j * (Q/q_j) (< L*Q) as 32-bit words in registers, then mod Q by
+//     conditional subtraction of Q << b.  Row-by-word products run as carry chains (mad.lo.cc / madc.hi.cc ->
+//     IMAD.WIDE with carry, even and odd columns separately so that every product lands on an aligned word pair);
+//     the Q/q_j rows live in shared memory (uniform across the block).
 // ---------------------------------------------------------------------------------------------------------------
+template <int W, int OFF, int N>
+PVW_DEV void mul_row_acc(u32 (&acc)[N], u32 m, const u32 (&q)[W]) {
+  static_assert(W % 2 == 0 && OFF + W + 1 < N, "accumulator too short");
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[OFF]), "+r"(acc[OFF + 1]) : "r"(m), "r"(q[0]));
+#pragma unroll
+  for (int i = 2; i < W; i += 2)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[OFF + i]), "+r"(acc[OFF + i + 1]) : "r"(m), "r"(q[i]));
+  asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[OFF + W]));
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[OFF + 1]), "+r"(acc[OFF + 2]) : "r"(m), "r"(q[1]));
+#pragma unroll
+  for (int i = 3; i < W; i += 2)
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[OFF + i]), "+r"(acc[OFF + i + 1]) : "r"(m), "r"(q[i]));
+  asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[OFF + W + 1]));
+}
+
 template <int NWT>
 __global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y, u64* __restrict__ X, uint64_t S, uint32_t L, uint32_t ellp1,
                                                        uint32_t NW, const u64* __restrict__ qhat, const u64* __restrict__ Qsh, uint32_t LB) {
+  constexpr int W = 2 * NWT;   // 32-bit words of one Q/q_j row
+  constexpr int N = W + 3;     // accumulator words: the sum is < L*Q < 2^(32 W + 7)
+  extern __shared__ __align__(16) u32 s_q[];  // [L][W] then [LB][W + 2]
+  {
+    const u32* g = reinterpret_cast<const u32*>(qhat);
+    for (uint32_t i = threadIdx.x; i < L * W; i += blockDim.x) s_q[i] = g[i];
+    const u32* gs = reinterpret_cast<const u32*>(Qsh);
+    for (uint32_t i = threadIdx.x; i < LB * (W + 2); i += blockDim.x) s_q[L * W + i] = gs[i];
+  }
+  __syncthreads();
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = blockIdx.y;
   if (s >= S) return;
-  u64 acc[NWT + 1];
+  u32 acc[N];
 #pragma unroll
-  for (int w = 0; w <= NWT; w++) acc[w] = 0;
+  for (int w = 0; w < N; w++) acc[w] = 0;
   for (uint32_t j = 0; j < L; j++) {
     const u64 yv = y[((size_t)j * ellp1 + i) * S + s];
-    const u64* qh = qhat + (size_t)j * NWT;
-    u64 carry = 0;
+    u32 q[W];
+    const uint2* row = reinterpret_cast<const uint2*>(s_q + (size_t)j * W);
 #pragma unroll
-    for (int w = 0; w < NWT; w++) {
-      const u64 qw = qh[w];
-      const u64 lo = yv * qw, hi = __umul64hi(yv, qw);
-      u64 t = acc[w] + carry;
-      const u64 c1 = t < carry;
-      t += lo;
-      const u64 c2 = t < lo;
-      acc[w] = t;
-      carry = hi + c1 + c2;  // hi <= 2^64 - 2, so no overflow
-    }
-    acc[NWT] += carry;
+    for (int w = 0; w < NWT; w++) { const uint2 v = row[w]; q[2 * w] = v.x; q[2 * w + 1] = v.y; }
+    mul_row_acc<W, 0>(acc, (u32)yv, q);
+    mul_row_acc<W, 1>(acc, (u32)(yv >> 32), q);
   }
   for (int b = (int)LB - 1; b >= 0; b--) {
-    const u64* qs = Qsh + (size_t)b * (NWT + 1);
-    bool ge = true;  // acc >= Q<<b ?
+    const u32* qs = s_q + (size_t)L * W + (size_t)b * (W + 2);
+    // borrow of acc - (Q << b) without storing the difference
+    u32 t, borrow;
+    asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(t) : "r"(acc[0]), "r"(qs[0]));
 #pragma unroll
-    for (int w = NWT; w >= 0; w--) {
-      const u64 qw = qs[w];
-      if (acc[w] != qw) { ge = acc[w] > qw; break; }
-    }
-    if (ge) {
-      u64 borrow = 0;
+    for (int w = 1; w < W + 2; w++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(t) : "r"(acc[w]), "r"(qs[w]));
+    asm volatile("subc.u32 %0, 0, 0;" : "=r"(borrow));
+    if (borrow == 0) {  // acc >= Q << b
+      asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(acc[0]) : "r"(qs[0]));
 #pragma unroll
-      for (int w = 0; w <= NWT; w++) {
-        const u64 qw = qs[w];
-        const u64 d1 = acc[w] - qw, b1 = acc[w] < qw;
-        const u64 d2 = d1 - borrow, b2 = d1 < borrow;
-        acc[w] = d2;
-        borrow = b1 | b2;
-      }
+      for (int w = 1; w < W + 2; w++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(acc[w]) : "r"(qs[w]));
     }
   }
   u64* xo = X + ((size_t)i * NW) * S + s;
 #pragma unroll
   for (int w = 0; w < NWT; w++)
-    if (w < (int)NW) xo[(size_t)w * S] = acc[w];
+    if (w < (int)NW) xo[(size_t)w * S] = ((u64)acc[2 * w + 1] << 32) | acc[2 * w];
 }
 
 void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st) {
   if (S == 0) return;
   dim3 grid((unsigned)((S + 127) / 128), T.ell + 1);
-#define PVW_LIFT_CASE(N)                                                                                     \
-  case N:                                                                                                    \
-    crt_lift_kernel<N><<<grid, 128, 0, st>>>(y, X, S, T.L, T.ell + 1, T.NW, T.qhat, T.Qsh, T.LB);          \
-    break;
+  const size_t smem = ((size_t)T.L * 2 * T.NWT + (size_t)T.LB * (2 * T.NWT + 2)) * 4;
+#define PVW_LIFT_CASE(N)                                                                                              \
+  case N: {                                                                                                           \
+    auto kern = crt_lift_kernel<N>;                                                                                   \
+    static bool attr = false;                                                                                         \
+    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }  \
+    kern<<<grid, 128, smem, st>>>(y, X, S, T.L, T.ell + 1, T.NW, T.qhat, T.Qsh, T.LB);                                \
+    break;                                                                                                            \
+  }
   switch (T.NWT) {
     PVW_LIFT_CASE(2)
     PVW_LIFT_CASE(4)

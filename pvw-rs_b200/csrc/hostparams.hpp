@@ -195,7 +195,7 @@ struct HostParams {
   BigU Q, delta, delta_pow;                 // parameters.rs:151-163
   uint32_t NW = 0;                           // words of Q
   std::vector<LimbConst> lc;                 // [L]
-  std::vector<uint64_t> tw, tw_sh, twi, twi_sh, gadget_hat;  // [L][ell] each
+  std::vector<uint64_t> tw, tw_sh, twi, twi_sh, gadget_hat, gadget_hat_sh;  // [L][ell] each
   // CRT lift: qhat[j] = Q / q_j  ([L][NW]),  Qsh[b] = Q << b  ([LB][NW+1])
   std::vector<uint64_t> qhat, Qsh; uint32_t LB = 0;
   // decode tail constants (NW words each unless noted)
@@ -263,7 +263,7 @@ struct HostParams {
     NW = (uint32_t)Q.w.size();
 
     lc.resize(L);
-    tw.assign((size_t)L * ell, 0); tw_sh = tw; twi = tw; twi_sh = tw; gadget_hat = tw;
+    tw.assign((size_t)L * ell, 0); tw_sh = tw; twi = tw; twi_sh = tw; gadget_hat = tw; gadget_hat_sh = tw;
     qhat.assign((size_t)L * NW, 0);
     for (uint32_t j = 0; j < L; j++) {
       uint64_t q = moduli[j]; LimbConst& c = lc[j];
@@ -289,6 +289,7 @@ struct HostParams {
       uint64_t* g = &gadget_hat[(size_t)j * ell]; uint64_t pw = 1 % q;
       for (uint32_t t = 0; t < ell; t++) { g[t] = pw; pw = h_mulmod(pw, c.delta, q); }
       host_ntt_fwd(g, j);
+      for (uint32_t t = 0; t < ell; t++) gadget_hat_sh[(size_t)j * ell + t] = h_shoup(g[t], q);
     }
     LB = 1; while ((1u << LB) <= L) LB++;
     Qsh.assign((size_t)LB * (NW + 1), 0);

@@ -20,6 +20,7 @@ struct DevTables {
   const u64* twi;          // [L][ell] psi^-brv(i)                    (inverse NTT)
   const u64* twi_sh;
   const u64* gadget_hat;   // [L][ell] NTT([1, D, .., D^(l-1)] mod q) (parameters.rs:288-308)
+  const u64* gadget_hat_sh;  //        Shoup companions
   // CRT lift
   const u64* qhat;         // [L][NWT]   Q/q_j, zero padded to the template width
   const u64* Qsh;          // [LB][NWT+1] Q << b

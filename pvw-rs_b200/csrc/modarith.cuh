@@ -58,10 +58,9 @@ PVW_DEV u64 mulmod_shoup(u64 a, u64 w, u64 w_sh, u64 q) {
 }
 // i64 -> canonical residue: ((x % q) + q) % q   (parameters.rs:437-452, Poly::from_coefficients)
 PVW_DEV u64 reduce_i64(long long x, const LimbConst& c) {
-  if (x >= 0) return reduce64((u64)x, c);
-  u64 m = (u64)(-(x + 1)) + 1ull;
-  u64 r = reduce64(m, c);
-  return r ? c.q - r : 0;
+  const u64 m = x >= 0 ? (u64)x : (u64)(-(x + 1)) + 1ull;  // |x| without overflow
+  const u64 r = m < c.q ? m : reduce64(m, c);              // secrets / errors are tiny: no multiply on the common path
+  return (x >= 0 || r == 0) ? r : c.q - r;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

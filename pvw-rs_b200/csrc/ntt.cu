@@ -14,13 +14,15 @@ template <int ELL>
 __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
-                                                        const u64* __restrict__ tw_sh, const u64* __restrict__ gadget_hat) {
-  __shared__ u64 s_tw[ELL], s_tw_sh[ELL], s_g[ELL];
+                                                        const u64* __restrict__ tw_sh, const u64* __restrict__ gadget_hat,
+                                                        const u64* __restrict__ gadget_hat_sh) {
+  __shared__ u64 s_tw[ELL], s_tw_sh[ELL], s_g[ELL], s_g_sh[ELL];
   const uint32_t limb = blockIdx.y;
   if (threadIdx.x < ELL) {
     s_tw[threadIdx.x] = tw[(size_t)limb * ELL + threadIdx.x];
     s_tw_sh[threadIdx.x] = tw_sh[(size_t)limb * ELL + threadIdx.x];
     s_g[threadIdx.x] = gadget_hat[(size_t)limb * ELL + threadIdx.x];
+    s_g_sh[threadIdx.x] = gadget_hat_sh[(size_t)limb * ELL + threadIdx.x];
   }
   __syncthreads();
   const LimbConst lc = lcs[limb];
@@ -38,7 +40,7 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   if (m != nullptr) {
     u64 mr = reduce_i64((long long)m[idx], lc);  // `scalars[p] as i64`, encryption.rs:195
 #pragma unroll
-    for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], mulmod(mr, s_g[t], lc), lc.q);
+    for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], mulmod_shoup(mr, s_g[t], s_g_sh[t], lc.q), lc.q);
   }
   uint64_t vec = idx / inner, j = idx % inner;
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
@@ -52,7 +54,7 @@ void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, u
   dim3 grid((unsigned)((count + 127) / 128), T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
-    ntt_small_kernel<E><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat); \
+    ntt_small_kernel<E><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh); \
     break;
   switch (T.ell) {
     PVW_NTT_CASE(8)

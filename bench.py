@@ -152,7 +152,7 @@ def run_reference(args):
                        "the Rust crate and its fhe-math dependency cannot be built in this image"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": co.threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -383,9 +383,31 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roofline, "cpu_baseline": cpu,
             "hbm_roof_shares_per_s": peak * 1e9 / bytes_per_share(n) * world}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.  Route fd 1 to
+    stderr for the whole run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -407,6 +429,7 @@ def main():
                    "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
             raise SystemExit(subprocess.call(cmd))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -133,6 +133,7 @@ void upload_tables(pvw_ctx* c) {
   T.L = L; T.ell = ell; T.NW = NW; T.NWT = NWT; T.LB = LB;
   T.divM_n = hp.divM.n; T.divM_shift = hp.divM.shift; T.divM_vinv = hp.divM.vinv;
   T.div2D_n = hp.div2D.n; T.div2D_shift = hp.div2D.shift; T.div2D_vinv = hp.div2D.vinv;
+  T.tail_impl = 1;
 }
 
 void check_launch(pvw_ctx* c, size_t n = 1) {
@@ -660,6 +661,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     if (n == "gemm_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0 or 1"); c->gemm_impl = (int)value; }
     else if (n == "gemm_tile") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0 or 1"); c->gemm_tile = (int)value; }
     else if (n == "refill_lag") { require(value >= 1 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..3"); c->refill_lag = (int)value; }
+    else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }
     else if (n == "profile") {

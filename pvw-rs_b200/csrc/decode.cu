@@ -339,10 +339,258 @@ __global__ void __launch_bounds__(128) decode_tail_kernel(const u64* __restrict_
   out[p * out_ps + d] = result;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// (3') the same tail with every multi-precision value in registers: sizes are template parameters (NW words of Q,
+//      NM words of M = D^(l-1), ND words of 2D), loops fully unrolled, constants broadcast from shared memory.
+//      Quotient digits that are provably zero (top words of the running remainder) are skipped, so a share whose
+//      noise is small costs a few digit steps while arbitrary inputs still take the full Knuth D path.
+//      Bit-identical to decode_tail_kernel (tests/test_gpu_parity.py runs both on the same inputs).
+// ---------------------------------------------------------------------------------------------------------------
+struct TailConst {  // offsets (in u64 words) into the shared constant block
+  int Q, halfQ, M, halfM, D, vM, v2D;
+};
+
+template <int N>
+PVW_DEV bool gt_n(const u64 (&a)[N], const u64* b) {  // a > b
+  bool gt = false, decided = false;
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    const u64 bw = b[i];
+    if (!decided && a[i] != bw) { gt = a[i] > bw; decided = true; }
+  }
+  return gt;
+}
+template <int N>
+PVW_DEV void rsub_n(u64 (&a)[N], const u64* b) {  // a = b - a
+  u64 borrow = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const u64 bw = b[i], d1 = bw - a[i], b1 = bw < a[i], d2 = d1 - borrow, b2 = d1 < borrow;
+    a[i] = d2;
+    borrow = b1 | b2;
+  }
+}
+template <int N>
+PVW_DEV bool is_zero_n(const u64 (&a)[N]) {
+  u64 o = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) o |= a[i];
+  return o == 0;
+}
+// Knuth D on a normalised dividend un[NU+1] (in place; remainder left in un[0..NV), still shifted) by the normalised
+// divisor v[NV]; q[NU-NV+1] receives the quotient.
+template <int NU, int NV>
+PVW_DEV void divrem_fixed(u64 (&un)[NU + 1], const u64* v, u64 vinv, u64 (&q)[NU - NV + 1]) {
+  const u64 vt = v[NV - 1];
+#pragma unroll
+  for (int j = NU - NV; j >= 0; j--) {
+    const u64 u1 = un[j + NV], u0 = un[j + NV - 1];
+    if (u1 == 0 && u0 < vt) { q[j] = 0; continue; }  // digit is 0: (u1, u0, ...) < v
+    u64 qhat, rhat;
+    bool rhat_ovf = false;
+    if (u1 >= vt) {
+      qhat = ~0ull;
+      rhat = u0 + vt;
+      rhat_ovf = rhat < u0;
+    } else {
+      qhat = div_2by1(u1, u0, vt, vinv, &rhat);
+    }
+    if (NV >= 2) {
+      const u64 v2 = v[NV - 2], u2 = un[j + NV - 2];
+      while (!rhat_ovf) {
+        const u64 ph = __umul64hi(qhat, v2), pl = qhat * v2;
+        if (ph > rhat || (ph == rhat && pl > u2)) {
+          qhat--;
+          const u64 nr = rhat + vt;
+          rhat_ovf = nr < rhat;
+          rhat = nr;
+        } else {
+          break;
+        }
+      }
+    }
+    u64 carry = 0, borrow = 0;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const u64 vw = v[i];
+      const u64 pl = qhat * vw, ph = __umul64hi(qhat, vw);
+      const u64 lo = pl + carry;
+      carry = ph + (lo < pl);
+      const u64 x = un[i + j];
+      const u64 d1 = x - lo, b1 = x < lo;
+      const u64 d2 = d1 - borrow, b2 = d1 < borrow;
+      un[i + j] = d2;
+      borrow = b1 | b2;
+    }
+    {
+      const u64 x = un[j + NV];
+      const u64 d1 = x - carry, b1 = x < carry;
+      const u64 d2 = d1 - borrow, b2 = d1 < borrow;
+      un[j + NV] = d2;
+      borrow = b1 | b2;
+    }
+    if (borrow) {
+      qhat--;
+      u64 c = 0;
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        const u64 vw = v[i];
+        const u64 s1 = un[i + j] + vw, c1 = s1 < vw;
+        const u64 s2 = s1 + c, c2 = s2 < c;
+        un[i + j] = s2;
+        c = c1 | c2;
+      }
+      un[j + NV] += c;
+    }
+    q[j] = qhat;
+  }
+}
+
+template <int NW, int NM, int ND>
+__global__ void __launch_bounds__(128) decode_tail_fixed_kernel(const u64* __restrict__ X, uint64_t S, uint32_t Pc, uint32_t ell, u64* __restrict__ out,
+                                                                size_t out_ps, const DevTables T) {
+  __shared__ u64 sc[5 * NW + NM + ND];
+  const u64* cQ = sc; const u64* cHQ = sc + NW; const u64* cM = sc + 2 * NW; const u64* cHM = sc + 3 * NW; const u64* cD = sc + 4 * NW;
+  const u64* cvM = sc + 5 * NW; const u64* cv2D = sc + 5 * NW + NM;
+  for (int i = threadIdx.x; i < 5 * NW + NM + ND; i += blockDim.x) {
+    const u64* src = i < NW ? T.Qw + i : i < 2 * NW ? T.halfQ + (i - NW) : i < 3 * NW ? T.Mw + (i - 2 * NW) : i < 4 * NW ? T.halfM + (i - 3 * NW)
+                     : i < 5 * NW ? T.Dw + (i - 4 * NW) : i < 5 * NW + NM ? T.divM_v + (i - 5 * NW) : T.div2D_v + (i - 5 * NW - NM);
+    sc[i] = *src;
+  }
+  __syncthreads();
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int shM = (int)T.divM_shift, sh2D = (int)T.div2D_shift;
+  u64 noise[NW];
+  // ---- last component: centred remainder modulo M (reduce_modulo_poly, decryption.rs:154-178)
+  {
+    u64 cur[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) cur[w] = X[((size_t)(ell - 1) * NW + w) * S + s];
+    const bool neg = gt_n<NW>(cur, cHQ);
+    if (neg) rsub_n<NW>(cur, cQ);                 // |centre(last)|
+    u64 un[NW + 1];
+    un[NW] = shM ? cur[NW - 1] >> (64 - shM) : 0;
+#pragma unroll
+    for (int i = NW - 1; i > 0; i--) un[i] = shM ? (cur[i] << shM) | (cur[i - 1] >> (64 - shM)) : cur[i];
+    un[0] = cur[0] << shM;
+    u64 q[NW - NM + 1];
+    divrem_fixed<NW, NM>(un, cvM, T.divM_vinv, q);
+    u64 rem[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) rem[i] = i < NM ? (shM ? (un[i] >> shM) | (un[i + 1] << (64 - shM)) : un[i]) : 0;
+    bool rneg = neg;
+    if (gt_n<NW>(rem, cHM)) { rsub_n<NW>(rem, cM); rneg = !neg; }
+    if (is_zero_n<NW>(rem)) rneg = false;
+    if (rneg) rsub_n<NW>(rem, cQ);                // signed value -> [0, Q) (bigints_to_poly, parameters.rs:437-452)
+#pragma unroll
+    for (int w = 0; w < NW; w++) noise[w] = rem[w];
+  }
+  // ---- back-substitution noise_i = round((noise_{i+1} - tmp_i) / D)  (decryption.rs:44-48, :180-207)
+  for (int i = (int)ell - 2; i >= 0; i--) {
+    u64 num[NW + 2];
+    u64 borrow = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {                // noise - tmp_i
+      const u64 c = X[((size_t)i * NW + w) * S + s];
+      const u64 d1 = noise[w] - c, b1 = noise[w] < c, d2 = d1 - borrow, b2 = d1 < borrow;
+      num[w] = d2;
+      borrow = b1 | b2;
+    }
+    if (borrow) {                                  // ... mod Q
+      u64 c = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        const u64 qw = cQ[w], s1 = num[w] + qw, c1 = s1 < qw, s2 = s1 + c, c2 = s2 < c;
+        num[w] = s2;
+        c = c1 | c2;
+      }
+    }
+    bool nneg;
+    {
+      u64 t[NW];
+#pragma unroll
+      for (int w = 0; w < NW; w++) t[w] = num[w];
+      nneg = gt_n<NW>(t, cHQ);
+      if (nneg) rsub_n<NW>(t, cQ);
+      // 2|num| + D, NW+1 words, then normalise by the shift of 2D
+      u64 c = 0, carry = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        const u64 x = (t[w] << 1) | c;
+        c = t[w] >> 63;
+        const u64 dw = cD[w], s1 = x + dw, c1 = s1 < dw, s2 = s1 + carry, c2 = s2 < carry;
+        num[w] = s2;
+        carry = c1 | c2;
+      }
+      num[NW] = c + carry;
+    }
+    num[NW + 1] = sh2D ? num[NW] >> (64 - sh2D) : 0;
+#pragma unroll
+    for (int w = NW; w > 0; w--) num[w] = sh2D ? (num[w] << sh2D) | (num[w - 1] >> (64 - sh2D)) : num[w];
+    num[0] = num[0] << sh2D;
+    u64 q[NW + 1 - ND + 1];
+    divrem_fixed<NW + 1, ND>(num, cv2D, T.div2D_vinv, q);
+    // quotient < Q: NW words are enough
+    u64 qq[NW];
+    bool qzero = true;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { qq[w] = w < NW + 1 - ND + 1 ? q[w] : 0; qzero = qzero && qq[w] == 0; }
+    if (nneg && !qzero) rsub_n<NW>(qq, cQ);
+#pragma unroll
+    for (int w = 0; w < NW; w++) noise[w] = qq[w];
+  }
+  // ---- plaintext = (-z_0) - noise_0 mod Q, centred, then extract_constant_term_as_u64 (decryption.rs:226-247)
+  u64 num[NW];
+  {
+    u64 borrow = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      const u64 c = X[((size_t)ell * NW + w) * S + s];
+      const u64 d1 = c - noise[w], b1 = c < noise[w], d2 = d1 - borrow, b2 = d1 < borrow;
+      num[w] = d2;
+      borrow = b1 | b2;
+    }
+    if (borrow) {
+      u64 c = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        const u64 qw = cQ[w], s1 = num[w] + qw, c1 = s1 < qw, s2 = s1 + c, c2 = s2 < c;
+        num[w] = s2;
+        c = c1 | c2;
+      }
+    }
+  }
+  u64 result;
+  bool fits = true;
+#pragma unroll
+  for (int w = 1; w < NW; w++) fits = fits && num[w] == 0;
+  if (gt_n<NW>(num, cHQ)) {                        // negative: value = num - Q
+    u64 mag[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) mag[w] = num[w];
+    rsub_n<NW>(mag, cQ);
+    bool small = mag[0] <= 1000;
+#pragma unroll
+    for (int w = 1; w < NW; w++) small = small && mag[w] == 0;
+    result = small ? 0 : (fits ? num[0] : 0);
+  } else {
+    result = fits ? num[0] : 0;
+  }
+  const uint64_t d = s / Pc, p = s % Pc;
+  out[p * out_ps + d] = result;
+}
+
 void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t D, u64* out, size_t out_ps, cudaStream_t st) {
   const uint64_t S = (uint64_t)Pc * D;
   if (S == 0) return;
-  decode_tail_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T);
+  const unsigned blocks = (unsigned)((S + 127) / 128);
+  if (T.tail_impl != 0) {  // register-resident specialisations for the 128- and 256-bit parameter shapes
+    if (T.NW == 17 && T.divM_n == 15 && T.div2D_n == 3) { decode_tail_fixed_kernel<17, 15, 3><<<blocks, 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T); return; }
+    if (T.NW == 33 && T.divM_n == 31 && T.div2D_n == 3) { decode_tail_fixed_kernel<33, 31, 3><<<blocks, 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T); return; }
+    if (T.NW == 4 && T.divM_n == 4 && T.div2D_n == 1) { decode_tail_fixed_kernel<4, 4, 1><<<blocks, 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T); return; }
+  }
+  decode_tail_kernel<<<blocks, 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T);
 }
 
 size_t decode_scratch_words_y(const DevTables& T, uint64_t S) { return (size_t)T.L * (T.ell + 1) * S; }

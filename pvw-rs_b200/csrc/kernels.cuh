@@ -30,6 +30,7 @@ struct DevTables {
   uint32_t L, ell, NW, NWT, LB;
   uint32_t divM_n, divM_shift, div2D_n, div2D_shift;
   u64 divM_vinv, div2D_vinv;
+  int tail_impl;  // 1 = register-resident decode tail where a specialisation exists, 0 = generic kernel
 };
 
 // ---- ntt.cu -------------------------------------------------------------------------------------------------

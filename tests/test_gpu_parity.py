@@ -137,7 +137,10 @@ def test_decode_of_arbitrary_polynomials(pkg, name):
     for i, m in enumerate([-1001, -1000, -999, -1, 0, 1, 2 ** 63 - 1, -(2 ** 63)]):
         enc = co.encode_scalar(m & (2 ** 64 - 1))
         z[2 + i] = (np.array(P.moduli, dtype=np.uint64)[:, None] - enc) % np.array(P.moduli, dtype=np.uint64)[:, None]
-    assert (eng.decode_batch(z) == co.decode(z)).all()
+    want = co.decode(z)
+    for impl in (1, 0):                                   # register-resident specialisation (where one exists) and generic tail
+        eng.set_option("tail_impl", impl)
+        assert (eng.decode_batch(z) == want).all(), f"tail_impl={impl}"
 
 
 @pytest.mark.parametrize("name", ["EX", "RAG", "T16"])

@@ -174,17 +174,18 @@ void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
   const int tile = a.tile;
   switch (a.ell) {
     case 8:
-      if (matvec) launch_cfg<8, 4, 1, 1, 4, 2>(a, impl, st);
+      if (matvec && tile == 0) launch_cfg<8, 2, 1, 1, 8, 1>(a, impl, st);
+      else if (matvec) launch_cfg<8, 1, 1, 1, 16, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<8, 4, 4, 4, 8, 1>(a, impl, st);
       else launch_cfg<8, 4, 2, 4, 8, 2>(a, impl, st);
       break;
     case 16:
-      if (matvec) launch_cfg<16, 4, 1, 1, 4, 2>(a, impl, st);
+      if (matvec) launch_cfg<16, 2, 1, 1, 8, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<16, 4, 4, 4, 8, 1>(a, impl, st);
       else launch_cfg<16, 4, 2, 4, 8, 2>(a, impl, st);
       break;
     case 32:
-      if (matvec) launch_cfg<32, 4, 1, 1, 4, 2>(a, impl, st);
+      if (matvec) launch_cfg<32, 4, 1, 1, 4, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<32, 4, 4, 2, 4, 1>(a, impl, st);
       else launch_cfg<32, 4, 2, 2, 4, 2>(a, impl, st);
       break;

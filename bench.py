@@ -245,10 +245,13 @@ def run_b200(args):
     n_m, n_r, n_e1, n_e2, n_sk = (t.numpy() for t in (h_m, h_r, h_e1, h_e2, h_sk))
     n_m = n_m.view(np.uint64)
 
+    h_out = torch.empty((nrows, D), dtype=torch.int64).pin_memory()
+    n_out = h_out.numpy().view(np.uint64)
+
     def step_host():
         eng.encrypt_batch(0, n_m, n_r, n_e1, n_e2, c1_range=(c1_lo, c1_hi))
         gather_c1()
-        return eng.decrypt_batch(parties, n_sk, D=D)
+        return eng.decrypt_batch(parties, n_sk, D=D, out=n_out)
 
     def barrier():
         if world > 1:
@@ -357,11 +360,28 @@ def run_b200(args):
     except Exception:
         pass
     mac_rate = (mac_bytes / ((k + 1.0) * 8)) * k / (mac_ms * 1e-3) if mac_ms > 0 else 0.0
+    # NTT kernel against the measured Shoup modular-multiply rate: forward butterflies + gadget multiplies per step
+    shoup_peak = None
+    try:
+        for ln in open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")):
+            if "mulmod_shoup_per_s" in ln:
+                shoup_peak = float(json.loads(ln)["mulmod_shoup_per_s"])
+    except Exception:
+        pass
+    ntt_ms, ntt_n, _ = prof["ntt_small"]
+    polys = args.steps * (D * k + (c1_hi - c1_lo) * k + D * nrows + nrows * k)          # r, e1 slice, e2 (+m), sk
+    log2l = l.bit_length() - 1
+    ntt_mulmods = polys * L * ((l // 2) * log2l) + args.steps * D * nrows * L * l        # butterflies + m * g_hat
+    ntt_rate = ntt_mulmods / (ntt_ms * 1e-3) if ntt_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "mac_gemm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback", "traffic": traffic,
                 "launches_per_step": mac_n / args.steps, "avg_launch_ms": mac_ms / max(mac_n, 1),
                 "algorithmic_bytes_per_launch": mac_bytes / max(mac_n, 1),
                 "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": round(mac_ms / ms_total, 4),
+                "ntt": {"kernel": "ntt_small", "achieved": ntt_rate, "peak": shoup_peak, "unit": "Shoup modular multiplies/s",
+                        "frac": (ntt_rate / shoup_peak) if shoup_peak else None,
+                        "what": "forward butterflies + gadget multiplies of r, e1, e2, sk per step over the kernel's event time; peak = "
+                                "register-resident mulmod_shoup loop (profiles/r01_int_peaks.json)"},
                 "single_call": {"what": "D = 1 (one reference-style encrypt call / one all-party decrypt pass): HBM-bound matrix-vector "
                                         "form of the same kernel, L2 flushed between calls, rows = %d" % nrows,
                                 **{kname: dict(v, frac=v["achieved_GBps"] / peak) for kname, v in (single or {}).items()}},

@@ -64,6 +64,9 @@ struct pvw_ctx {
   int device = 0;
   uint32_t row0 = 0, nrows = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host<->device staging copies of the host-pointer calls, overlapped with kernels
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_ev;
   DevTables T{};
   DevBuf tables;                 // one allocation holding every constant table
   DevBuf A, At, B;
@@ -181,6 +184,16 @@ const void* stage_in(pvw_ctx* c, DevBuf& buf, const void* src, size_t bytes, uin
   return buf.p;
 }
 
+// host-pointer calls: the same copy, but on the copy stream, so that it overlaps kernels already queued on the compute
+// stream; `ready` is recorded after it and the consumer makes the compute stream wait for it
+const void* stage_in_overlapped(pvw_ctx* c, DevBuf& buf, const void* src, size_t bytes, uint32_t flags, cudaEvent_t ready) {
+  if (flags & PVW_IO_DEVICE) return src;
+  buf.ensure(bytes);
+  CUDA_CHECK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  CUDA_CHECK(cudaEventRecord(ready, c->copy_stream));
+  return buf.p;
+}
+
 // host-layout polynomials [count][L][ell]  <->  limb-major [L][count][ell] slice inside a bigger array
 void to_limb_major(pvw_ctx* c, const u64* in_host_layout, uint64_t count, u64* out, size_t out_limb_stride) {
   const uint32_t L = c->hp.L, ell = c->hp.ell;
@@ -280,6 +293,8 @@ int pvw_ctx_create(pvw_ctx** out, const pvw_params_desc* d) {
     c->device = d->device;
     c->use();
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     upload_tables(c);
     *out = c;
     return PVW_OK;
@@ -299,6 +314,9 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->chunk_ev) cudaEventDestroy(e);
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
@@ -478,7 +496,15 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS,
             fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
     const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const bool host = !(flags & PVW_IO_DEVICE);
+    // copy order matters (one host-to-device DMA queue): the small inputs the first kernels need go first, then the big
+    // ones (e2, m) on the copy stream, waited for only after the c2 product
     const long long* d_r = (const long long*)stage_in(c, c->in_small, r, (size_t)D * k * ell * 8, flags);
+    const long long* d_e1 = nullptr;
+    if (c1_hi > c1_lo)
+      d_e1 = (const long long*)stage_in(c, c->in_small2, e1 + (size_t)c1_lo * k * ell, (size_t)(c1_hi - c1_lo) * k * ell * 8, flags);
+    const long long* d_e2 = (const long long*)stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags, c->ev[0]);
+    const u64* d_m = (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]);
     // r_hat[d][limb][j][ell]   (encryption.rs:147-154)
     c->rhat.ensure((size_t)D * w1 * 8);
     launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream); });
@@ -486,8 +512,6 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
     if (c1_hi > c1_lo) {
       const uint32_t Dc = c1_hi - c1_lo;
-      const int64_t* e1p = e1 + (size_t)c1_lo * k * ell;
-      const long long* d_e1 = (const long long*)stage_in(c, c->in_small2, e1p, (size_t)Dc * k * ell * 8, flags);
       // c1 <- NTT(e1)   (encryption.rs:161-167), then c1 += A r_hat   (crs.rs:187-199, encryption.rs:171-173)
       launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)Dc * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream); });
       GemmArgs g{};
@@ -498,16 +522,22 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       gemm(c, g);
     }
     {
-      // c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
-      const long long* d_e2 = (const long long*)stage_in(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags);
-      const u64* d_m = (const u64*)stage_in(c, c->in_m, m, (size_t)D * nrows * 8, flags);
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream); });
+      // device inputs: c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
+      // host inputs:   c2 <- B r_hat first (it does not need e2 / m, whose copy is still in flight), then c2 += NTT(e2) + m g_hat
+      auto preload = [&](bool accumulate) {
+        launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream, accumulate); });
+      };
+      if (!host) preload(false);
       GemmArgs g{};
       g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
       g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
       g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2;
-      g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
+      g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = host ? 2 : 0; g.lc = c->T.lc;
       gemm(c, g);
+      if (host) {
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+        preload(true);
+      }
     }
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -577,14 +607,37 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       d_slots = c->idxd.as<uint32_t>();
     }
     CUDA_CHECK(cudaStreamSynchronize(c->stream));  // `local` goes out of scope below only after use; keep it simple and safe
-    const long long* d_sk = (const long long*)stage_in(c, c->in_small, sk, (size_t)P * k * ell * 8, flags);
+    const bool host = !(flags & PVW_IO_DEVICE);
+    const long long* d_sk = reinterpret_cast<const long long*>(sk);
     u64* d_out = reinterpret_cast<u64*>(out);
-    if (!(flags & PVW_IO_DEVICE)) { c->outd.ensure((size_t)P * D * 8); d_out = c->outd.as<u64>(); }
+    if (host) {
+      c->in_small.ensure((size_t)P * k * ell * 8);
+      d_sk = c->in_small.as<long long>();
+      c->outd.ensure((size_t)P * D * 8);
+      d_out = c->outd.as<u64>();
+    }
     uint32_t Pc_max = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(P, c->decrypt_chunk_shares / std::max<uint32_t>(D, 1)));
     c->shat.ensure((size_t)L * Pc_max * k * ell * 8);
     c->z.ensure((size_t)D * L * Pc_max * ell * 8);
-    for (uint32_t p0 = 0; p0 < P; p0 += Pc_max) {
-      const uint32_t Pc = std::min(Pc_max, P - p0);
+    c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * D) * 8);   // sized for the largest chunk up front: growing a
+    c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * D) * 8);   // buffer mid-call would synchronise the device
+    // host inputs: a short first chunk, so that little of the secret-key copy is exposed before the kernels start
+    const uint32_t first = host ? std::max<uint32_t>(1, std::min<uint32_t>(Pc_max, std::max<uint32_t>(Pc_max / 8, 64))) : Pc_max;
+    if (host) {  // every chunk's secret keys are queued now, in order, each with its own event: chunk i+1 arrives while chunk i computes
+      uint32_t i = 0;
+      for (uint32_t p0 = 0; p0 < P; i++) {
+        const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
+        if (c->chunk_ev.size() <= i) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->chunk_ev.push_back(e); }
+        CUDA_CHECK(cudaMemcpyAsync(c->in_small.as<long long>() + (size_t)p0 * k * ell, sk + (size_t)p0 * k * ell, (size_t)Pc * k * ell * 8,
+                                   cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_CHECK(cudaEventRecord(c->chunk_ev[i], c->copy_stream));
+        p0 += Pc;
+      }
+    }
+    uint32_t chunk_no = 0;
+    for (uint32_t p0 = 0; p0 < P; chunk_no++) {
+      const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
+      if (host) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[chunk_no], 0));
       // s_hat[limb][p][j][ell]   (SecretKey::get_polynomial, secret_key.rs:98-112 -- once per party, not per ciphertext)
       launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream); });
       // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274)
@@ -596,10 +649,16 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       g.rows = Pc; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
       gemm(c, g);
       decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, D, d_out + (size_t)p0 * D, D);
+      if (host) {  // this chunk's plaintexts go home while the next chunk computes
+        CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev[3], 0));
+        CUDA_CHECK(cudaMemcpyAsync(out + (size_t)p0 * D, d_out + (size_t)p0 * D, (size_t)Pc * D * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+      }
+      p0 += Pc;
     }
-    if (!(flags & PVW_IO_DEVICE)) {
-      CUDA_CHECK(cudaMemcpyAsync(out, d_out, (size_t)P * D * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (host) {
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
     }
   });
 }

@@ -38,7 +38,7 @@ struct DevTables {
 //   item idx in [0,count): vec = idx / inner, j = idx % inner;  out[vec*vstride + limb*lstride + j*ell + c]
 //   value = NTT(rns(coef[idx]))[c] (+ (m[idx] as i64 mod q) * gadget_hat[limb][c] when m != nullptr)
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st);
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false);
 // generic strided block copy:  out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c],  c < blk
 void launch_permute(const u64* in, u64* out, uint64_t Bn, uint64_t X, uint64_t Y, uint32_t blk, size_t ibs, size_t ixs, size_t iys,
                     size_t obs, size_t oxs, size_t oys, cudaStream_t st);
@@ -48,6 +48,7 @@ void launch_permute(const u64* in, u64* out, uint64_t Bn, uint64_t X, uint64_t Y
 //   acc[row][d][c] = sum_{j<k} M[limb][row][j][c] * V[d][limb][j][c]  mod q_limb
 //   mode 0: O = acc + O (in place: O was pre-loaded with NTT(e) (+ m*g))   -- c1, c2, keygen
 //   mode 1: O = acc - S                                                    -- decrypt (S = c2)
+//   mode 2: O = acc (store only; NTT(e) (+ m*g) is added afterwards by ntt_small in accumulate mode)
 struct GemmArgs {
   const u64* M; size_t M_ls, M_rs;        // M[limb*M_ls + row*M_rs + j*ell + c]
   const u64* V; size_t V_ls, V_ds;        // V[d*V_ds + limb*V_ls + j*ell + c]

@@ -119,6 +119,7 @@ struct Worker {
         u64* o = g.O + (size_t)d * g.O_ds + (size_t)limb * g.O_ls + (size_t)row * ELL + c;
         if (g.mode == 0) {
           v = addmod(v, *o, lc.q);
+        } else if (g.mode == 2) {
         } else {
           const uint32_t srow = g.S_rowmap ? g.S_rowmap[row] : row;
           v = submod(v, g.S[(size_t)ds * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * ELL + c], lc.q);

@@ -10,7 +10,7 @@
 
 namespace pvw {
 
-template <int ELL>
+template <int ELL, bool ACCUM>
 __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
@@ -45,16 +45,26 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   uint64_t vec = idx / inner, j = idx % inner;
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
 #pragma unroll
-  for (int t = 0; t < ELL / 2; t++) dst[t] = make_ulonglong2(a[2 * t], a[2 * t + 1]);
+  for (int t = 0; t < ELL / 2; t++) {
+    if (ACCUM) {  // out += value (the matrix product was stored first; host-pointer encrypt overlaps the e2 / m copy with it)
+      const ulonglong2 o = dst[t];
+      dst[t] = make_ulonglong2(addmod(a[2 * t], o.x, lc.q), addmod(a[2 * t + 1], o.y, lc.q));
+    } else {
+      dst[t] = make_ulonglong2(a[2 * t], a[2 * t + 1]);
+    }
+  }
 }
 
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st) {
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate) {
   if (count == 0) return;
   dim3 grid((unsigned)((count + 127) / 128), T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
-    ntt_small_kernel<E><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh); \
+    if (accumulate)                                                                                                           \
+      ntt_small_kernel<E, true><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+    else                                                                                                                      \
+      ntt_small_kernel<E, false><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh); \
     break;
   switch (T.ell) {
     PVW_NTT_CASE(8)

@@ -293,7 +293,12 @@ class Engine:
                                                    _ffi.PVW_IO_DEVICE))
             self._after_device_call()
             return out
-        res = np.empty((P, D), dtype=np.uint64)
+        if out is not None:      # caller-provided host buffer (e.g. pinned memory): no allocation / page faults per call
+            res = out
+            if not (isinstance(res, np.ndarray) and res.dtype == np.uint64 and res.shape == (P, D) and res.flags.c_contiguous):
+                raise PvwError("DimensionMismatch", f"out: need a C-contiguous uint64 array of shape {(P, D)}")
+        else:
+            res = np.empty((P, D), dtype=np.uint64)
         self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr,
                                                res.ctypes.data, 0))
         return res

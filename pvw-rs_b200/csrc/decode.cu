@@ -145,8 +145,7 @@ void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaS
 #define PVW_LIFT_CASE(N)                                                                                              \
   case N: {                                                                                                           \
     auto kern = crt_lift_kernel<N>;                                                                                   \
-    static bool attr = false;                                                                                         \
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }  \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);                              \
     kern<<<grid, 128, smem, st>>>(y, X, S, T.L, T.ell + 1, T.NW, T.qhat, T.Qsh, T.LB);                                \
     break;                                                                                                            \
   }

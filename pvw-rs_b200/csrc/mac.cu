@@ -155,13 +155,11 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
   dim3 grid((a.rows + C::RT - 1) / C::RT, (a.D + C::DT - 1) / C::DT, a.L);
   if (impl == 0) {
     auto kern = mac_gemm_sync_kernel<ELL, TR, TD, GD, KC, NB>;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::STAGE); attr = true; }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::STAGE);  // per device: set on every launch
     kern<<<grid, kComputeThreads, C::STAGE, st>>>(a);
   } else {
     auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC, NB>;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * C::STAGE); attr = true; }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * C::STAGE);
     kern<<<grid, kComputeThreads, NS * C::STAGE, st>>>(a);
   }
 }

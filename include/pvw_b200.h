@@ -81,6 +81,15 @@ int pvw_params_correctness_condition(const pvw_ctx *ctx, int *ok);
 int pvw_crs_upload(pvw_ctx *ctx, const uint64_t *A /* [k][k][L][ell] */, uint32_t flags);
 int pvw_crs_download(pvw_ctx *ctx, uint64_t *A /* [k][k][L][ell] */);
 
+/* Seeded CRS: PvwCrs::new_deterministic (crs.rs:45-67) and new_from_tag (crs.rs:74-90).  Host-side expansion (as in the
+ * reference: ChaCha8 master -> 32-byte element seeds -> fhe-math Poly::random_from_seed = SHA-256 + ChaCha8 + Uniform(0..q_j);
+ * restated from memory, see csrc/crsgen.hpp) followed by the upload.  A_out (may be NULL) receives the matrix [k][k][L][ell]. */
+int pvw_crs_generate_deterministic(pvw_ctx *ctx, const uint8_t seed[32], uint64_t *A_out);
+int pvw_crs_generate_from_tag(pvw_ctx *ctx, const char *tag, uint64_t *A_out);
+/* the same expansion without a context or a device (pure host arithmetic), and the tag -> seed map of new_from_tag */
+int pvw_crs_expand_seed(uint32_t k, uint32_t ell, uint32_t L, const uint64_t *moduli, const uint8_t seed[32], uint64_t *A_out);
+int pvw_crs_tag_to_seed(const char *tag, uint8_t seed_out[32]);
+
 /* GlobalPublicKey storage (src/keys/public_key.rs:43-54): add_public_key (:214-250) for rows [row, row+count) of B.
  * `row` is a GLOBAL party index and must lie inside this context's shard.  num_keys = max(index)+1 as in :245-247. */
 int pvw_pk_upload_rows(pvw_ctx *ctx, uint32_t row, uint32_t count, const uint64_t *B /* [count][k][L][ell] */, uint32_t flags);

@@ -609,6 +609,73 @@ def decrypt_party_shares(P: Params, all_cts, sk_coeffs, party_index: int) -> Lis
 
 
 # --------------------------------------------------------------------------------------------------
+# Seeded CRS (src/params/crs.rs:45-90).  fhe-math / rand internals recalled: PARITY UNPINNED.
+# --------------------------------------------------------------------------------------------------
+def chacha8_from_seed(seed32: bytes) -> "ChaCha8Rng":
+    """ChaCha8Rng::from_seed"""
+    return ChaCha8Rng(bytes(seed32))
+
+
+def uniform_u64_sample(rng: "ChaCha8Rng", q: int) -> int:
+    """rand 0.8.5 Uniform::<u64>::from(0..q).sample(rng)"""
+    ints_to_reject = (MASK64 - q + 1) % q
+    zone = MASK64 - ints_to_reject
+    while True:
+        m = rng.next_u64() * q
+        if (m & MASK64) <= zone:
+            return m >> 64
+
+
+def poly_random_from_seed(P: "Params", seed32: bytes) -> Poly:
+    """fhe-math Poly::random_from_seed(ctx, Ntt, seed): ChaCha8(SHA-256(seed)), each RNS row = Uniform(0..q_j) samples"""
+    import hashlib
+    prng = chacha8_from_seed(hashlib.sha256(bytes(seed32)).digest())
+    return [[uniform_u64_sample(prng, q) for _ in range(P.l)] for q in P.moduli]
+
+
+def crs_new_deterministic(P: "Params", seed32: bytes) -> List[List[Poly]]:
+    """PvwCrs::new_deterministic, crs.rs:45-67: master ChaCha8 -> gen::<[u8; 32]>() per element (one u32 per byte)"""
+    master = chacha8_from_seed(seed32)
+    A = []
+    for _ in range(P.k):
+        row = []
+        for _ in range(P.k):
+            element_seed = bytes(master.next_u32() & 0xFF for _ in range(32))
+            row.append(poly_random_from_seed(P, element_seed))
+        A.append(row)
+    return A
+
+
+def siphash13_zero_key(msg: bytes) -> int:
+    """Rust DefaultHasher::new() = SipHash-1-3 with k0 = k1 = 0"""
+    rotl = lambda x, b: ((x << b) | (x >> (64 - b))) & MASK64
+    v = [0x736F6D6570736575, 0x646F72616E646F6D, 0x6C7967656E657261, 0x7465646279746573]
+
+    def rnd():
+        v[0] = (v[0] + v[1]) & MASK64; v[1] = rotl(v[1], 13); v[1] ^= v[0]; v[0] = rotl(v[0], 32)
+        v[2] = (v[2] + v[3]) & MASK64; v[3] = rotl(v[3], 16); v[3] ^= v[2]
+        v[0] = (v[0] + v[3]) & MASK64; v[3] = rotl(v[3], 21); v[3] ^= v[0]
+        v[2] = (v[2] + v[1]) & MASK64; v[1] = rotl(v[1], 17); v[1] ^= v[2]; v[2] = rotl(v[2], 32)
+
+    n = len(msg)
+    full = n - n % 8
+    for i in range(0, full, 8):
+        m = int.from_bytes(msg[i:i + 8], "little")
+        v[3] ^= m; rnd(); v[0] ^= m
+    last = ((n & 0xFF) << 56) | int.from_bytes(msg[full:], "little")
+    v[3] ^= last; rnd(); v[0] ^= last
+    v[2] ^= 0xFF
+    rnd(); rnd(); rnd()
+    return v[0] ^ v[1] ^ v[2] ^ v[3]
+
+
+def crs_seed_from_tag(tag: str) -> bytes:
+    """new_from_tag, crs.rs:74-90: hash of (tag + "CRS") as a str (bytes + 0xff), u64 cycled to 32 bytes"""
+    h = siphash13_zero_key((tag + "CRS").encode() + b"\xff")
+    return h.to_bytes(8, "little") * 4
+
+
+# --------------------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY 8d / A.7), flat index = row-major position in the named array
 # --------------------------------------------------------------------------------------------------
 def synth_crs(P: Params, seed=DEFAULT_SEED) -> List[List[Poly]]:

@@ -38,6 +38,10 @@ SIGNATURES = {
     "pvw_params_correctness_condition": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "pvw_crs_upload": (C.c_int, [_vp, _vp, _u32]),
     "pvw_crs_download": (C.c_int, [_vp, _vp]),
+    "pvw_crs_generate_deterministic": (C.c_int, [_vp, _vp, _vp]),
+    "pvw_crs_generate_from_tag": (C.c_int, [_vp, C.c_char_p, _vp]),
+    "pvw_crs_expand_seed": (C.c_int, [_u32, _u32, _u32, _vp, _vp, _vp]),
+    "pvw_crs_tag_to_seed": (C.c_int, [C.c_char_p, _vp]),
     "pvw_pk_upload_rows": (C.c_int, [_vp, _u32, _u32, _vp, _u32]),
     "pvw_pk_download_rows": (C.c_int, [_vp, _u32, _u32, _vp]),
     "pvw_pk_num_keys": (C.c_int, [_vp, C.POINTER(_u32)]),

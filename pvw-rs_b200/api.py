@@ -171,6 +171,19 @@ class PvwParametersBuilder:
 # --------------------------------------------------------------------------------------------------------------
 # CRS -- src/params/crs.rs
 # --------------------------------------------------------------------------------------------------------------
+def expand_crs_seed(params: "PvwParameters", seed: bytes) -> np.ndarray:
+    from . import _ffi
+    seed = bytes(seed)
+    if len(seed) != 32:
+        raise PvwError("InvalidParameters", "the master seed must be 32 bytes")
+    mods = np.array(params.moduli(), dtype=np.uint64)
+    out = np.empty((params.k, params.k, params.L, params.l), dtype=np.uint64)
+    rc = _ffi.load().pvw_crs_expand_seed(params.k, params.l, params.L, mods.ctypes.data, seed, out.ctypes.data)
+    if rc != 0:
+        raise PvwError(_ffi.STATUS_NAMES.get(rc, "InternalError"), "CRS seed expansion failed")
+    return out
+
+
 class PvwCrs:
     """PvwCrs{matrix: k x k polynomials in NTT form, params} (crs.rs:12-17); matrix is a host array [k][k][L][l]."""
 
@@ -190,6 +203,22 @@ class PvwCrs:
         for j, q in enumerate(params.moduli()):
             m[:, :, j, :] = g.integers(0, q, size=(params.k, params.k, params.l), dtype=np.uint64)
         return cls(params, m)
+
+    @classmethod
+    def new_deterministic(cls, params: PvwParameters, seed: bytes) -> "PvwCrs":
+        """crs.rs:45-67: same 32-byte seed => identical CRS (host-side expansion in the library, no device needed)"""
+        return cls(params, expand_crs_seed(params, seed))
+
+    @classmethod
+    def new_from_tag(cls, params: PvwParameters, tag: str) -> "PvwCrs":
+        """crs.rs:74-90"""
+        import ctypes
+        from . import _ffi
+        seed = (ctypes.c_uint8 * 32)()
+        rc = _ffi.load().pvw_crs_tag_to_seed(tag.encode(), seed)
+        if rc != 0:
+            raise PvwError(_ffi.STATUS_NAMES.get(rc, "InternalError"), "tag")
+        return cls.new_deterministic(params, bytes(seed))
 
     def dimensions(self):
         return self.matrix.shape[0], self.matrix.shape[1]

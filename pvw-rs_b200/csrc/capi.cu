@@ -19,6 +19,7 @@
 
 #include "../../include/pvw_b200.h"
 #include "hostparams.hpp"
+#include "crsgen.hpp"
 #include "kernels.cuh"
 
 using namespace pvw;
@@ -366,6 +367,39 @@ int pvw_crs_download(pvw_ctx* c, uint64_t* A) {
     const size_t kk = (size_t)c->hp.k * c->hp.k;
     download_polys(c, c->A.as<u64>(), kk * c->hp.ell, kk, A);
   });
+}
+
+int pvw_crs_tag_to_seed(const char* tag, uint8_t seed_out[32]) {
+  if (!tag || !seed_out) return PVW_ERR_INVALID_PARAMETERS;
+  crs_tag_to_seed(tag, seed_out);
+  return PVW_OK;
+}
+int pvw_crs_expand_seed(uint32_t k, uint32_t ell, uint32_t L, const uint64_t* moduli, const uint8_t seed[32], uint64_t* A_out) {
+  if (!moduli || !seed || !A_out || k == 0 || ell == 0 || L == 0) return PVW_ERR_INVALID_PARAMETERS;
+  for (uint32_t j = 0; j < L; j++) if (moduli[j] < 2) return PVW_ERR_INVALID_PARAMETERS;
+  crs_new_deterministic(seed, k, moduli, L, ell, A_out);
+  return PVW_OK;
+}
+int pvw_crs_generate_deterministic(pvw_ctx* c, const uint8_t seed[32], uint64_t* A_out) {
+  return guarded(c, [&] {
+    require(seed != nullptr, PVW_ERR_INVALID_PARAMETERS, "seed is null");
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+    const size_t kk = (size_t)k * k;
+    std::vector<uint64_t> local;
+    uint64_t* A = A_out;
+    if (!A) { local.resize(kk * L * ell); A = local.data(); }
+    crs_new_deterministic(seed, k, c->hp.moduli.data(), L, ell, A);
+    c->A.ensure((size_t)L * kk * ell * 8);
+    upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, PVW_IO_HOST);
+    c->A_set = true;
+    c->At_valid = false;
+  });
+}
+int pvw_crs_generate_from_tag(pvw_ctx* c, const char* tag, uint64_t* A_out) {
+  if (!tag) return PVW_ERR_INVALID_PARAMETERS;
+  uint8_t seed[32];
+  crs_tag_to_seed(tag, seed);
+  return pvw_crs_generate_deterministic(c, seed, A_out);
 }
 
 static void ensure_B(pvw_ctx* c) {

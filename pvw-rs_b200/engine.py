@@ -173,6 +173,21 @@ class Engine:
         if a.device:
             self._after_device_call()
 
+    def crs_generate_deterministic(self, seed: bytes, want_matrix: bool = False):
+        """PvwCrs::new_deterministic (crs.rs:45-67): expand the 32-byte master seed on the host and upload"""
+        seed = bytes(seed)
+        if len(seed) != 32:
+            raise PvwError("InvalidParameters", "the master seed must be 32 bytes")
+        out = np.empty((self.k, self.k) + self.poly, dtype=np.uint64) if want_matrix else None
+        self._check(self.lib.pvw_crs_generate_deterministic(self.h, seed, out.ctypes.data if want_matrix else None))
+        return out
+
+    def crs_generate_from_tag(self, tag: str, want_matrix: bool = False):
+        """PvwCrs::new_from_tag (crs.rs:74-90)"""
+        out = np.empty((self.k, self.k) + self.poly, dtype=np.uint64) if want_matrix else None
+        self._check(self.lib.pvw_crs_generate_from_tag(self.h, tag.encode(), out.ctypes.data if want_matrix else None))
+        return out
+
     def crs_download(self) -> np.ndarray:
         out = np.empty((self.k, self.k) + self.poly, dtype=np.uint64)
         self._check(self.lib.pvw_crs_download(self.h, out.ctypes.data))

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_sync_kernel(cons
 // Nine warps would cap the kernel at 168 registers (three warps on one sub-partition share 16 K registers), so the
 // eight compute warps feed themselves: warp w owns rows {w, w+8, ...} of the staged tile; before it starts chunk i it
 // refills the stage that chunk i-1 used (everybody has left it: `empty` barrier) with chunk i-1+NS.
-template <int ELL, int TR, int TD, int GD, int KC, int NB>
+template <int ELL, int TR, int TD, int GD, int KC, int NB, int NS>
 __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tma_kernel(const GemmArgs g) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
   constexpr int NW = kComputeThreads / 32;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tma_kernel(const
   wk.epilogue(g, limb, r0, d0);
 }
 
-template <int ELL, int TR, int TD, int GD, int KC, int NB>
+template <int ELL, int TR, int TD, int GD, int KC, int NB, int NS = kStages>
 static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
   dim3 grid((a.rows + C::RT - 1) / C::RT, (a.D + C::DT - 1) / C::DT, a.L);
@@ -158,7 +158,7 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::STAGE);  // per device: set on every launch
     kern<<<grid, kComputeThreads, C::STAGE, st>>>(a);
   } else {
-    auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC, NB>;
+    auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC, NB, NS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * C::STAGE);
     kern<<<grid, kComputeThreads, NS * C::STAGE, st>>>(a);
   }
@@ -167,25 +167,30 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
 void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
   if (a.rows == 0 || a.D == 0) return;
   const bool matvec = a.D == 1;
-  // tile 0: 4x4 register tile, one CTA per SM (255 registers); tile 1: 4x2, two CTAs per SM (<= 128 registers) so that
-  // one CTA's prologue / epilogue overlaps the other's main loop
+  // tile 1 (default): 4x2 register tile, two CTAs per SM (<= 128 registers: one CTA's prologue / epilogue overlaps the
+  //   other's main loop), 16 polynomials per stage, double buffered -- the per-chunk barrier round trip is the
+  //   overhead that matters (8 -> 16 polynomials per stage: -8 % kernel time);
+  // tile 2: the same tile with 8 polynomials per stage in a 4-stage ring; tile 0: 4x4 tile, one CTA per SM (255 registers)
   const int tile = a.tile;
   switch (a.ell) {
     case 8:
       if (matvec && tile == 0) launch_cfg<8, 2, 1, 1, 8, 1>(a, impl, st);
       else if (matvec) launch_cfg<8, 1, 1, 1, 16, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<8, 4, 4, 4, 8, 1>(a, impl, st);
-      else launch_cfg<8, 4, 2, 4, 8, 2>(a, impl, st);
+      else if (tile == 2) launch_cfg<8, 4, 2, 4, 8, 2>(a, impl, st);
+      else launch_cfg<8, 4, 2, 4, 16, 2, 2>(a, impl, st);
       break;
     case 16:
       if (matvec) launch_cfg<16, 2, 1, 1, 8, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<16, 4, 4, 4, 8, 1>(a, impl, st);
-      else launch_cfg<16, 4, 2, 4, 8, 2>(a, impl, st);
+      else if (tile == 2) launch_cfg<16, 4, 2, 4, 8, 2>(a, impl, st);
+      else launch_cfg<16, 4, 2, 4, 16, 2, 2>(a, impl, st);
       break;
     case 32:
       if (matvec) launch_cfg<32, 4, 1, 1, 4, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<32, 4, 4, 2, 4, 1>(a, impl, st);
-      else launch_cfg<32, 4, 2, 2, 4, 2>(a, impl, st);
+      else if (tile == 2) launch_cfg<32, 4, 2, 2, 4, 2>(a, impl, st);
+      else launch_cfg<32, 4, 2, 2, 8, 2, 2>(a, impl, st);
       break;
   }
 }

@@ -6,7 +6,7 @@
 namespace pvw {
 
 constexpr int kComputeThreads = 256;
-constexpr int NS = 4;  // pipeline stages
+constexpr int kStages = 4;  // default pipeline depth
 
 template <int ELL, int TR, int TD, int GD, int KC, int THREADS = kComputeThreads>
 struct TileCfg {

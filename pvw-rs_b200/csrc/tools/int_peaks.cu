@@ -350,19 +350,15 @@ int main(int argc, char** argv) {
   double t4 = time_ms([&] { k_mack<CH><<<blocks, threads>>>(out, in, iters); });
   {
     const int wi = iters / 8;
-    worker_rate<Worker<8, 4, 4, 4, 8, 4, false, false, 256>, 1>("4x4 nj4 unrolled canonical (production)", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 4, 4, 8, 4, true, false, 256>, 1>("4x4 nj4 rolled canonical", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 4, 4, 8, 4, false, true, 256>, 1>("4x4 nj4 unrolled packed", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 4, 4, 8, 4, true, true, 256>, 1>("4x4 nj4 rolled packed", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 4, 4, 8, 2, false, true, 256>, 1>("4x4 nj2 unrolled packed", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 4, 4, 8, 8, false, true, 256>, 1>("4x4 nj8 unrolled packed", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, true, 256>, 2>("4x2 nj4 unrolled packed 2cta", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, true, true, 256>, 2>("4x2 nj4 rolled packed 2cta", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 256>, 2>("4x2 nj4 unrolled canonical 2cta", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 8, 8, 4, false, true, 512>, 1>("4x2 nj4 unrolled packed 512thr", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 2, 4, 4, 8, 4, false, true, 256>, 2>("2x4 nj4 unrolled packed 2cta", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 4, 3, 4, 8, 4, false, true, 256>, 1>("4x3 nj4 unrolled packed", out, in, sms, wi, 1);
-    worker_rate<Worker<8, 2, 2, 4, 8, 4, false, true, 256>, 3>("2x2 nj4 unrolled packed 3cta", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 256>, 2>("4x2 canonical 256thr x2 (production)", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 192>, 3>("4x2 canonical 192thr x3", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 320>, 2>("4x2 canonical 320thr x2", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 128>, 4>("4x2 canonical 128thr x4", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 384>, 1>("4x2 canonical 384thr x1", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 2, 8, 4, false, false, 256>, 2>("4x2 GD=2 canonical 256thr x2", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 8, 8, 4, false, false, 256>, 2>("4x2 GD=8 canonical 256thr x2", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 4, 4, 8, 4, false, false, 256>, 1>("4x4 canonical 256thr x1", out, in, sms, wi, 0);
+    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, true, 256>, 2>("4x2 packed 256thr x2", out, in, sms, wi, 1);
   }
   double tt[4];
   tt[0] = time_ms([&] { k_tile<0><<<sms, 256>>>(out, in, iters / 4); });

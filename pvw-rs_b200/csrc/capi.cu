@@ -751,9 +751,9 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
   return guarded(c, [&] {
     require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");
     std::string n(name);
-    if (n == "gemm_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0 or 1"); c->gemm_impl = (int)value; }
-    else if (n == "gemm_tile") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..2"); c->gemm_tile = (int)value; }
-    else if (n == "refill_lag") { require(value >= 1 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..3"); c->refill_lag = (int)value; }
+    if (n == "gemm_impl") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0, 1 or 2"); c->gemm_impl = (int)value; }
+    else if (n == "gemm_tile") { require(value >= 0 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..3"); c->gemm_tile = (int)value; }
+    else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
     else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }

@@ -21,6 +21,8 @@
 //     cp.async.bulk (TMA, SASS UBLKCP) into a 4-stage shared-memory ring guarded by mbarriers (impl 1);
 //     impl 0 is the same tile with synchronous loads (bring-up / cross-check path).
 //   * D == 1 (a single `encrypt` call) degenerates to the HBM-bound matrix-vector product with DT = 1.
+#include <cuda.h>
+
 #include <cstdio>
 
 #include "kernels.cuh"
@@ -149,6 +151,95 @@ __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tma_kernel(const
   wk.epilogue(g, limb, r0, d0);
 }
 
+// ---- impl 2: the matrix tile as ONE tensor-map TMA box per chunk ---------------------------------------------------------
+// cp.async.bulk.tensor.3d over M viewed as u64[L][rows][k*ell]: box = KC*ell x RT x 1.  Out-of-range rows / polynomials
+// are zero-filled by the TMA unit (their products vanish), so there is no tail path.  Only warp 0 feeds the ring: lane 0
+// issues the box, lanes 0..DT-1 one bulk copy each for the dealer rows; the other warps just wait and compute.
+__device__ __forceinline__ void tensor_g2s_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+template <int ELL, int TR, int TD, int GD, int KC, int NB, int NS>
+__global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tensor_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmapM) {
+  using W = Worker<ELL, TR, TD, GD, KC, 4, false, false, kComputeThreads, true>;
+  using C = typename W::C;
+  constexpr int NW = kComputeThreads / 32;
+  static_assert(C::DT <= 32, "one lane per dealer row");
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bars[2 * NS];  // full[NS], empty[NS]
+  const uint32_t limb = blockIdx.z, r0 = blockIdx.x * C::RT, d0 = blockIdx.y * C::DT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar0 = smem_u32(bars);
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) {
+      mbar_init(bar0 + 8 * s, 1);          // full: one arrive.expect_tx by the feeding lane
+      mbar_init(bar0 + 8 * (NS + s), NW);  // empty: one arrive per warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t nchunks = (g.k + KC - 1) / KC;
+  const u64* my_v = nullptr;
+  if (warp == 0 && lane < C::DT) {
+    uint32_t d = min(d0 + (uint32_t)lane, g.D - 1);
+    if (g.V_dmap) d = g.V_dmap[d];
+    my_v = g.V + (size_t)d * g.V_ds + (size_t)limb * g.V_ls;
+  }
+  auto refill = [&](uint32_t chunk) {  // warp 0 only
+    const int s = chunk % NS;
+    const uint32_t kc = min((uint32_t)KC, g.k - chunk * KC);
+    const uint32_t v_bytes = kc * ELL * 8;
+    const uint32_t dst = smem_u32(smem) + s * C::STAGE;
+    if (lane == 0) {
+      mbar_expect_tx(bar0 + 8 * s, C::MBYTES + C::DT * v_bytes);
+      tensor_g2s_3d(dst, &tmapM, (int)(chunk * KC * ELL), (int)r0, (int)limb, bar0 + 8 * s);
+    }
+    __syncwarp();
+    if (lane < C::DT) bulk_g2s(dst + C::MBYTES + lane * C::VROWB, my_v + (size_t)chunk * KC * ELL, v_bytes, bar0 + 8 * s);
+  };
+  if (warp == 0)
+    for (uint32_t ch = 0; ch < nchunks && ch < (uint32_t)NS; ch++) refill(ch);
+  W wk;
+  wk.init(tid, (u32)g.lc[limb].pad);
+  const uint32_t lag = g.refill_lag >= 1 && g.refill_lag < NS ? g.refill_lag : 1;
+  for (uint32_t it = 0; it < nchunks; it++) {
+    if (warp == 0 && it >= lag && it - lag + NS < nchunks) {
+      const uint32_t prev = it - lag;
+      mbar_wait(bar0 + 8 * (NS + prev % NS), (prev / NS) & 1);  // every warp has finished chunk it-lag
+      refill(prev + NS);
+    }
+    const int s = it % NS;
+    mbar_wait(bar0 + 8 * s, (it / NS) & 1);
+    wk.template chunk<true>(smem + (size_t)s * C::STAGE, KC);  // a short last chunk is zero-filled by the TMA unit
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar0 + 8 * (NS + s));
+  }
+  wk.epilogue(g, limb, r0, d0);
+}
+
+// tensor map over M as u64[L][rows][k*ell] (driver entry point fetched at run time: no link-time libcuda dependency)
+static bool make_tensor_map(CUtensorMap* tm, const GemmArgs& a, uint32_t box_inner, uint32_t box_rows) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<encode_fn>(fn);
+  }
+  if (!encode) return false;
+  if (((uintptr_t)a.M & 15) || ((a.M_rs * 8) & 15) || ((a.M_ls * 8) & 15)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)a.k * a.ell, a.rows, a.L};
+  const cuuint64_t strides[2] = {(cuuint64_t)a.M_rs * 8, (cuuint64_t)a.M_ls * 8};
+  const cuuint32_t box[3] = {box_inner, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<u64*>(a.M), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int ELL, int TR, int TD, int GD, int KC, int NB, int NS = kStages>
 static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
   using C = TileCfg<ELL, TR, TD, GD, KC>;
@@ -157,6 +248,13 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
     auto kern = mac_gemm_sync_kernel<ELL, TR, TD, GD, KC, NB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::STAGE);  // per device: set on every launch
     kern<<<grid, kComputeThreads, C::STAGE, st>>>(a);
+  } else if (impl == 2 && KC * ELL <= 256) {
+    using CD = TileCfg<ELL, TR, TD, GD, KC, kComputeThreads, true>;
+    CUtensorMap tm;
+    if (!make_tensor_map(&tm, a, KC * ELL, CD::RT)) { launch_cfg<ELL, TR, TD, GD, KC, NB, NS>(a, 1, st); return; }
+    auto kern = mac_gemm_tensor_kernel<ELL, TR, TD, GD, KC, NB, NS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * CD::STAGE);
+    kern<<<grid, kComputeThreads, NS * CD::STAGE, st>>>(a, tm);
   } else {
     auto kern = mac_gemm_tma_kernel<ELL, TR, TD, GD, KC, NB, NS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * C::STAGE);
@@ -168,9 +266,10 @@ void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
   if (a.rows == 0 || a.D == 0) return;
   const bool matvec = a.D == 1;
   // tile 1 (default): 4x2 register tile, two CTAs per SM (<= 128 registers: one CTA's prologue / epilogue overlaps the
-  //   other's main loop), 16 polynomials per stage, double buffered -- the per-chunk barrier round trip is the
-  //   overhead that matters (8 -> 16 polynomials per stage: -8 % kernel time);
-  // tile 2: the same tile with 8 polynomials per stage in a 4-stage ring; tile 0: 4x4 tile, one CTA per SM (255 registers)
+  //   other's main loop); CTA tile 16 rows x 16 dealers (fewest staged rows per output), 16 polynomials per stage, three
+  //   stages refilled with a lag of two chunks.  Measured steps (C3, ms of mac_gemm per bench step): 8 polynomials x 4
+  //   stages 43.0 -> 16 x 2 39.6 (the per-chunk barrier round trip is the overhead that matters) -> 16 x 16 tile, 3 stages,
+  //   lag 2: 38.5 (slack against warp skew).  tile 2: 32 x 8 tile, 8 x 4 stages; tile 0: 4x4 register tile, one CTA per SM
   const int tile = a.tile;
   switch (a.ell) {
     case 8:
@@ -178,7 +277,8 @@ void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
       else if (matvec) launch_cfg<8, 1, 1, 1, 16, 1>(a, impl, st);
       else if (tile == 0) launch_cfg<8, 4, 4, 4, 8, 1>(a, impl, st);
       else if (tile == 2) launch_cfg<8, 4, 2, 4, 8, 2>(a, impl, st);
-      else launch_cfg<8, 4, 2, 4, 16, 2, 2>(a, impl, st);
+      else if (tile == 3) launch_cfg<8, 4, 2, 4, 16, 2, 2>(a, impl, st);   // 32 rows x 8 dealers, 16 polynomials x 2 stages
+      else launch_cfg<8, 4, 2, 8, 16, 2, 3>(a, impl, st);
       break;
     case 16:
       if (matvec) launch_cfg<16, 2, 1, 1, 8, 1>(a, impl, st);

@@ -8,7 +8,7 @@ namespace pvw {
 constexpr int kComputeThreads = 256;
 constexpr int kStages = 4;  // default pipeline depth
 
-template <int ELL, int TR, int TD, int GD, int KC, int THREADS = kComputeThreads>
+template <int ELL, int TR, int TD, int GD, int KC, int THREADS = kComputeThreads, bool DENSE_M = false>
 struct TileCfg {
   // KC = polynomials (j indices) per pipeline stage
   static constexpr int G = THREADS / ELL;  // (row-group, dealer-group) pairs per CTA
@@ -26,15 +26,21 @@ struct TileCfg {
     return 16;
   }
   static constexpr int ROWB = KC * ELL * 8 + pick_pad();
-  static constexpr int STAGE = (RT + DT) * ROWB;
+  // DENSE_M: the matrix rows arrive as ONE tensor-map (TMA) box, densely packed (pitch = KC*ELL*8); sub-tiles that share
+  // a row read it as a broadcast, so no stagger is needed there -- only the dealer rows keep the padded pitch
+  static constexpr int MROWB = DENSE_M ? KC * ELL * 8 : ROWB;
+  static constexpr int VROWB = ROWB;
+  static constexpr int MBYTES = RT * MROWB;
+  static constexpr int STAGE = ((MBYTES + DT * VROWB + 127) / 128) * 128;
   static_assert(G % GD == 0, "bad tile");
 };
 
 // NJ_: polynomials per straight-line block; ROLL: blocks in a real loop (small code) instead of unrolled;
 // PACKED: operands are stored as 31-bit halves (x1 << 32 | x0, modarith.cuh pack_halves) instead of canonical residues
-template <int ELL, int TR, int TD, int GD, int KC, int NJ_ = 4, bool ROLL = false, bool PACKED = false, int THREADS_ = kComputeThreads>
+template <int ELL, int TR, int TD, int GD, int KC, int NJ_ = 4, bool ROLL = false, bool PACKED = false, int THREADS_ = kComputeThreads,
+          bool DENSE_M = false>
 struct Worker {
-  using C = TileCfg<ELL, TR, TD, GD, KC, THREADS_>;
+  using C = TileCfg<ELL, TR, TD, GD, KC, THREADS_, DENSE_M>;
   static constexpr int THREADS = THREADS_;
   int c, gr, gd;
   u32 zero;  // run-time 0 (see add_alu)
@@ -59,7 +65,7 @@ struct Worker {
     for (int u = 0; u < TD; u++)
 #pragma unroll
       for (int i = 0; i < NJ; i++) {
-        const u64 x = *reinterpret_cast<const u64*>(vs + u * C::ROWB + (jj0 + i) * ELL * 8);
+        const u64 x = *reinterpret_cast<const u64*>(vs + u * C::VROWB + (jj0 + i) * ELL * 8);
         b0[u][i] = PACKED ? (u32)x : ((u32)x & 0x7fffffffu);
         b1[u][i] = PACKED ? (u32)(x >> 32) : (u32)(x >> 31);
       }
@@ -68,7 +74,7 @@ struct Worker {
       SplitOp a[NJ];
 #pragma unroll
       for (int i = 0; i < NJ; i++) {
-        const u64 x = *reinterpret_cast<const u64*>(ms + t * C::ROWB + (jj0 + i) * ELL * 8);
+        const u64 x = *reinterpret_cast<const u64*>(ms + t * C::MROWB + (jj0 + i) * ELL * 8);
         if (PACKED) { a[i].x0 = (u32)x; a[i].x1 = (u32)(x >> 32); a[i].xs = add_alu(a[i].x0, a[i].x1, zero); }
         else a[i] = split_op(x, zero);
       }
@@ -85,8 +91,8 @@ struct Worker {
   // one staged chunk: kc polynomials of every row / dealer of the tile
   template <bool FULL>
   __device__ __forceinline__ void chunk(const unsigned char* stage, int kc) {
-    const unsigned char* ms = stage + (size_t)(gr * TR) * C::ROWB + c * 8;
-    const unsigned char* vs = stage + (size_t)(C::RT + gd * TD) * C::ROWB + c * 8;
+    const unsigned char* ms = stage + (size_t)(gr * TR) * C::MROWB + c * 8;
+    const unsigned char* vs = stage + C::MBYTES + (size_t)(gd * TD) * C::VROWB + c * 8;
     constexpr int NJ = KC % NJ_ == 0 ? NJ_ : (KC % 2 == 0 ? 2 : 1);
     if (FULL && ROLL) {
 #pragma unroll 1

@@ -78,7 +78,7 @@ def test_keygen_matches_oracle(pkg, name):
     assert (eng2.pk_download_rows(0, P.n) == S.B).all()
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("name,D", [("EX", 1), ("EX", 7), ("T16", 5), ("VDs", 3), ("L32", 2), ("RAG", 1), ("RAG", 6)])
 def test_encrypt_decrypt_matches_oracle(pkg, name, D, impl):
     P = params(name)

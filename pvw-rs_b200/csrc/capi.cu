@@ -125,6 +125,9 @@ void upload_tables(pvw_ctx* c) {
          o_D = put(hp.Dw.data(), NW);
   std::vector<uint64_t> dM(hp.divM.v), d2D(hp.div2D.v);
   size_t o_dM = put(dM.data(), dM.size()), o_d2D = put(d2D.data(), d2D.size());
+  auto putv = [&](const std::vector<uint64_t>& v) { pad2(); return v.empty() ? blob.size() : put(v.data(), v.size()); };
+  size_t o_shc = putv(hp.sh_c), o_shcs = putv(hp.sh_c_sh), o_shq = putv(hp.sh_qhat), o_shQ = putv(hp.sh_Q), o_shh = putv(hp.sh_halfQ),
+         o_shv = putv(hp.sh_v), o_shvs = putv(hp.sh_v_sh), o_shr = putv(hp.sh_r), o_shrs = putv(hp.sh_r_sh);
   c->tables.ensure(blob.size() * 8);
   CUDA_CHECK(cudaMemcpy(c->tables.p, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
   const u64* base = c->tables.as<u64>();
@@ -138,6 +141,9 @@ void upload_tables(pvw_ctx* c) {
   T.divM_n = hp.divM.n; T.divM_shift = hp.divM.shift; T.divM_vinv = hp.divM.vinv;
   T.div2D_n = hp.div2D.n; T.div2D_shift = hp.div2D.shift; T.div2D_vinv = hp.div2D.vinv;
   T.tail_impl = 1;
+  T.sh_c = base + o_shc; T.sh_c_sh = base + o_shcs; T.sh_qhat = base + o_shq; T.sh_Q = base + o_shQ; T.sh_halfQ = base + o_shh;
+  T.sh_v = base + o_shv; T.sh_v_sh = base + o_shvs; T.sh_r = base + o_shr; T.sh_r_sh = base + o_shrs;
+  T.shortL = hp.shortL; T.shortSW = hp.shortSW; T.lift_fast = hp.shortL > 0 ? 1 : 0;
 }
 
 void check_launch(pvw_ctx* c, size_t n = 1) {
@@ -754,6 +760,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     if (n == "gemm_impl") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0, 1 or 2"); c->gemm_impl = (int)value; }
     else if (n == "gemm_tile") { require(value >= 0 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..3"); c->gemm_tile = (int)value; }
     else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
+    else if (n == "lift_fast") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "lift_fast must be 0 or 1"); c->T.lift_fast = (value && c->hp.shortL > 0) ? 1 : 0; }
     else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }

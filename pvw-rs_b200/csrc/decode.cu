@@ -90,9 +90,94 @@ PVW_DEV void mul_row_acc(u32 (&acc)[N], u32 m, const u32 (&q)[W]) {
   asm volatile("addc.u32 %0, %0, 0;" : "+r"(acc[OFF + W + 1]));
 }
 
+// Short lift (fast path of the CRT lift).  The values a decodable share produces (tmp_i ~ Delta * noise, w = m + noise)
+// are far smaller than Q, so they are determined by a sub-basis q_0..q_{Ls-1} (product Q_s): lift there, centre, and
+// VERIFY the candidate x against every remaining residue.  If all L residues agree, x = v (mod Q) with |x| <= Q_s/2 < Q/2,
+// i.e. x is exactly the centred value of the full lift -- the result is bit-identical by CRT uniqueness; any mismatch
+// (undecodable / adversarial inputs) falls through to the full lift below.
+template <int SW>
+PVW_DEV bool short_lift(const u64* __restrict__ y, size_t ystride, uint32_t L, const DevTables& T, const u64* __restrict__ vc,
+                        u64 (&mag)[4], bool& neg) {
+  u64 acc[SW + 1];
+#pragma unroll
+  for (int w = 0; w <= SW; w++) acc[w] = 0;
+  const uint32_t Ls = T.shortL;
+  for (uint32_t j = 0; j < Ls; j++) {
+    const u64 t = mulmod_shoup(y[(size_t)j * ystride], T.sh_c[j], T.sh_c_sh[j], T.lc[j].q);
+    u64 carry = 0;
+#pragma unroll
+    for (int w = 0; w < SW; w++) {
+      const u64 qw = T.sh_qhat[(size_t)j * SW + w];
+      const u64 lo = t * qw, hi = __umul64hi(t, qw);
+      u64 x = acc[w] + carry;
+      const u64 c1 = x < carry;
+      x += lo;
+      const u64 c2 = x < lo;
+      acc[w] = x;
+      carry = hi + c1 + c2;
+    }
+    acc[SW] += carry;
+  }
+  for (uint32_t r = 1; r < Ls; r++) {  // acc < Ls * Q_s
+    bool ge = acc[SW] != 0;
+    if (!ge) {
+      ge = true;
+#pragma unroll
+      for (int w = SW - 1; w >= 0; w--) {
+        const u64 qw = T.sh_Q[w];
+        if (acc[w] != qw) { ge = acc[w] > qw; break; }
+      }
+    }
+    if (ge) {
+      u64 borrow = 0;
+#pragma unroll
+      for (int w = 0; w < SW; w++) {
+        const u64 qw = T.sh_Q[w], d1 = acc[w] - qw, b1 = acc[w] < qw, d2 = d1 - borrow, b2 = d1 < borrow;
+        acc[w] = d2;
+        borrow = b1 | b2;
+      }
+      acc[SW] -= borrow;
+    }
+  }
+  neg = false;
+#pragma unroll
+  for (int w = SW - 1; w >= 0; w--) {
+    const u64 hw = T.sh_halfQ[w];
+    if (acc[w] != hw) { neg = acc[w] > hw; break; }
+  }
+  if (neg) {
+    u64 borrow = 0;
+#pragma unroll
+    for (int w = 0; w < SW; w++) {
+      const u64 qw = T.sh_Q[w], d1 = qw - acc[w], b1 = qw < acc[w], d2 = d1 - borrow, b2 = d1 < borrow;
+      acc[w] = d2;
+      borrow = b1 | b2;
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 4; w++) mag[w] = w < SW ? acc[w] : 0;
+  bool ok = true;
+#pragma unroll 4
+  for (uint32_t j = Ls; j < L; j++) {
+    const u64* cj = vc + (size_t)j * 10;  // shared memory: q, floor(2^64/q), (Q/q) mod q + Shoup, 2^64 / 2^128 / 2^192 mod q + Shoup
+    const u64 q = cj[0];
+    u64 r = mag[0] - __umul64hi(mag[0], cj[1]) * q;  // < 3q
+    r = r >= 2 * q ? r - 2 * q : r;
+    r = r >= q ? r - q : r;
+#pragma unroll
+    for (int w = 1; w < SW; w++) r += mulmod_shoup(mag[w], cj[2 + 2 * w], cj[3 + 2 * w], q);  // < SW * q < 2^64
+#pragma unroll
+    for (int w = 1; w < SW; w++) r = r >= q ? r - q : r;
+    if (neg) r = r ? q - r : 0;
+    const u64 v = mulmod_shoup(y[(size_t)j * ystride], cj[2], cj[3], q);
+    ok = ok && (r == v);
+  }
+  return ok;
+}
+
 template <int NWT>
 __global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y, u64* __restrict__ X, uint64_t S, uint32_t L, uint32_t ellp1,
-                                                       uint32_t NW, const u64* __restrict__ qhat, const u64* __restrict__ Qsh, uint32_t LB) {
+                                                       uint32_t NW, const u64* __restrict__ qhat, const u64* __restrict__ Qsh, uint32_t LB, const DevTables T) {
   constexpr int W = 2 * NWT;   // 32-bit words of one Q/q_j row
   constexpr int N = W + 3;     // accumulator words: the sum is < L*Q < 2^(32 W + 7)
   extern __shared__ __align__(16) u32 s_q[];  // [L][W] then [LB][W + 2]
@@ -102,10 +187,45 @@ __global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y
     const u32* gs = reinterpret_cast<const u32*>(Qsh);
     for (uint32_t i = threadIdx.x; i < LB * (W + 2); i += blockDim.x) s_q[L * W + i] = gs[i];
   }
+  u64* s_vc = reinterpret_cast<u64*>(s_q + (((size_t)L * W + (size_t)LB * (W + 2) + 3) & ~(size_t)3));  // [L][10], 16-byte aligned
+  if (T.lift_fast) {
+    for (uint32_t j = threadIdx.x; j < L; j += blockDim.x) {
+      u64* cj = s_vc + (size_t)j * 10;
+      cj[0] = T.lc[j].q; cj[1] = T.lc[j].mu64; cj[2] = T.sh_v[j]; cj[3] = T.sh_v_sh[j];
+      for (int t = 0; t < 3; t++) { cj[4 + 2 * t] = T.sh_r[(size_t)j * 3 + t]; cj[5 + 2 * t] = T.sh_r_sh[(size_t)j * 3 + t]; }
+    }
+  }
   __syncthreads();
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = blockIdx.y;
   if (s >= S) return;
+  if (T.lift_fast && i + 2 != ellp1) {  // every value except `last` (index l-1) is small for a decodable share
+    u64 mag[4];
+    bool neg = false, ok = false;
+    const u64* yb = y + (size_t)i * S + s;
+    const size_t ystride = (size_t)ellp1 * S;
+    switch (T.shortSW) {
+      case 1: ok = short_lift<1>(yb, ystride, L, T, s_vc, mag, neg); break;
+      case 2: ok = short_lift<2>(yb, ystride, L, T, s_vc, mag, neg); break;
+      case 3: ok = short_lift<3>(yb, ystride, L, T, s_vc, mag, neg); break;
+      case 4: ok = short_lift<4>(yb, ystride, L, T, s_vc, mag, neg); break;
+    }
+    if (ok) {
+      u64* xo = X + ((size_t)i * NW) * S + s;
+      const bool zero = (mag[0] | mag[1] | mag[2] | mag[3]) == 0;
+      if (!neg || zero) {
+        for (uint32_t w = 0; w < NW; w++) xo[(size_t)w * S] = w < 4 ? mag[w] : 0;
+      } else {  // Q - |x|
+        u64 borrow = 0;
+        for (uint32_t w = 0; w < NW; w++) {
+          const u64 qw = T.Qw[w], mw = w < 4 ? mag[w] : 0, d1 = qw - mw, b1 = qw < mw, d2 = d1 - borrow, b2 = d1 < borrow;
+          xo[(size_t)w * S] = d2;
+          borrow = b1 | b2;
+        }
+      }
+      return;
+    }
+  }
   u32 acc[N];
 #pragma unroll
   for (int w = 0; w < N; w++) acc[w] = 0;
@@ -141,12 +261,12 @@ __global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y
 void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st) {
   if (S == 0) return;
   dim3 grid((unsigned)((S + 127) / 128), T.ell + 1);
-  const size_t smem = ((size_t)T.L * 2 * T.NWT + (size_t)T.LB * (2 * T.NWT + 2)) * 4;
+  const size_t smem = ((size_t)T.L * 2 * T.NWT + (size_t)T.LB * (2 * T.NWT + 2) + 4) * 4 + (size_t)T.L * 10 * 8;
 #define PVW_LIFT_CASE(N)                                                                                              \
   case N: {                                                                                                           \
     auto kern = crt_lift_kernel<N>;                                                                                   \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);                              \
-    kern<<<grid, 128, smem, st>>>(y, X, S, T.L, T.ell + 1, T.NW, T.qhat, T.Qsh, T.LB);                                \
+    kern<<<grid, 128, smem, st>>>(y, X, S, T.L, T.ell + 1, T.NW, T.qhat, T.Qsh, T.LB, T);                             \
     break;                                                                                                            \
   }
   switch (T.NWT) {

@@ -200,6 +200,14 @@ struct HostParams {
   std::vector<uint64_t> qhat, Qsh; uint32_t LB = 0;
   // decode tail constants (NW words each unless noted)
   std::vector<uint64_t> Qw, halfQ, Mw, halfM, Dw;   // Q, floor(Q/2), M = delta^(ell-1), floor(M/2), delta
+  // short CRT lift (decode fast path): sub-basis q_0..q_{Ls-1} whose product Q_s exceeds every value a decodable
+  // share produces (|tmp_i| ~ Delta * noise, |w| < 2^65); Ls == 0 disables it
+  uint32_t shortL = 0, shortSW = 0;                 // limbs and 64-bit words of Q_s
+  std::vector<uint64_t> sh_c, sh_c_sh;              // [Ls] (Q/q_j mod q_j) * (Q_s/q_j)^-1 mod q_j  (+ Shoup companion)
+  std::vector<uint64_t> sh_qhat;                    // [Ls][SW] Q_s / q_j
+  std::vector<uint64_t> sh_Q, sh_halfQ;             // [SW]
+  std::vector<uint64_t> sh_v, sh_v_sh;              // [L] (Q/q_j) mod q_j: v_j = y_j * sh_v_j  (+ Shoup)
+  std::vector<uint64_t> sh_r, sh_r_sh;              // [L][3] 2^64, 2^128, 2^192 mod q_j (+ Shoup)
   // Knuth-D divisors, normalised so that the top bit of the top word is set
   struct Divisor { std::vector<uint64_t> v; uint32_t n = 0, shift = 0; uint64_t vinv = 0; };
   Divisor divM, div2D;
@@ -300,6 +308,40 @@ struct HostParams {
     delta.to_words(Dw.data(), NW);
     divM = make_divisor(delta_pow);
     div2D = make_divisor(BigU::add(delta, delta));
+    // short lift
+    sh_v.assign(L, 0); sh_v_sh = sh_v; sh_r.assign((size_t)L * 3, 0); sh_r_sh = sh_r;
+    for (uint32_t j = 0; j < L; j++) {
+      const uint64_t q = moduli[j];
+      BigU qh = BigU::divmod_small(Q, q, nullptr);
+      sh_v[j] = qh.mod_small(q); sh_v_sh[j] = h_shoup(sh_v[j], q);
+      uint64_t r = (uint64_t)((((u128)1) << 64) % q), pw = r;
+      for (int t = 0; t < 3; t++) { sh_r[(size_t)j * 3 + t] = pw; sh_r_sh[(size_t)j * 3 + t] = h_shoup(pw, q); pw = h_mulmod(pw, r, q); }
+    }
+    shortL = 0; shortSW = 0;
+    {
+      const size_t need_bits = delta.bits() + 64 + 2;
+      BigU Qs(1);
+      for (uint32_t s = 1; s < L; s++) {
+        Qs = BigU::mul_small(Qs, moduli[s - 1]);
+        if (Qs.bits() > need_bits + 1 && Qs.w.size() <= 4) { shortL = s; break; }
+        if (Qs.w.size() > 4) break;
+      }
+      if (shortL) {
+        BigU Qs2(1);
+        for (uint32_t j = 0; j < shortL; j++) Qs2 = BigU::mul_small(Qs2, moduli[j]);
+        shortSW = (uint32_t)Qs2.w.size();
+        sh_Q.assign(shortSW, 0); sh_halfQ = sh_Q;
+        Qs2.to_words(sh_Q.data(), shortSW); BigU::shr1(Qs2).to_words(sh_halfQ.data(), shortSW);
+        sh_c.assign(shortL, 0); sh_c_sh = sh_c; sh_qhat.assign((size_t)shortL * shortSW, 0);
+        for (uint32_t j = 0; j < shortL; j++) {
+          const uint64_t q = moduli[j];
+          BigU h = BigU::divmod_small(Qs2, q, nullptr);
+          h.to_words(&sh_qhat[(size_t)j * shortSW], shortSW);
+          const uint64_t inv = h_powmod(h.mod_small(q), q - 2, q);
+          sh_c[j] = h_mulmod(sh_v[j], inv, q); sh_c_sh[j] = h_shoup(sh_c[j], q);
+        }
+      }
+    }
   }
 
   // verify_correctness_condition, parameters.rs:510-551 (f64, same evaluation order)

@@ -30,6 +30,10 @@ struct DevTables {
   uint32_t L, ell, NW, NWT, LB;
   uint32_t divM_n, divM_shift, div2D_n, div2D_shift;
   u64 divM_vinv, div2D_vinv;
+  // short lift (decode fast path), see hostparams.hpp
+  const u64 *sh_c, *sh_c_sh, *sh_qhat, *sh_Q, *sh_halfQ, *sh_v, *sh_v_sh, *sh_r, *sh_r_sh;
+  uint32_t shortL, shortSW;
+  int lift_fast;  // 1 = try the short lift first
   int tail_impl;  // 1 = register-resident decode tail where a specialisation exists, 0 = generic kernel
 };
 

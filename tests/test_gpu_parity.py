@@ -138,9 +138,18 @@ def test_decode_of_arbitrary_polynomials(pkg, name):
         enc = co.encode_scalar(m & (2 ** 64 - 1))
         z[2 + i] = (np.array(P.moduli, dtype=np.uint64)[:, None] - enc) % np.array(P.moduli, dtype=np.uint64)[:, None]
     want = co.decode(z)
-    for impl in (1, 0):                                   # register-resident specialisation (where one exists) and generic tail
+    # valid shares too (small noise: the short-lift fast path applies), next to the garbage above
+    rng2 = np.random.default_rng(4)
+    for i in range(10, 60):
+        m = int(rng2.integers(0, 2 ** 62))
+        noise = rng2.integers(-50, 51, size=P.l)
+        zz = [(-(m * P.delta ** t + int(noise[t]))) % P.Q for t in range(P.l)]
+        z[i] = np.array(P.ntt_forward(P.bigints_to_poly(zz)), dtype=np.uint64)
+    want = co.decode(z)
+    for impl, fast in ((1, 1), (0, 1), (1, 0), (0, 0)):   # register-resident / generic tail x short-lift on / off
         eng.set_option("tail_impl", impl)
-        assert (eng.decode_batch(z) == want).all(), f"tail_impl={impl}"
+        eng.set_option("lift_fast", fast)
+        assert (eng.decode_batch(z) == want).all(), f"tail_impl={impl} lift_fast={fast}"
 
 
 @pytest.mark.parametrize("name", ["EX", "RAG", "T16"])

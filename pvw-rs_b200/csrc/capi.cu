@@ -202,36 +202,36 @@ const void* stage_in_overlapped(pvw_ctx* c, DevBuf& buf, const void* src, size_t
 }
 
 // host-layout polynomials [count][L][ell]  <->  limb-major [L][count][ell] slice inside a bigger array
-void to_limb_major(pvw_ctx* c, const u64* in_host_layout, uint64_t count, u64* out, size_t out_limb_stride) {
+void to_limb_major(pvw_ctx* c, const u64* in_host_layout, uint64_t count, u64* out, size_t out_limb_stride, bool operand) {
   const uint32_t L = c->hp.L, ell = c->hp.ell;
-  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(in_host_layout, out, 1, count, L, ell, 0, (size_t)L * ell, ell, 0, ell, out_limb_stride, c->stream); });
+  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(in_host_layout, out, 1, count, L, ell, 0, (size_t)L * ell, ell, 0, ell, out_limb_stride, c->stream, operand ? 1 : 0); });
 }
-void from_limb_major(pvw_ctx* c, const u64* in, size_t in_limb_stride, uint64_t count, u64* out_host_layout) {
+void from_limb_major(pvw_ctx* c, const u64* in, size_t in_limb_stride, uint64_t count, u64* out_host_layout, bool operand) {
   const uint32_t L = c->hp.L, ell = c->hp.ell;
   // x = limb is the fastest thread axis here so that the host-layout side (the output) is written contiguously
-  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(in, out_host_layout, 1, L, count, ell, 0, in_limb_stride, ell, 0, ell, (size_t)L * ell, c->stream); });
+  launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(in, out_host_layout, 1, L, count, ell, 0, in_limb_stride, ell, 0, ell, (size_t)L * ell, c->stream, operand ? 2 : 0); });
 }
 
 // upload `count` polynomials given in host layout (host or device memory) into limb-major dst (+ offset handled by caller)
-void upload_polys(pvw_ctx* c, const uint64_t* src, uint64_t count, u64* dst, size_t dst_limb_stride, uint32_t flags) {
+void upload_polys(pvw_ctx* c, const uint64_t* src, uint64_t count, u64* dst, size_t dst_limb_stride, uint32_t flags, bool operand) {
   const size_t poly = c->poly();
-  if (flags & PVW_IO_DEVICE) { to_limb_major(c, reinterpret_cast<const u64*>(src), count, dst, dst_limb_stride); return; }
+  if (flags & PVW_IO_DEVICE) { to_limb_major(c, reinterpret_cast<const u64*>(src), count, dst, dst_limb_stride, operand); return; }
   uint64_t per = std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / (poly * 8));
   for (uint64_t o = 0; o < count; o += per) {
     uint64_t n = std::min(per, count - o);
     c->stage.ensure(n * poly * 8);
     CUDA_CHECK(cudaMemcpyAsync(c->stage.p, src + o * poly, n * poly * 8, cudaMemcpyHostToDevice, c->stream));
-    to_limb_major(c, c->stage.as<u64>(), n, dst + o * c->hp.ell, dst_limb_stride);
+    to_limb_major(c, c->stage.as<u64>(), n, dst + o * c->hp.ell, dst_limb_stride, operand);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
   }
 }
-void download_polys(pvw_ctx* c, const u64* src, size_t src_limb_stride, uint64_t count, uint64_t* dst_host) {
+void download_polys(pvw_ctx* c, const u64* src, size_t src_limb_stride, uint64_t count, uint64_t* dst_host, bool operand) {
   const size_t poly = c->poly();
   uint64_t per = std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / (poly * 8));
   for (uint64_t o = 0; o < count; o += per) {
     uint64_t n = std::min(per, count - o);
     c->stage.ensure(n * poly * 8);
-    from_limb_major(c, src + o * c->hp.ell, src_limb_stride, n, c->stage.as<u64>());
+    from_limb_major(c, src + o * c->hp.ell, src_limb_stride, n, c->stage.as<u64>(), operand);
     CUDA_CHECK(cudaMemcpyAsync(dst_host + o * poly, c->stage.p, n * poly * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
@@ -362,7 +362,7 @@ int pvw_crs_upload(pvw_ctx* c, const uint64_t* A, uint32_t flags) {
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
     const size_t kk = (size_t)k * k;
     c->A.ensure((size_t)L * kk * ell * 8);
-    upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, flags);
+    upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, flags, true);
     c->A_set = true;
     c->At_valid = false;
   });
@@ -371,7 +371,7 @@ int pvw_crs_download(pvw_ctx* c, uint64_t* A) {
   return guarded(c, [&] {
     require(c->A_set, PVW_ERR_INVALID_PARAMETERS, "CRS has not been uploaded");
     const size_t kk = (size_t)c->hp.k * c->hp.k;
-    download_polys(c, c->A.as<u64>(), kk * c->hp.ell, kk, A);
+    download_polys(c, c->A.as<u64>(), kk * c->hp.ell, kk, A, true);
   });
 }
 
@@ -396,7 +396,7 @@ int pvw_crs_generate_deterministic(pvw_ctx* c, const uint8_t seed[32], uint64_t*
     if (!A) { local.resize(kk * L * ell); A = local.data(); }
     crs_new_deterministic(seed, k, c->hp.moduli.data(), L, ell, A);
     c->A.ensure((size_t)L * kk * ell * 8);
-    upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, PVW_IO_HOST);
+    upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, PVW_IO_HOST, true);
     c->A_set = true;
     c->At_valid = false;
   });
@@ -428,7 +428,7 @@ int pvw_pk_upload_rows(pvw_ctx* c, uint32_t row, uint32_t count, const uint64_t*
     check_rows(c, row, count);
     ensure_B(c);
     const uint32_t k = c->hp.k, ell = c->hp.ell;
-    upload_polys(c, B, (uint64_t)count * k, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, flags);
+    upload_polys(c, B, (uint64_t)count * k, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, flags, true);
     c->num_keys = std::max(c->num_keys, row + count);
   });
 }
@@ -438,7 +438,7 @@ int pvw_pk_download_rows(pvw_ctx* c, uint32_t row, uint32_t count, uint64_t* B) 
     check_rows(c, row, count);
     ensure_B(c);
     const uint32_t k = c->hp.k, ell = c->hp.ell;
-    download_polys(c, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, (uint64_t)count * k, B);
+    download_polys(c, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, (uint64_t)count * k, B, true);
   });
 }
 int pvw_pk_num_keys(const pvw_ctx* c, uint32_t* num_keys) {
@@ -461,7 +461,7 @@ int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk
     const long long* d_e = (const long long*)stage_in(c, c->in_small2, e, small, flags);
     // s_hat[p][limb][j][ell]
     c->rhat.ensure((size_t)count * L * k * ell * 8);
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, c->stream); });
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, c->stream, false, true); });
     // B rows <- NTT(e): item idx = p*k + cidx lands at B[limb][row+p][cidx]
     u64* Brow = c->B.as<u64>() + (size_t)(row - c->row0) * k * ell;
     launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e, nullptr, (uint64_t)count * k, (uint32_t)std::min<uint64_t>((uint64_t)count * k, 0xFFFFFFFFu), Brow, 0,
@@ -469,7 +469,7 @@ int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk
     GemmArgs g{};
     g.M = c->At.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
     g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell;
-    g.O = Brow; g.O_ls = (size_t)c->nrows * k * ell; g.O_ds = (size_t)k * ell;
+    g.O = Brow; g.O_ls = (size_t)c->nrows * k * ell; g.O_ds = (size_t)k * ell; g.O_packed = 1;  // B is an operand of the c2 product
     g.rows = k; g.D = count; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
     gemm(c, g);
     c->num_keys = std::max(c->num_keys, row + count);
@@ -489,7 +489,7 @@ int pvw_crs_multiply_by_randomness(pvw_ctx* c, uint32_t D, const uint64_t* r_hat
     c->z.ensure((size_t)D * per * 8);
     CUDA_CHECK(cudaMemcpyAsync(c->stage.p, r_hat, (size_t)D * per * 8, cudaMemcpyHostToDevice, c->stream));
     // [D][k][L][ell] -> [D][L][k][ell]
-    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(c->stage.as<u64>(), c->rhat.as<u64>(), D, k, L, ell, per, (size_t)L * ell, ell, per, ell, (size_t)k * ell, c->stream); });
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_permute(c->stage.as<u64>(), c->rhat.as<u64>(), D, k, L, ell, per, (size_t)L * ell, ell, per, ell, (size_t)k * ell, c->stream, 1); });
     CUDA_CHECK(cudaMemsetAsync(c->z.p, 0, (size_t)D * per * 8, c->stream));
     GemmArgs g{};
     g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
@@ -547,7 +547,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     const u64* d_m = (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]);
     // r_hat[d][limb][j][ell]   (encryption.rs:147-154)
     c->rhat.ensure((size_t)D * w1 * 8);
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream); });
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream, false, true); });
     u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
     if (c1_hi > c1_lo) {
@@ -557,7 +557,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       GemmArgs g{};
       g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
       g.V = c->rhat.as<u64>() + (size_t)c1_lo * w1; g.V_ls = (size_t)k * ell; g.V_ds = w1;
-      g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1;
+      g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_packed = 1;  // c1 is an operand of the decrypt product
       g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
       gemm(c, g);
     }
@@ -587,16 +587,16 @@ int pvw_ct_download(pvw_ctx* c, uint32_t slot, uint64_t* c1, uint64_t* c2) {
   return guarded(c, [&] {
     require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
-    if (c1) download_polys(c, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, k, c1);
-    if (c2) download_polys(c, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, nrows, c2);
+    if (c1) download_polys(c, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, k, c1, true);
+    if (c2) download_polys(c, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, nrows, c2, false);
   });
 }
 int pvw_ct_upload(pvw_ctx* c, uint32_t slot, const uint64_t* c1, const uint64_t* c2) {
   return guarded(c, [&] {
     require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
-    if (c1) upload_polys(c, c1, k, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, PVW_IO_HOST);
-    if (c2) upload_polys(c, c2, nrows, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, PVW_IO_HOST);
+    if (c1) upload_polys(c, c1, k, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, PVW_IO_HOST, true);
+    if (c2) upload_polys(c, c2, nrows, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, PVW_IO_HOST, false);
   });
 }
 int pvw_ct_c1_device_ptr(pvw_ctx* c, uint32_t slot, void** ptr, uint64_t* slot_stride) {
@@ -679,7 +679,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
       if (host) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[chunk_no], 0));
       // s_hat[limb][p][j][ell]   (SecretKey::get_polynomial, secret_key.rs:98-112 -- once per party, not per ciphertext)
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream); });
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream, false, true); });
       // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274)
       GemmArgs g{};
       g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;

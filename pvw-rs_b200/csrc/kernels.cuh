@@ -1,4 +1,7 @@
 // kernels.cuh -- launcher declarations shared by the .cu files of libpvw_b200.so.
+// Operand form: every array the multiply-accumulate kernel reads as M or V (A, At, B, r_hat, s_hat, the c1 store) holds each
+// residue x < 2^62 as packed 31-bit halves ((x >> 31) << 32 | (x & 0x7fffffff)), so that the inner loop needs no shifts or
+// masks; everything else (c2 store, z, decode scratch, all host-facing data) holds canonical residues.
 // Device layout ("limb-major"): a vector of polynomials is stored as [..][L][len][ell] so that, for one RNS limb,
 // the `len` polynomials' ell-slot blocks are contiguous (len*ell*8 bytes): the modulus is uniform per CTA and a
 // row of k polynomials is one contiguous 1D bulk-copy (TMA) source.
@@ -41,11 +44,13 @@ struct DevTables {
 // small signed coefficients -> RNS -> forward NTT (+ optional message encoding), written in the device layout:
 //   item idx in [0,count): vec = idx / inner, j = idx % inner;  out[vec*vstride + limb*lstride + j*ell + c]
 //   value = NTT(rns(coef[idx]))[c] (+ (m[idx] as i64 mod q) * gadget_hat[limb][c] when m != nullptr)
+// pack_out: write the 31-bit-halves operand form (modarith.cuh pack_halves) that the multiply-accumulate kernel reads
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false);
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false, bool pack_out = false);
 // generic strided block copy:  out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c],  c < blk
+// xform: 0 = plain copy, 1 = canonical residue -> packed halves, 2 = packed halves -> canonical residue
 void launch_permute(const u64* in, u64* out, uint64_t Bn, uint64_t X, uint64_t Y, uint32_t blk, size_t ibs, size_t ixs, size_t iys,
-                    size_t obs, size_t oxs, size_t oys, cudaStream_t st);
+                    size_t obs, size_t oxs, size_t oys, cudaStream_t st, int xform = 0);
 
 // ---- mac.cu -------------------------------------------------------------------------------------------------
 // NTT-domain polynomial matrix product for every limb and slot:
@@ -63,6 +68,7 @@ struct GemmArgs {
   uint32_t rows, D, k, L, ell;
   int mode;
   const LimbConst* lc;
+  int O_packed;    // 1: O is written in the packed-halves operand form (it is the M or V operand of a later product)
   int tile;        // register-tile / occupancy variant (mac.cu launch_mac_gemm)
   int refill_lag;  // chunks between a stage's last use and its refill (1 .. NS-1)
 };

@@ -161,7 +161,7 @@ __device__ __forceinline__ void tensor_g2s_3d(uint32_t dst, const CUtensorMap* t
 }
 template <int ELL, int TR, int TD, int GD, int KC, int NB, int NS>
 __global__ void __launch_bounds__(kComputeThreads, NB) mac_gemm_tensor_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap tmapM) {
-  using W = Worker<ELL, TR, TD, GD, KC, 4, false, false, kComputeThreads, true>;
+  using W = Worker<ELL, TR, TD, GD, KC, 4, false, true, kComputeThreads, true>;
   using C = typename W::C;
   constexpr int NW = kComputeThreads / 32;
   static_assert(C::DT <= 32, "one lane per dealer row");

@@ -37,7 +37,7 @@ struct TileCfg {
 
 // NJ_: polynomials per straight-line block; ROLL: blocks in a real loop (small code) instead of unrolled;
 // PACKED: operands are stored as 31-bit halves (x1 << 32 | x0, modarith.cuh pack_halves) instead of canonical residues
-template <int ELL, int TR, int TD, int GD, int KC, int NJ_ = 4, bool ROLL = false, bool PACKED = false, int THREADS_ = kComputeThreads,
+template <int ELL, int TR, int TD, int GD, int KC, int NJ_ = 4, bool ROLL = false, bool PACKED = true, int THREADS_ = kComputeThreads,
           bool DENSE_M = false>
 struct Worker {
   using C = TileCfg<ELL, TR, TD, GD, KC, THREADS_, DENSE_M>;
@@ -103,7 +103,9 @@ struct Worker {
 #pragma unroll
       for (int jj = 0; jj < KC; jj += NJ) {
         block<NJ>(ms, vs, jj);
+#ifndef PVW_EXP_NO_BARRIER
         asm volatile("" ::: "memory");
+#endif
       }
     } else {
 #pragma unroll 1
@@ -130,7 +132,7 @@ struct Worker {
           const uint32_t srow = g.S_rowmap ? g.S_rowmap[row] : row;
           v = submod(v, g.S[(size_t)ds * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * ELL + c], lc.q);
         }
-        *o = v;
+        *o = g.O_packed ? pack_halves(v) : v;
       }
     }
   }

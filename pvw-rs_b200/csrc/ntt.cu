@@ -10,7 +10,7 @@
 
 namespace pvw {
 
-template <int ELL, bool ACCUM>
+template <int ELL, int MODE>  // MODE 0: store canonical, 1: accumulate into canonical, 2: store packed halves (operand form)
 __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
@@ -46,9 +46,11 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
 #pragma unroll
   for (int t = 0; t < ELL / 2; t++) {
-    if (ACCUM) {  // out += value (the matrix product was stored first; host-pointer encrypt overlaps the e2 / m copy with it)
+    if (MODE == 1) {  // out += value (the matrix product was stored first; host-pointer encrypt overlaps the e2 / m copy with it)
       const ulonglong2 o = dst[t];
       dst[t] = make_ulonglong2(addmod(a[2 * t], o.x, lc.q), addmod(a[2 * t + 1], o.y, lc.q));
+    } else if (MODE == 2) {
+      dst[t] = make_ulonglong2(pack_halves(a[2 * t]), pack_halves(a[2 * t + 1]));
     } else {
       dst[t] = make_ulonglong2(a[2 * t], a[2 * t + 1]);
     }
@@ -56,15 +58,17 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 }
 
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate) {
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out) {
   if (count == 0) return;
   dim3 grid((unsigned)((count + 127) / 128), T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
     if (accumulate)                                                                                                           \
-      ntt_small_kernel<E, true><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+      ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+    else if (pack_out)                                                                                                        \
+      ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
     else                                                                                                                      \
-      ntt_small_kernel<E, false><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh); \
+      ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
     break;
   switch (T.ell) {
     PVW_NTT_CASE(8)
@@ -75,6 +79,7 @@ void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, u
 }
 
 // out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c]; one thread per 16 bytes (blk is a multiple of 2)
+template <int XFORM>
 __global__ void __launch_bounds__(256) permute_kernel(const ulonglong2* __restrict__ in, ulonglong2* __restrict__ out, uint64_t total,
                                                       uint64_t X, uint64_t Y, uint32_t blk2, size_t ibs, size_t ixs, size_t iys, size_t obs,
                                                       size_t oxs, size_t oys) {
@@ -85,15 +90,22 @@ __global__ void __launch_bounds__(256) permute_kernel(const ulonglong2* __restri
   uint64_t x = r % X; r /= X;   // x fastest: consecutive threads walk the output's contiguous axis when oxs == blk
   uint64_t y = r % Y;
   uint64_t b = r / Y;
-  out[(b * obs + x * oxs + y * oys) / 2 + c] = in[(b * ibs + x * ixs + y * iys) / 2 + c];
+  ulonglong2 v = in[(b * ibs + x * ixs + y * iys) / 2 + c];
+  if (XFORM == 1) v = make_ulonglong2(pack_halves(v.x), pack_halves(v.y));
+  if (XFORM == 2) v = make_ulonglong2(unpack_halves(v.x), unpack_halves(v.y));
+  out[(b * obs + x * oxs + y * oys) / 2 + c] = v;
 }
 
 void launch_permute(const u64* in, u64* out, uint64_t Bn, uint64_t X, uint64_t Y, uint32_t blk, size_t ibs, size_t ixs, size_t iys,
-                    size_t obs, size_t oxs, size_t oys, cudaStream_t st) {
+                    size_t obs, size_t oxs, size_t oys, cudaStream_t st, int xform) {
   uint64_t total = Bn * X * Y * (blk / 2);
   if (total == 0) return;
-  permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(in), reinterpret_cast<ulonglong2*>(out),
-                                                                  total, X, Y, blk / 2, ibs, ixs, iys, obs, oxs, oys);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const ulonglong2* i2 = reinterpret_cast<const ulonglong2*>(in);
+  ulonglong2* o2 = reinterpret_cast<ulonglong2*>(out);
+  if (xform == 1) permute_kernel<1><<<blocks, 256, 0, st>>>(i2, o2, total, X, Y, blk / 2, ibs, ixs, iys, obs, oxs, oys);
+  else if (xform == 2) permute_kernel<2><<<blocks, 256, 0, st>>>(i2, o2, total, X, Y, blk / 2, ibs, ixs, iys, obs, oxs, oys);
+  else permute_kernel<0><<<blocks, 256, 0, st>>>(i2, o2, total, X, Y, blk / 2, ibs, ixs, iys, obs, oxs, oys);
 }
 
 }  // namespace pvw

@@ -276,7 +276,7 @@ static double worker_rate(const char* name, u64* out, const u64* in, int sms, in
     float ms; cudaEventElapsedTime(&ms, a, b);
     if (r > 0 && ms < best) best = ms;
   }
-  const double macs = (double)sms * NB * W::C::RT * W::C::DT * 8 /*ell*/ * 8 /*KC*/ * iters;
+  const double macs = (double)sms * NB * W::C::RT * W::C::DT * 8 /*ell*/ * (double)(W::C::STAGE > 0 ? (W::C::ROWB - 16) / 64 : 8) * iters;
   printf("{\"worker\": \"%s\", \"regs\": %d, \"ctas_per_sm\": %d, \"mac_per_s\": %.4g, \"err\": \"%s\"}\n", name, fa.numRegs, occ,
          macs / (best * 1e-3), cudaGetErrorString(cudaGetLastError()));
   return macs / (best * 1e-3);
@@ -350,15 +350,11 @@ int main(int argc, char** argv) {
   double t4 = time_ms([&] { k_mack<CH><<<blocks, threads>>>(out, in, iters); });
   {
     const int wi = iters / 8;
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 256>, 2>("4x2 canonical 256thr x2 (production)", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 192>, 3>("4x2 canonical 192thr x3", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 320>, 2>("4x2 canonical 320thr x2", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 128>, 4>("4x2 canonical 128thr x4", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, false, 384>, 1>("4x2 canonical 384thr x1", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 2, 8, 4, false, false, 256>, 2>("4x2 GD=2 canonical 256thr x2", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 8, 8, 4, false, false, 256>, 2>("4x2 GD=8 canonical 256thr x2", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 4, 4, 8, 4, false, false, 256>, 1>("4x4 canonical 256thr x1", out, in, sms, wi, 0);
-    worker_rate<Worker<8, 4, 2, 4, 8, 4, false, true, 256>, 2>("4x2 packed 256thr x2", out, in, sms, wi, 1);
+    worker_rate<Worker<8, 4, 2, 8, 16, 4, false, false, 256>, 2>("4x2 GD8 KC16 nj4 (production)", out, in, sms, wi / 2, 0);
+    worker_rate<Worker<8, 4, 2, 8, 16, 8, false, false, 256>, 2>("4x2 GD8 KC16 nj8", out, in, sms, wi / 2, 0);
+    worker_rate<Worker<8, 4, 2, 8, 16, 2, false, false, 256>, 2>("4x2 GD8 KC16 nj2", out, in, sms, wi / 2, 0);
+    worker_rate<Worker<8, 4, 2, 8, 16, 4, false, true, 256>, 2>("4x2 GD8 KC16 nj4 packed", out, in, sms, wi / 2, 1);
+    worker_rate<Worker<8, 2, 4, 8, 16, 4, false, false, 256>, 2>("2x4 GD8 KC16 nj4", out, in, sms, wi / 2, 0);
   }
   double tt[4];
   tt[0] = time_ms([&] { k_tile<0><<<sms, 256>>>(out, in, iters / 4); });

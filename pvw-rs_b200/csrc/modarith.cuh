@@ -64,6 +64,7 @@ PVW_DEV u64 reduce_i64(long long x, const LimbConst& c) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// [measured alternative, used only by tools/int_peaks.cu: 2.1e12 MAC/s in registers]
 // Lazy 160-bit accumulator for sum_j a_j * b_j with a_j, b_j < 2^62: products are added unreduced and one Barrett
 // reduction runs after the whole k-term sum (k < 2^32).  The four 32x32 partial products go to an "even" column
 // set (a0*b0 at bit 0, a1*b1 at bit 64; words e0..e4) and an "odd" one (a0*b1 + a1*b0 at bit 32; words o0..o2) so
@@ -111,6 +112,7 @@ PVW_DEV u64 acc_reduce(const Acc160& c, const LimbConst& lc) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// [PRODUCTION accumulator of mac.cu: 2.8e12 MAC/s in registers]
 // Three-multiply lazy accumulator (Karatsuba on 31-bit halves).  x = x1*2^31 + x0 with x0, x1 < 2^31 (x < 2^62) and
 // xs = x0 + x1 < 2^32, so all three partial products are single 32x32->64 IMAD.WIDE.U32:
 //     a*b = H*2^62 + (K - L - H)*2^31 + L,   L = a0*b0,  H = a1*b1,  K = as*bs.
@@ -136,8 +138,8 @@ struct AccK {
   u32 l0, l1, l2, h0, h1, h2, k0, k1, k2;
 };
 PVW_DEV void acck_zero(AccK& c) { c.l0 = c.l1 = c.l2 = c.h0 = c.h1 = c.h2 = c.k0 = c.k1 = c.k2 = 0; }
-// SPLIT_L: form L = a0*b0 with a plain IMAD.WIDE (no addend: 2 fma-pipe cycles instead of 4) and add it into the 96-bit
-// sum with three IADD3 on the otherwise idle alu pipe -- balances the two pipes (integer-pipe model)
+// PVW_SPLIT_L=1 (measured, slower in situ): form L = a0*b0 with a plain IMAD.WIDE (no addend) and add it into the 96-bit
+// sum with three IADD3 on the alu pipe
 #ifndef PVW_SPLIT_L
 #define PVW_SPLIT_L 0
 #endif
@@ -202,11 +204,12 @@ PVW_DEV u64 acck_reduce(const AccK& c, const LimbConst& lc) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Carry-free lazy accumulator (the production path of mac.cu).  Measured on B200 (tools/int_peaks.cu): a plain
-// IMAD.WIDE.U32 issues at 64 lanes/clk/SM, one that produces or consumes a carry at half that.  So operands are kept
-// as 31-bit halves packed in one word, x = x1*2^31 + x0 -> (x1 << 32) | x0, every partial product is < 2^62, and
-// four consecutive terms are summed in plain 64-bit IMAD.WIDE accumulators (no carry possible) before being folded
-// into 96-bit sums on the alu pipe:  4 IMAD.WIDE (fma pipe) + ~2.5 IADD3 (alu pipe) per multiply-accumulate.
+// Packed operand form (production): x = x1*2^31 + x0 is stored as (x1 << 32) | x0, see kernels.cuh.
+//
+// [measured alternative, used only by tools/int_peaks.cu: 1.6e12 MAC/s -- ptxas re-associates the plain mad.wide chains
+//  into IMAD.WIDE(RZ) + IADD3 + IMAD.X, so dropping the carries does not pay]
+// Carry-free lazy accumulator: every partial product of 31-bit halves is < 2^62, so four consecutive terms are summed in
+// plain 64-bit accumulators (no carry possible) before being folded into 96-bit sums:
 //     a*b = H*2^62 + (M01 + M10)*2^31 + L,   L = a0*b0, M01 = a0*b1, M10 = a1*b0, H = a1*b1
 // ---------------------------------------------------------------------------------------------------------------
 PVW_DEV u64 pack_halves(u64 x) { return ((x >> 31) << 32) | (x & 0x7fffffffull); }       // x < 2^62
@@ -255,6 +258,7 @@ PVW_DEV u64 accw_reduce(const AccW& c, const LimbConst& lc) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// [measured alternative, used only by tools/int_peaks.cu: 2.0e12 MAC/s]
 // Hybrid: Karatsuba with the two small products (L = a0*b0, H = a1*b1 < 2^62) summed carry-free four at a time and
 // the cross term K = (a0+a1)*(b0+b1) < 2^64 accumulated with carry.  Packed operand word: (x1 << 32) | x0.
 // ---------------------------------------------------------------------------------------------------------------

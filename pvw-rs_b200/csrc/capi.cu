@@ -241,7 +241,7 @@ void require(bool cond, int code, const std::string& msg) { if (!cond) throw Pvw
 
 void gemm(pvw_ctx* c, GemmArgs a) {
   a.tile = c->gemm_tile;
-  a.refill_lag = c->refill_lag;
+  a.refill_lag = a.D == 1 ? 1 : c->refill_lag;  // the HBM-bound matrix-vector form wants the deepest prefetch
   // algorithmic bytes: per (dealer, row) one k-polynomial operand row read + one polynomial written
   const double bytes = (double)a.D * a.rows * (a.k + 1.0) * a.L * a.ell * 8.0;
   launch(c, PVW_KERNEL_MAC, bytes, [&] { launch_mac_gemm(a, c->gemm_impl, c->stream); });

@@ -274,14 +274,15 @@ void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
   switch (a.ell) {
     case 8:
       if (matvec && tile == 0) launch_cfg<8, 2, 1, 1, 8, 1>(a, impl, st);
-      else if (matvec) launch_cfg<8, 1, 1, 1, 16, 1>(a, impl, st);
+      else if (matvec && tile == 2) launch_cfg<8, 1, 1, 1, 16, 1>(a, impl, st);
+      else if (matvec) launch_cfg<8, 1, 1, 1, 16, 2, 3>(a, impl, st);   // D = 1: two CTAs/SM x 3 stages of 1 KB row copies: 91-95 % of HBM
       else if (tile == 0) launch_cfg<8, 4, 4, 4, 8, 1>(a, impl, st);
       else if (tile == 2) launch_cfg<8, 4, 2, 4, 8, 2>(a, impl, st);
       else if (tile == 3) launch_cfg<8, 4, 2, 4, 16, 2, 2>(a, impl, st);   // 32 rows x 8 dealers, 16 polynomials x 2 stages
       else launch_cfg<8, 4, 2, 8, 16, 2, 3>(a, impl, st);
       break;
     case 16:
-      if (matvec) launch_cfg<16, 2, 1, 1, 8, 1>(a, impl, st);
+      if (matvec) launch_cfg<16, 2, 1, 1, 8, 2, 3>(a, impl, st);
       else if (tile == 0) launch_cfg<16, 4, 4, 4, 8, 1>(a, impl, st);
       else if (tile == 2) launch_cfg<16, 4, 2, 4, 8, 2>(a, impl, st);
       else launch_cfg<16, 4, 2, 4, 16, 2, 2>(a, impl, st);

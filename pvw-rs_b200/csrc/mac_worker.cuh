@@ -3,6 +3,10 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef PVW_EXP_ORDER
+#define PVW_EXP_ORDER 0
+#endif
+
 namespace pvw {
 
 constexpr int kComputeThreads = 256;
@@ -78,11 +82,19 @@ struct Worker {
         if (PACKED) { a[i].x0 = (u32)x; a[i].x1 = (u32)(x >> 32); a[i].xs = add_alu(a[i].x0, a[i].x1, zero); }
         else a[i] = split_op(x, zero);
       }
+#if PVW_EXP_ORDER == 1
+#pragma unroll
+      for (int i = 0; i < NJ; i++)
+#pragma unroll
+        for (int u = 0; u < TD; u++) {
+          SplitOp b;
+#else
 #pragma unroll
       for (int u = 0; u < TD; u++)
 #pragma unroll
         for (int i = 0; i < NJ; i++) {
           SplitOp b;
+#endif
           b.x0 = b0[u][i]; b.x1 = b1[u][i]; b.xs = add_alu(b0[u][i], b1[u][i], zero);
           acck_mac(acc[t][u], a[i], b);
         }

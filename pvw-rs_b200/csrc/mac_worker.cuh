@@ -3,9 +3,6 @@
 #pragma once
 #include "kernels.cuh"
 
-#ifndef PVW_EXP_ORDER
-#define PVW_EXP_ORDER 0
-#endif
 
 namespace pvw {
 
@@ -82,19 +79,11 @@ struct Worker {
         if (PACKED) { a[i].x0 = (u32)x; a[i].x1 = (u32)(x >> 32); a[i].xs = add_alu(a[i].x0, a[i].x1, zero); }
         else a[i] = split_op(x, zero);
       }
-#if PVW_EXP_ORDER == 1
-#pragma unroll
-      for (int i = 0; i < NJ; i++)
-#pragma unroll
-        for (int u = 0; u < TD; u++) {
-          SplitOp b;
-#else
 #pragma unroll
       for (int u = 0; u < TD; u++)
 #pragma unroll
-        for (int i = 0; i < NJ; i++) {
+        for (int i = 0; i < NJ; i++) {  // (loop order is irrelevant: ptxas re-schedules the independent carry chains)
           SplitOp b;
-#endif
           b.x0 = b0[u][i]; b.x1 = b1[u][i]; b.xs = add_alu(b0[u][i], b1[u][i], zero);
           acck_mac(acc[t][u], a[i], b);
         }
@@ -115,7 +104,7 @@ struct Worker {
 #pragma unroll
       for (int jj = 0; jj < KC; jj += NJ) {
         block<NJ>(ms, vs, jj);
-#ifndef PVW_EXP_NO_BARRIER
+#ifndef PVW_EXP_NO_BARRIER  // measured: without the barrier the kernel spills and runs at half the rate
         asm volatile("" ::: "memory");
 #endif
       }

@@ -40,7 +40,9 @@ typedef enum {
   PVW_ERR_ENCRYPTION = -4,         /* PvwError::EncryptionError     errors.rs:20 */
   PVW_ERR_DECRYPTION = -5,         /* PvwError::DecryptionError     errors.rs:23 */
   PVW_ERR_KEYGEN = -6,             /* PvwError::KeyGenerationError  errors.rs:26 */
-  PVW_ERR_INTERNAL = -7            /* PvwError::InternalError       errors.rs:68 (CUDA failures, missing device) */
+  PVW_ERR_INTERNAL = -7,           /* PvwError::InternalError       errors.rs:68 (CUDA failures, missing device) */
+  PVW_ERR_DESERIALIZATION = -8,    /* PvwError::DeserializationError errors.rs:35 (malformed wire bytes)          */
+  PVW_ERR_INSUFFICIENT_DATA = -9   /* PvwError::InsufficientData    errors.rs:62 (wire buffer too short)          */
 } pvw_status;
 
 enum { PVW_IO_HOST = 0u, PVW_IO_DEVICE = 1u };
@@ -151,6 +153,50 @@ int pvw_ntt_forward_small(pvw_ctx *ctx, uint32_t count, const int64_t *coeffs /*
 /* PvwParameters::encode_scalar (parameters.rs:346-367) for `count` scalars: out = NTT((m as i64) * [1, D, .., D^(l-1)]) */
 int pvw_encode_scalars(pvw_ctx *ctx, uint32_t count, const uint64_t *m /* [count] */, uint64_t *out /* [count][L][ell] */);
 
+/* ---- wire format (the crate's `serde` feature; bincode 1.3 of the hand-written Serialize impls) -------------------
+ * A polynomial travels as a bincode `Vec<u8>` holding fhe-math's `Poly::to_bytes` (protobuf `Rq`: representation = NTT,
+ * degree, residues bit-packed at bit_length(q_j - 1) bits, limb after limb).  For one parameter set every such record
+ * has the same size, so every struct below has a fixed layout, returned by pvw_wire_layout_get():
+ *   PvwCiphertext    (src/crypto/encryption.rs:298-354)  [u64 k][k records] [u64 n][n records] [params]
+ *   public-key row   (src/keys/public_key.rs:471-487, :522-537)  [u64 k][k records]  = PublicKey.key_polynomials = one
+ *                    row of GlobalPublicKey.matrix
+ *   PvwCrs           (src/params/crs.rs:228-249)         [u64 k] k x ([u64 k][k records]) [params]
+ *   PvwParameters    (src/params/parameters.rs:606-623)  n, k, l as u64; Vec<u64> moduli; f32 variance; two decimal strings
+ * The serialisers run on the device where the data lives; deserialisers validate (lengths, Rq header, embedded
+ * parameters == this context's, residues < q_j) before they write anything and fail with PVW_ERR_DESERIALIZATION.
+ * Only the canonical encoding the reference's own serialiser emits is accepted.  The third-party encodings (bincode,
+ * prost, fhe-util transcode) are restated from their published behaviour: parity unpinned, see DESIGN.md.
+ * With PVW_IO_DEVICE the byte buffers are device pointers and the calls are asynchronous, except that every
+ * deserialiser synchronises once to read the validation verdict. */
+typedef struct {
+  uint64_t poly_bytes;        /* Poly::to_bytes length                                   */
+  uint64_t record_bytes;      /* 8 + poly_bytes: one element of a Vec<Vec<u8>>           */
+  uint64_t params_bytes;      /* bincode(PvwParameters)                                  */
+  uint64_t pk_row_bytes;      /* 8 + k * record_bytes                                    */
+  uint64_t ciphertext_bytes;  /* bincode(PvwCiphertext) for all n parties                */
+  uint64_t crs_bytes;         /* bincode(PvwCrs)                                         */
+  uint64_t ct_c1_offset, ct_c2_offset, ct_params_offset; /* sections of a ciphertext blob; the record of party p starts at
+                                                            ct_c2_offset + 8 + p * record_bytes */
+} pvw_wire_layout;
+int pvw_wire_layout_get(const pvw_ctx *ctx, pvw_wire_layout *out);
+int pvw_wire_params(const pvw_ctx *ctx, uint8_t *out, uint64_t cap);
+/* bincode::serialize(&PvwCiphertext) (encryption.rs:298-317) for store slots [slot0, slot0 + D): blob d at out + d*stride.
+ * A row-sharded context writes the envelope, c1 and the c2 records of its own parties only (host output: the other
+ * records are zero-filled; device output: left untouched), so that the ranks' byte ranges can simply be concatenated. */
+int pvw_wire_ct_serialize(pvw_ctx *ctx, uint32_t slot0, uint32_t D, uint8_t *out, uint64_t stride, uint32_t flags);
+/* bincode::deserialize::<PvwCiphertext> (encryption.rs:319-354) into store slots; a sharded context reads c1 and its own
+ * parties' c2 records. */
+int pvw_wire_ct_deserialize(pvw_ctx *ctx, uint32_t slot0, uint32_t D, const uint8_t *in, uint64_t stride, uint32_t flags);
+/* rows [row, row + count) of GlobalPublicKey.matrix as `count` consecutive Vec<Vec<u8>> (public_key.rs:528-533, :471-487) */
+int pvw_wire_pk_serialize_rows(pvw_ctx *ctx, uint32_t row, uint32_t count, uint8_t *out, uint32_t flags);
+int pvw_wire_pk_deserialize_rows(pvw_ctx *ctx, uint32_t row, uint32_t count, const uint8_t *in, uint32_t flags);
+/* bincode::serialize(&PvwCrs) / deserialize (crs.rs:228-295) */
+int pvw_wire_crs_serialize(pvw_ctx *ctx, uint8_t *out, uint64_t cap, uint32_t flags);
+int pvw_wire_crs_deserialize(pvw_ctx *ctx, const uint8_t *in, uint64_t len, uint32_t flags);
+/* `count` polynomials in the host layout <-> `count` records (e.g. GlobalPublicKey.error_polynomials); host pointers */
+int pvw_wire_polys_serialize(pvw_ctx *ctx, uint32_t count, const uint64_t *polys /* [count][L][ell] */, uint8_t *out);
+int pvw_wire_polys_deserialize(pvw_ctx *ctx, uint32_t count, const uint8_t *in, uint64_t *polys /* [count][L][ell] */);
+
 /* blocks until all work queued by this context has finished; returns a sticky CUDA error if one occurred */
 int pvw_ctx_synchronize(pvw_ctx *ctx);
 /* the CUDA stream (cudaStream_t) all work of the context is ordered on, for CUDA-event timing by the caller */
@@ -162,7 +208,7 @@ int pvw_ctx_set_option(pvw_ctx *ctx, const char *name, int64_t value);
  * option "profile" is 1 (2 = enable and reset, 0 = disable and reset): total milliseconds, launches and algorithmic
  * bytes accumulated since the last reset.  Synchronises the stream. */
 enum { PVW_KERNEL_NTT = 0, PVW_KERNEL_MAC = 1, PVW_KERNEL_DECODE_RNS = 2, PVW_KERNEL_CRT_LIFT = 3, PVW_KERNEL_DECODE_TAIL = 4,
-       PVW_KERNEL_PERMUTE = 5, PVW_KERNEL_KINDS = 6 };
+       PVW_KERNEL_PERMUTE = 5, PVW_KERNEL_WIRE = 6, PVW_KERNEL_KINDS = 7 };
 int pvw_ctx_profile(pvw_ctx *ctx, int kind, double *ms_total, uint64_t *launches, double *algorithmic_bytes);
 /* number of kernels launched by this context so far */
 uint64_t pvw_ctx_launch_count(const pvw_ctx *ctx);

@@ -9,7 +9,9 @@ from .api import (GlobalPublicKey, Party, PublicKey, PvwCiphertext, PvwCrs, PvwP
                   SecretKey, decrypt_party_shares, decrypt_party_value, encrypt, encrypt_all_party_shares,
                   encrypt_broadcast, encrypt_party_shares, sample_uniform_coefficients, sample_vec_cbd)
 
-__all__ = ["Engine", "sharding", "PvwError", "GlobalPublicKey", "Party", "PublicKey", "PvwCiphertext", "PvwCrs", "PvwParameters",
+from . import serde  # noqa: E402  (needs api)
+
+__all__ = ["Engine", "sharding", "serde", "PvwError", "GlobalPublicKey", "Party", "PublicKey", "PvwCiphertext", "PvwCrs", "PvwParameters",
            "PvwParametersBuilder", "SecretKey", "decrypt_party_shares", "decrypt_party_value", "encrypt",
            "encrypt_all_party_shares", "encrypt_broadcast", "encrypt_party_shares", "sample_uniform_coefficients",
            "sample_vec_cbd"]

@@ -15,7 +15,7 @@ PVW_OK = 0
 PVW_IO_HOST, PVW_IO_DEVICE = 0, 1
 STATUS_NAMES = {
     0: "Ok", -1: "InvalidParameters", -2: "DimensionMismatch", -3: "IndexOutOfBounds", -4: "EncryptionError",
-    -5: "DecryptionError", -6: "KeyGenerationError", -7: "InternalError",
+    -5: "DecryptionError", -6: "KeyGenerationError", -7: "InternalError", -8: "DeserializationError", -9: "InsufficientData",
 }
 
 
@@ -24,6 +24,11 @@ class PvwParamsDesc(C.Structure):
                 ("moduli", C.POINTER(C.c_uint64)), ("psi", C.POINTER(C.c_uint64)),
                 ("secret_variance", C.c_float), ("error_bound_1", C.c_uint64), ("error_bound_2", C.c_uint64),
                 ("row0", C.c_uint32), ("nrows", C.c_uint32), ("device", C.c_int32)]
+
+
+class PvwWireLayout(C.Structure):
+    _fields_ = [(name, C.c_uint64) for name in ("poly_bytes", "record_bytes", "params_bytes", "pk_row_bytes", "ciphertext_bytes",
+                                                "crs_bytes", "ct_c1_offset", "ct_c2_offset", "ct_params_offset")]
 
 
 _vp, _u32, _u64, _i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64
@@ -56,6 +61,16 @@ SIGNATURES = {
     "pvw_decode_batch": (C.c_int, [_vp, _u32, _vp, _vp]),
     "pvw_ntt_forward_small": (C.c_int, [_vp, _u32, _vp, _vp]),
     "pvw_encode_scalars": (C.c_int, [_vp, _u32, _vp, _vp]),
+    "pvw_wire_layout_get": (C.c_int, [_vp, C.POINTER(PvwWireLayout)]),
+    "pvw_wire_params": (C.c_int, [_vp, _vp, _u64]),
+    "pvw_wire_ct_serialize": (C.c_int, [_vp, _u32, _u32, _vp, _u64, _u32]),
+    "pvw_wire_ct_deserialize": (C.c_int, [_vp, _u32, _u32, _vp, _u64, _u32]),
+    "pvw_wire_pk_serialize_rows": (C.c_int, [_vp, _u32, _u32, _vp, _u32]),
+    "pvw_wire_pk_deserialize_rows": (C.c_int, [_vp, _u32, _u32, _vp, _u32]),
+    "pvw_wire_crs_serialize": (C.c_int, [_vp, _vp, _u64, _u32]),
+    "pvw_wire_crs_deserialize": (C.c_int, [_vp, _vp, _u64, _u32]),
+    "pvw_wire_polys_serialize": (C.c_int, [_vp, _u32, _vp, _vp]),
+    "pvw_wire_polys_deserialize": (C.c_int, [_vp, _u32, _vp, _vp]),
     "pvw_ctx_synchronize": (C.c_int, [_vp]),
     "pvw_ctx_stream": (_vp, [_vp]),
     "pvw_ctx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
@@ -64,7 +79,7 @@ SIGNATURES = {
     "pvw_version": (C.c_char_p, []),
 }
 
-KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute"]
+KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute", "wire"]
 
 _lib = None
 

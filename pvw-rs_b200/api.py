@@ -340,6 +340,7 @@ class GlobalPublicKey:
         self.engine.crs_upload(crs.matrix)
         self._slots = _SlotPool(self.engine, ct_capacity if ct_capacity is not None else max(self.params.n, 4))
         self._lock = threading.RLock()
+        self.error_polynomials: List[np.ndarray] = []      # per party: [k][L][l] NTT-form errors, or an empty array (public_key.rs:53)
 
     new = classmethod(lambda cls, crs: cls(crs))
 
@@ -377,6 +378,32 @@ class GlobalPublicKey:
         e = sample_uniform_coefficients(P.error_bound_1, P.k * P.l, rng).reshape(P.k, P.l) if errors is None else np.asarray(errors, np.int64)
         with self._lock:
             self.engine.keygen_batch(party.index(), party.secret_key().secret_coeffs[None], e[None])
+
+    def generate_and_add(self, index: int, secret_key: SecretKey, rng=None, errors=None):
+        """public_key.rs:268-277"""
+        self.generate_and_add_party(Party(index, self.params, secret_key=secret_key), rng, errors)
+
+    def generate_and_add_with_errors(self, index: int, secret_key: SecretKey, rng=None, errors=None):
+        """public_key.rs:304-321: like generate_and_add, and the NTT-form error polynomials are kept"""
+        P = self.params
+        if index >= P.n:
+            raise PvwError("IndexOutOfBounds", f"Party index {index} exceeds maximum {P.n - 1}")
+        e = sample_uniform_coefficients(P.error_bound_1, P.k * P.l, rng).reshape(P.k, P.l) if errors is None else np.asarray(errors, np.int64)
+        with self._lock:
+            self.engine.keygen_batch(index, secret_key.secret_coeffs[None], e[None])
+            while len(self.error_polynomials) <= index:
+                self.error_polynomials.append(np.zeros((0, P.L, P.l), dtype=np.uint64))
+            self.error_polynomials[index] = self.engine.ntt_forward_small(e)
+
+    def generate_and_add_party_with_errors(self, party: Party, rng=None, errors=None):
+        """public_key.rs:322-329"""
+        self.generate_and_add_with_errors(party.index(), party.secret_key(), rng, errors)
+
+    def get_party_errors(self, party_index: int):
+        return self.error_polynomials[party_index] if 0 <= party_index < len(self.error_polynomials) else None
+
+    def get_all_errors(self):
+        return self.error_polynomials
 
     def generate_all_party_keys(self, parties: Sequence[Party], rng=None, errors=None):
         """public_key.rs:376-401: parties' indices must be 0..len-1 in order; one batched device keygen"""

@@ -77,6 +77,13 @@ struct pvw_ctx {
   DevBuf c1s, c2s;
   // grow-only scratch
   DevBuf stage, rhat, in_small, in_small2, in_m, shat, z, y, X, outd, idxd, idxp;
+  // wire format (wire.cu): record tables, envelope templates (device copies at wire_env) and a staging buffer
+  WireTables W{};
+  DevBuf wire_tab, wire_buf;
+  std::vector<uint8_t> params_blob;                  // bincode(PvwParameters), parameters.rs:606-623
+  const uint8_t *env_k = nullptr, *env_n = nullptr, *env_params = nullptr;
+  int* wire_err = nullptr;
+  uint64_t rq_bytes = 0;
   std::string err;
   uint64_t launches = 0;
   // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg): events bracket each launch on `stream`
@@ -144,6 +151,83 @@ void upload_tables(pvw_ctx* c) {
   T.sh_c = base + o_shc; T.sh_c_sh = base + o_shcs; T.sh_qhat = base + o_shq; T.sh_Q = base + o_shQ; T.sh_halfQ = base + o_shh;
   T.sh_v = base + o_shv; T.sh_v_sh = base + o_shvs; T.sh_r = base + o_shr; T.sh_r_sh = base + o_shrs;
   T.shortL = hp.shortL; T.shortSW = hp.shortSW; T.lift_fast = hp.shortL > 0 ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wire format constants (recalled third-party encodings, see oracle/pvw_wire.py)
+// ------------------------------------------------------------------------------------------------------------
+void put_varint(std::vector<uint8_t>& v, uint64_t x) {
+  while (x >= 0x80) { v.push_back((uint8_t)(x | 0x80)); x >>= 7; }
+  v.push_back((uint8_t)x);
+}
+void put_u64le(std::vector<uint8_t>& v, uint64_t x) { for (int i = 0; i < 8; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+
+void upload_wire_tables(pvw_ctx* c) {
+  const HostParams& hp = c->hp;
+  const uint32_t L = hp.L, ell = hp.ell;
+  std::vector<uint32_t> nbits(L), magic(L), limb_off(L + 1, 0);
+  for (uint32_t j = 0; j < L; j++) {
+    uint32_t nb = 0;
+    for (uint64_t x = hp.moduli[j] - 1; x; x >>= 1) nb++;                 // fhe-math Modulus::serialize_vec: 64 - lzcnt(p - 1)
+    nbits[j] = nb;
+    magic[j] = (1u << 20) / nb + 1;
+    limb_off[j + 1] = limb_off[j] + ell * nb / 8;                         // ell is a multiple of 8: no padding bits
+  }
+  const uint32_t packed = limb_off[L];
+  std::vector<uint8_t> limb_of(packed);
+  for (uint32_t j = 0; j < L; j++) std::fill(limb_of.begin() + limb_off[j], limb_of.begin() + limb_off[j + 1], (uint8_t)j);
+  // Rq { representation = NTT (2); degree = ell; coefficients = packed; allow_variable_time = false (omitted) }
+  std::vector<uint8_t> rq = {0x08, 0x02, 0x10};
+  put_varint(rq, ell);
+  rq.push_back(0x1a);
+  put_varint(rq, packed);
+  c->rq_bytes = rq.size() + packed;
+  std::vector<uint8_t> pre;
+  put_u64le(pre, c->rq_bytes);                                            // bincode Vec<u8> length
+  pre.insert(pre.end(), rq.begin(), rq.end());
+  // bincode(PvwParameters): n, k, l (usize as u64), moduli Vec<u64>, secret_variance f32, the bounds as decimal strings
+  std::vector<uint8_t>& pb = c->params_blob;
+  pb.clear();
+  put_u64le(pb, hp.n); put_u64le(pb, hp.k); put_u64le(pb, hp.ell);
+  put_u64le(pb, L);
+  for (uint32_t j = 0; j < L; j++) put_u64le(pb, hp.moduli[j]);
+  uint32_t fbits; memcpy(&fbits, &hp.secret_variance, 4);
+  for (int i = 0; i < 4; i++) pb.push_back((uint8_t)(fbits >> (8 * i)));
+  for (uint64_t b : {hp.b1, hp.b2}) {
+    const std::string sdec = std::to_string(b);
+    put_u64le(pb, sdec.size());
+    pb.insert(pb.end(), sdec.begin(), sdec.end());
+  }
+  // one device blob: [u32 tables][u64 moduli][bytes]
+  std::vector<uint8_t> blob;
+  auto put = [&](const void* src, size_t bytes, size_t align) {
+    while (blob.size() % align) blob.push_back(0);
+    const size_t off = blob.size();
+    blob.insert(blob.end(), (const uint8_t*)src, (const uint8_t*)src + bytes);
+    return off;
+  };
+  const size_t o_mod = put(hp.moduli.data(), (size_t)L * 8, 8), o_nb = put(nbits.data(), (size_t)L * 4, 4), o_mg = put(magic.data(), (size_t)L * 4, 4),
+               o_lo = put(limb_off.data(), (size_t)(L + 1) * 4, 4), o_lf = put(limb_of.data(), packed, 4), o_pre = put(pre.data(), pre.size(), 4);
+  std::vector<uint8_t> ek, en;
+  put_u64le(ek, hp.k); put_u64le(en, hp.n);
+  const size_t o_ek = put(ek.data(), 8, 8), o_en = put(en.data(), 8, 8), o_pb = put(pb.data(), pb.size(), 8);
+  int zero = 0;
+  const size_t o_err = put(&zero, 4, 4);
+  c->wire_tab.ensure(blob.size());
+  CUDA_CHECK(cudaMemcpy(c->wire_tab.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  uint8_t* base = c->wire_tab.as<uint8_t>();
+  WireTables& W = c->W;
+  W.moduli = reinterpret_cast<const u64*>(base + o_mod);
+  W.nbits = reinterpret_cast<const uint32_t*>(base + o_nb);
+  W.magic = reinterpret_cast<const uint32_t*>(base + o_mg);
+  W.limb_off = reinterpret_cast<const uint32_t*>(base + o_lo);
+  W.limb_of = base + o_lf;
+  W.pre = base + o_pre;
+  W.L = L; W.ell = ell; W.pre_len = (uint32_t)pre.size(); W.packed_bytes = packed; W.rec_bytes = (uint32_t)pre.size() + packed;
+  W.sg = 16;
+  for (uint32_t j = 0; j < L; j++) if (limb_off[j + 1] - limb_off[j] > 64) W.sg = 32;
+  c->env_k = base + o_ek; c->env_n = base + o_en; c->env_params = base + o_pb;
+  c->wire_err = reinterpret_cast<int*>(base + o_err);
 }
 
 void check_launch(pvw_ctx* c, size_t n = 1) {
@@ -303,6 +387,7 @@ int pvw_ctx_create(pvw_ctx** out, const pvw_params_desc* d) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     upload_tables(c);
+    upload_wire_tables(c);
     *out = c;
     return PVW_OK;
   } catch (const PvwException& e) {
@@ -327,7 +412,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->wire_tab, &c->wire_buf})
     b->release();
   delete c;
 }
@@ -744,6 +829,268 @@ int pvw_encode_scalars(pvw_ctx* c, uint32_t count, const uint64_t* m, uint64_t* 
     CUDA_CHECK(cudaMemcpyAsync(c->in_m.p, m, (size_t)count * 8, cudaMemcpyHostToDevice, c->stream));
     launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, c->in_small.as<long long>(), c->in_m.as<u64>(), count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream); });
     CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wire format
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct WireSizes { uint64_t rec, row, ct, crs, params; };
+WireSizes wire_sizes(const pvw_ctx* c) {
+  WireSizes z;
+  z.rec = c->W.rec_bytes;
+  z.params = c->params_blob.size();
+  z.row = 8 + (uint64_t)c->hp.k * z.rec;                                         // Vec<Vec<u8>> of k polynomials
+  z.ct = z.row + 8 + (uint64_t)c->hp.n * z.rec + z.params;                       // encryption.rs:298-317
+  z.crs = 8 + (uint64_t)c->hp.k * z.row + z.params;                              // crs.rs:228-249
+  return z;
+}
+void wire_pack(pvw_ctx* c, const u64* src, size_t ls, size_t bs, uint64_t count, uint32_t batch, bool packed, uint8_t* out, size_t obs) {
+  const double bytes = (double)batch * count * (c->poly() * 8.0 + c->W.rec_bytes);
+  launch(c, PVW_KERNEL_WIRE, bytes, [&] { launch_wire_pack(c->W, src, ls, bs, count, batch, packed ? 1 : 0, out, obs, c->stream); });
+}
+void wire_unpack(pvw_ctx* c, const uint8_t* in, size_t ibs, uint64_t count, uint32_t batch, u64* dst, size_t ls, size_t bs, bool packed, bool write) {
+  const double bytes = (double)batch * count * ((write ? c->poly() * 8.0 : 0.0) + c->W.rec_bytes);
+  launch(c, PVW_KERNEL_WIRE, bytes, [&] { launch_wire_unpack(c->W, in, ibs, count, batch, dst, ls, bs, packed ? 1 : 0, write ? 1 : 0, c->wire_err, c->stream); });
+}
+void wire_fill(pvw_ctx* c, uint8_t* out, size_t obs, uint32_t batch, const uint8_t* tmpl, uint32_t len) {
+  launch(c, PVW_KERNEL_WIRE, 0.0, [&] { launch_wire_fill(out, obs, batch, tmpl, len, c->stream); });
+}
+void wire_expect(pvw_ctx* c, const uint8_t* in, size_t ibs, uint32_t batch, const uint8_t* tmpl, uint32_t len) {
+  launch(c, PVW_KERNEL_WIRE, 0.0, [&] { launch_wire_expect(in, ibs, batch, tmpl, len, c->wire_err, c->stream); });
+}
+void wire_err_reset(pvw_ctx* c) { CUDA_CHECK(cudaMemsetAsync(c->wire_err, 0, 4, c->stream)); }
+// synchronises; throws DeserializationError when any validation kernel since the last reset flagged something
+void wire_err_check(pvw_ctx* c, const char* what) {
+  int e = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&e, c->wire_err, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (!e) return;
+  std::string why;
+  if (e & WIRE_ERR_ENVELOPE) why += " length prefixes or embedded parameters differ from this context's;";
+  if (e & WIRE_ERR_HEADER) why += " a polynomial record has the wrong length, representation or degree;";
+  if (e & WIRE_ERR_RESIDUE) why += " a coefficient is not reduced modulo its prime;";
+  throw PvwException(PVW_ERR_DESERIALIZATION, std::string(what) + ":" + why);
+}
+// bytes -> device: returns a device pointer holding `bytes` bytes of `src` (host or device per flags)
+const uint8_t* wire_stage_in(pvw_ctx* c, const uint8_t* src, size_t bytes, uint32_t flags) {
+  if (flags & PVW_IO_DEVICE) return src;
+  c->wire_buf.ensure(bytes);
+  CUDA_CHECK(cudaMemcpyAsync(c->wire_buf.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return c->wire_buf.as<uint8_t>();
+}
+
+}  // namespace
+
+int pvw_wire_layout_get(const pvw_ctx* c, pvw_wire_layout* out) {
+  if (!c || !out) return PVW_ERR_INVALID_PARAMETERS;
+  const WireSizes z = wire_sizes(c);
+  out->poly_bytes = c->rq_bytes; out->record_bytes = z.rec; out->params_bytes = z.params; out->pk_row_bytes = z.row;
+  out->ciphertext_bytes = z.ct; out->crs_bytes = z.crs;
+  out->ct_c1_offset = 0; out->ct_c2_offset = z.row; out->ct_params_offset = z.ct - z.params;
+  return PVW_OK;
+}
+int pvw_wire_params(const pvw_ctx* c, uint8_t* out, uint64_t cap) {
+  if (!c || !out || cap < c->params_blob.size()) return PVW_ERR_INVALID_PARAMETERS;
+  memcpy(out, c->params_blob.data(), c->params_blob.size());
+  return PVW_OK;
+}
+
+int pvw_wire_ct_serialize(pvw_ctx* c, uint32_t slot0, uint32_t D, uint8_t* out, uint64_t stride, uint32_t flags) {
+  return guarded(c, [&] {
+    if (D == 0) return;
+    const WireSizes z = wire_sizes(c);
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows, n = c->hp.n;
+    require(out != nullptr, PVW_ERR_INVALID_PARAMETERS, "out is null");
+    require(stride >= z.ct, PVW_ERR_INVALID_PARAMETERS, fmt("stride %llu is smaller than one serialised ciphertext (%llu bytes)", (unsigned long long)stride, (unsigned long long)z.ct));
+    require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
+    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const bool host = !(flags & PVW_IO_DEVICE);
+    const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.ct) : D;
+    for (uint32_t d0 = 0; d0 < D; d0 += per) {
+      const uint32_t Dc = std::min(per, D - d0);
+      uint8_t* dev = out + (size_t)d0 * stride;
+      size_t ds = stride;
+      if (host) {
+        c->wire_buf.ensure((size_t)Dc * z.ct);
+        dev = c->wire_buf.as<uint8_t>(); ds = z.ct;
+        if (nrows < n) CUDA_CHECK(cudaMemsetAsync(dev, 0, (size_t)Dc * z.ct, c->stream));  // records of rows held by other shards
+      }
+      wire_fill(c, dev, ds, Dc, c->env_k, 8);
+      wire_pack(c, c->c1s.as<u64>() + (size_t)(slot0 + d0) * w1, (size_t)k * ell, w1, k, Dc, true, dev + 8, ds);
+      wire_fill(c, dev + z.row, ds, Dc, c->env_n, 8);
+      wire_pack(c, c->c2s.as<u64>() + (size_t)(slot0 + d0) * w2, (size_t)nrows * ell, w2, nrows, Dc, false, dev + z.row + 8 + (size_t)c->row0 * z.rec, ds);
+      wire_fill(c, dev + z.ct - z.params, ds, Dc, c->env_params, (uint32_t)z.params);
+      if (host) {
+        CUDA_CHECK(cudaMemcpy2DAsync(out + (size_t)d0 * stride, stride, dev, z.ct, z.ct, Dc, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      }
+    }
+  });
+}
+
+int pvw_wire_ct_deserialize(pvw_ctx* c, uint32_t slot0, uint32_t D, const uint8_t* in, uint64_t stride, uint32_t flags) {
+  return guarded(c, [&] {
+    if (D == 0) return;
+    const WireSizes z = wire_sizes(c);
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+    require(in != nullptr, PVW_ERR_INVALID_PARAMETERS, "in is null");
+    require(stride >= z.ct, PVW_ERR_INSUFFICIENT_DATA, fmt("expected %llu bytes per ciphertext, got %llu", (unsigned long long)z.ct, (unsigned long long)stride));
+    require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
+    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const bool host = !(flags & PVW_IO_DEVICE);
+    const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.ct) : D;
+    for (uint32_t d0 = 0; d0 < D; d0 += per) {
+      const uint32_t Dc = std::min(per, D - d0);
+      const uint8_t* dev = in + (size_t)d0 * stride;
+      size_t ds = stride;
+      if (host) {
+        c->wire_buf.ensure((size_t)Dc * z.ct);
+        CUDA_CHECK(cudaMemcpy2DAsync(c->wire_buf.p, z.ct, in + (size_t)d0 * stride, stride, z.ct, Dc, cudaMemcpyHostToDevice, c->stream));
+        dev = c->wire_buf.as<uint8_t>(); ds = z.ct;
+      }
+      u64* c1 = c->c1s.as<u64>() + (size_t)(slot0 + d0) * w1;
+      u64* c2 = c->c2s.as<u64>() + (size_t)(slot0 + d0) * w2;
+      const uint8_t* r2 = dev + z.row + 8 + (size_t)c->row0 * z.rec;
+      wire_err_reset(c);
+      wire_expect(c, dev, ds, Dc, c->env_k, 8);
+      wire_expect(c, dev + z.row, ds, Dc, c->env_n, 8);
+      wire_expect(c, dev + z.ct - z.params, ds, Dc, c->env_params, (uint32_t)z.params);
+      // validate everything first: a rejected blob leaves the store untouched (the reference returns Err, no side effects)
+      wire_unpack(c, dev + 8, ds, k, Dc, c1, (size_t)k * ell, w1, true, false);
+      wire_unpack(c, r2, ds, nrows, Dc, c2, (size_t)nrows * ell, w2, false, false);
+      wire_err_check(c, "PvwCiphertext");
+      wire_unpack(c, dev + 8, ds, k, Dc, c1, (size_t)k * ell, w1, true, true);
+      wire_unpack(c, r2, ds, nrows, Dc, c2, (size_t)nrows * ell, w2, false, true);
+      if (host) CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
+    }
+  });
+}
+
+int pvw_wire_pk_serialize_rows(pvw_ctx* c, uint32_t row, uint32_t count, uint8_t* out, uint32_t flags) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(out != nullptr, PVW_ERR_INVALID_PARAMETERS, "out is null");
+    check_rows(c, row, count);
+    ensure_B(c);
+    const WireSizes z = wire_sizes(c);
+    const uint32_t k = c->hp.k, ell = c->hp.ell;
+    const bool host = !(flags & PVW_IO_DEVICE);
+    const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.row) : count;
+    for (uint32_t r0 = 0; r0 < count; r0 += per) {
+      const uint32_t rc = std::min(per, count - r0);
+      uint8_t* dev = out + (size_t)r0 * z.row;
+      if (host) { c->wire_buf.ensure((size_t)rc * z.row); dev = c->wire_buf.as<uint8_t>(); }
+      wire_fill(c, dev, z.row, rc, c->env_k, 8);
+      wire_pack(c, c->B.as<u64>() + (size_t)(row - c->row0 + r0) * k * ell, (size_t)c->nrows * k * ell, (size_t)k * ell, k, rc, true, dev + 8, z.row);
+      if (host) {
+        CUDA_CHECK(cudaMemcpyAsync(out + (size_t)r0 * z.row, dev, (size_t)rc * z.row, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      }
+    }
+  });
+}
+
+int pvw_wire_pk_deserialize_rows(pvw_ctx* c, uint32_t row, uint32_t count, const uint8_t* in, uint32_t flags) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(in != nullptr, PVW_ERR_INVALID_PARAMETERS, "in is null");
+    check_rows(c, row, count);
+    ensure_B(c);
+    const WireSizes z = wire_sizes(c);
+    const uint32_t k = c->hp.k, ell = c->hp.ell;
+    const bool host = !(flags & PVW_IO_DEVICE);
+    const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.row) : count;
+    for (uint32_t r0 = 0; r0 < count; r0 += per) {
+      const uint32_t rc = std::min(per, count - r0);
+      const uint8_t* dev = wire_stage_in(c, in + (size_t)r0 * z.row, (size_t)rc * z.row, flags);
+      u64* dst = c->B.as<u64>() + (size_t)(row - c->row0 + r0) * k * ell;
+      wire_err_reset(c);
+      wire_expect(c, dev, z.row, rc, c->env_k, 8);
+      wire_unpack(c, dev + 8, z.row, k, rc, dst, (size_t)c->nrows * k * ell, (size_t)k * ell, true, false);
+      wire_err_check(c, "public key rows");
+      wire_unpack(c, dev + 8, z.row, k, rc, dst, (size_t)c->nrows * k * ell, (size_t)k * ell, true, true);
+      if (host) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    c->num_keys = std::max(c->num_keys, row + count);
+  });
+}
+
+int pvw_wire_crs_serialize(pvw_ctx* c, uint8_t* out, uint64_t cap, uint32_t flags) {
+  return guarded(c, [&] {
+    const WireSizes z = wire_sizes(c);
+    require(out != nullptr && cap >= z.crs, PVW_ERR_INVALID_PARAMETERS, fmt("the serialised CRS needs %llu bytes", (unsigned long long)z.crs));
+    require(c->A_set, PVW_ERR_INVALID_PARAMETERS, "CRS has not been uploaded");
+    const uint32_t k = c->hp.k, ell = c->hp.ell;
+    const bool host = !(flags & PVW_IO_DEVICE);
+    uint8_t* dev = out;
+    if (host) { c->wire_buf.ensure(z.crs); dev = c->wire_buf.as<uint8_t>(); }
+    wire_fill(c, dev, 0, 1, c->env_k, 8);                                          // outer Vec: k rows
+    wire_fill(c, dev + 8, z.row, k, c->env_k, 8);                                  // each row: k records
+    wire_pack(c, c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, k, k, true, dev + 16, z.row);
+    wire_fill(c, dev + z.crs - z.params, 0, 1, c->env_params, (uint32_t)z.params);
+    if (host) {
+      CUDA_CHECK(cudaMemcpyAsync(out, dev, z.crs, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+  });
+}
+
+int pvw_wire_crs_deserialize(pvw_ctx* c, const uint8_t* in, uint64_t len, uint32_t flags) {
+  return guarded(c, [&] {
+    const WireSizes z = wire_sizes(c);
+    require(in != nullptr, PVW_ERR_INVALID_PARAMETERS, "in is null");
+    require(len >= z.crs, PVW_ERR_INSUFFICIENT_DATA, fmt("expected %llu bytes, got %llu", (unsigned long long)z.crs, (unsigned long long)len));
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+    const uint8_t* dev = wire_stage_in(c, in, z.crs, flags);
+    c->A.ensure((size_t)L * k * k * ell * 8);
+    wire_err_reset(c);
+    wire_expect(c, dev, 0, 1, c->env_k, 8);
+    wire_expect(c, dev + 8, z.row, k, c->env_k, 8);
+    wire_expect(c, dev + z.crs - z.params, 0, 1, c->env_params, (uint32_t)z.params);
+    wire_unpack(c, dev + 16, z.row, k, k, c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, true, false);
+    wire_err_check(c, "PvwCrs");
+    wire_unpack(c, dev + 16, z.row, k, k, c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, true, true);
+    c->A_set = true;
+    c->At_valid = false;
+    if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_wire_polys_serialize(pvw_ctx* c, uint32_t count, const uint64_t* polys, uint8_t* out) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(polys && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    const size_t poly = c->poly(), rec = c->W.rec_bytes;
+    const uint32_t ell = c->hp.ell;
+    c->stage.ensure((size_t)count * poly * 8);
+    c->z.ensure((size_t)count * poly * 8);
+    c->wire_buf.ensure((size_t)count * rec);
+    CUDA_CHECK(cudaMemcpyAsync(c->stage.p, polys, (size_t)count * poly * 8, cudaMemcpyHostToDevice, c->stream));
+    to_limb_major(c, c->stage.as<u64>(), count, c->z.as<u64>(), (size_t)count * ell, false);
+    wire_pack(c, c->z.as<u64>(), (size_t)count * ell, 0, count, 1, false, c->wire_buf.as<uint8_t>(), 0);
+    CUDA_CHECK(cudaMemcpyAsync(out, c->wire_buf.p, (size_t)count * rec, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int pvw_wire_polys_deserialize(pvw_ctx* c, uint32_t count, const uint8_t* in, uint64_t* polys) {
+  return guarded(c, [&] {
+    if (count == 0) return;
+    require(polys && in, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    const size_t poly = c->poly(), rec = c->W.rec_bytes;
+    const uint32_t ell = c->hp.ell;
+    c->stage.ensure((size_t)count * poly * 8);
+    c->z.ensure((size_t)count * poly * 8);
+    const uint8_t* dev = wire_stage_in(c, in, (size_t)count * rec, PVW_IO_HOST);
+    wire_err_reset(c);
+    wire_unpack(c, dev, 0, count, 1, c->z.as<u64>(), (size_t)count * ell, 0, false, true);
+    wire_err_check(c, "polynomial records");
+    from_limb_major(c, c->z.as<u64>(), (size_t)count * ell, count, c->stage.as<u64>(), false);
+    CUDA_CHECK(cudaMemcpyAsync(polys, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
 }

@@ -86,4 +86,29 @@ void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t 
 size_t decode_scratch_words_y(const DevTables& T, uint64_t S);
 size_t decode_scratch_words_X(const DevTables& T, uint64_t S);
 
+// ---- wire.cu ------------------------------------------------------------------------------------------------
+// Wire format of one polynomial: a bincode `Vec<u8>` element = u64 length + fhe-math `Poly::to_bytes`
+// (protobuf Rq: representation, degree, coefficients = per limb the ell residues packed at bit_length(q_j - 1) bits).
+// Every record of one parameter set has the same size and the same first `pre_len` bytes.
+struct WireTables {
+  const uint8_t* pre;         // [pre_len]  u64 LE message length + the Rq fields before the packed residues
+  const uint8_t* limb_of;     // [packed_bytes] limb of each packed byte
+  const uint32_t* limb_off;   // [L + 1]    byte offset of each limb's residues inside the packed region
+  const uint32_t* nbits;      // [L]        bits per residue
+  const uint32_t* magic;      // [L]        floor(2^20 / nbits) + 1:  x / nbits == (x * magic) >> 20 for x < 2^11
+  const u64* moduli;          // [L]
+  uint32_t L, ell, pre_len, packed_bytes, rec_bytes;
+  uint32_t sg;                // lanes per (record, limb) pair in the pack kernel: 16 when every limb has <= 16 words, else 32
+};
+enum { WIRE_ERR_HEADER = 1, WIRE_ERR_RESIDUE = 2, WIRE_ERR_ENVELOPE = 4 };
+// polynomials src[b*bs + limb*ls + p*ell + c]  (p < count, b < batch)  ->  records out[b*obs + p*rec_bytes ..]
+void launch_wire_pack(const WireTables& W, const u64* src, size_t ls, size_t bs, uint64_t count, uint32_t batch, int src_packed,
+                      uint8_t* out, size_t obs, cudaStream_t st);
+// the inverse; write == 0 only validates.  *err |= WIRE_ERR_* on a malformed record / a residue >= q_j
+void launch_wire_unpack(const WireTables& W, const uint8_t* in, size_t ibs, uint64_t count, uint32_t batch, u64* dst, size_t ls, size_t bs,
+                        int dst_packed, int write, int* err, cudaStream_t st);
+// out[b*obs + i] = tmpl[i]  /  *err |= WIRE_ERR_ENVELOPE when in[b*ibs + i] != tmpl[i]      (i < len, b < batch)
+void launch_wire_fill(uint8_t* out, size_t obs, uint32_t batch, const uint8_t* tmpl, uint32_t len, cudaStream_t st);
+void launch_wire_expect(const uint8_t* in, size_t ibs, uint32_t batch, const uint8_t* tmpl, uint32_t len, int* err, cudaStream_t st);
+
 }  // namespace pvw

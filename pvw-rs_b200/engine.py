@@ -287,6 +287,107 @@ class Engine:
         h.__cuda_array_interface__ = {"shape": (count, stride), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
         return torch.as_tensor(h, device=f"cuda:{self.device}")
 
+    # -- wire format: bincode of the crate's serde impls, produced / parsed on the device ---------
+    @property
+    def wire_layout(self) -> "_ffi.PvwWireLayout":
+        if getattr(self, "_wire", None) is None:
+            w = _ffi.PvwWireLayout()
+            self._check(self.lib.pvw_wire_layout_get(self.h, C.byref(w)))
+            self._wire = w
+        return self._wire
+
+    def wire_params(self) -> bytes:
+        """bincode::serialize(&PvwParameters)  (parameters.rs:606-623)"""
+        buf = np.empty(self.wire_layout.params_bytes, dtype=np.uint8)
+        self._check(self.lib.pvw_wire_params(self.h, buf.ctypes.data, buf.size))
+        return buf.tobytes()
+
+    def _bytes_arg(self, x, nbytes: int, name: str):
+        """(pointer, keep-alive, on_device) of a byte buffer: numpy / bytes on the host or a torch.uint8 CUDA tensor"""
+        if _is_device_tensor(x):
+            import torch
+            if x.dtype != torch.uint8 or not x.is_contiguous():
+                raise PvwError("InvalidParameters", f"{name}: need a contiguous CUDA tensor of dtype uint8")
+            if x.numel() < nbytes:
+                raise PvwError("InsufficientData", f"{name}: expected {nbytes} bytes, got {x.numel()}")
+            return x.data_ptr(), x, True
+        a = np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray, memoryview)) else np.ascontiguousarray(x, dtype=np.uint8)
+        if a.size < nbytes:
+            raise PvwError("InsufficientData", f"{name}: expected {nbytes} bytes, got {a.size}")
+        return a.ctypes.data, a, False
+
+    def wire_ct_serialize(self, slot0: int, D: int, out=None, stride: Optional[int] = None):
+        """D stored ciphertexts -> D bincode(PvwCiphertext) blobs (encryption.rs:298-317), `stride` bytes apart.
+        out: None (a new host uint8 array [D][stride] is returned) or a torch.uint8 CUDA tensor (stays in HBM)."""
+        stride = int(stride or self.wire_layout.ciphertext_bytes)
+        if out is None:
+            out = np.empty((D, stride), dtype=np.uint8)
+        ptr, keep, dev = self._bytes_arg(out, D * stride, "out")
+        if dev:
+            self._before_device_call()
+        self._check(self.lib.pvw_wire_ct_serialize(self.h, slot0, D, ptr, stride, _ffi.PVW_IO_DEVICE if dev else 0))
+        if dev:
+            self._after_device_call()
+        return out
+
+    def wire_ct_deserialize(self, slot0: int, D: int, blobs, stride: Optional[int] = None):
+        stride = int(stride or self.wire_layout.ciphertext_bytes)
+        ptr, keep, dev = self._bytes_arg(blobs, D * stride if D else 0, "blobs")
+        if dev:
+            self._before_device_call()
+        self._check(self.lib.pvw_wire_ct_deserialize(self.h, slot0, D, ptr, stride, _ffi.PVW_IO_DEVICE if dev else 0))
+        if dev:
+            self._after_device_call()
+
+    def wire_pk_serialize_rows(self, row: int, count: int, out=None):
+        """rows of GlobalPublicKey.matrix as `count` consecutive Vec<Vec<u8>> (public_key.rs:528-533)"""
+        nb = count * self.wire_layout.pk_row_bytes
+        if out is None:
+            out = np.empty(nb, dtype=np.uint8)
+        ptr, keep, dev = self._bytes_arg(out, nb, "out")
+        if dev:
+            self._before_device_call()
+        self._check(self.lib.pvw_wire_pk_serialize_rows(self.h, row, count, ptr, _ffi.PVW_IO_DEVICE if dev else 0))
+        if dev:
+            self._after_device_call()
+        return out
+
+    def wire_pk_deserialize_rows(self, row: int, count: int, data):
+        ptr, keep, dev = self._bytes_arg(data, count * self.wire_layout.pk_row_bytes, "data")
+        if dev:
+            self._before_device_call()
+        self._check(self.lib.pvw_wire_pk_deserialize_rows(self.h, row, count, ptr, _ffi.PVW_IO_DEVICE if dev else 0))
+        if dev:
+            self._after_device_call()
+
+    def wire_crs_serialize(self) -> bytes:
+        """bincode::serialize(&PvwCrs)  (crs.rs:228-249)"""
+        buf = np.empty(self.wire_layout.crs_bytes, dtype=np.uint8)
+        self._check(self.lib.pvw_wire_crs_serialize(self.h, buf.ctypes.data, buf.size, 0))
+        return buf.tobytes()
+
+    def wire_crs_deserialize(self, data):
+        a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+        self._check(self.lib.pvw_wire_crs_deserialize(self.h, a.ctypes.data, a.size, 0))
+
+    def wire_polys_serialize(self, polys) -> bytes:
+        """[count][L][l] residues -> count records (u64 length + Poly::to_bytes each)"""
+        a = _Arg(polys, np.uint64, None, "polys")
+        if a.device or a.keep.ndim != 3 or a.keep.shape[1:] != self.poly:
+            raise PvwError("DimensionMismatch", f"polys: expected a host array [count]{list(self.poly)}")
+        count = a.keep.shape[0]
+        buf = np.empty(count * self.wire_layout.record_bytes, dtype=np.uint8)
+        self._check(self.lib.pvw_wire_polys_serialize(self.h, count, a.ptr, buf.ctypes.data))
+        return buf.tobytes()
+
+    def wire_polys_deserialize(self, data, count: int) -> np.ndarray:
+        ptr, keep, dev = self._bytes_arg(data, count * self.wire_layout.record_bytes, "data")
+        if dev:
+            raise PvwError("InvalidParameters", "data: host bytes expected")
+        out = np.empty((count,) + self.poly, dtype=np.uint64)
+        self._check(self.lib.pvw_wire_polys_deserialize(self.h, count, ptr, out.ctypes.data))
+        return out
+
     def decrypt_batch(self, party_idx, sk, dealer_slots=None, D: Optional[int] = None, out=None):
         """out[p][d] for P parties (global indices inside the shard) x D stored ciphertexts"""
         pidx = np.ascontiguousarray(party_idx, dtype=np.uint32)

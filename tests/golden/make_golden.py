@@ -44,7 +44,24 @@ def make(name, D, msg_mode):
     print(name, "ok", os.path.getsize(os.path.join(HERE, f"{name}.npz")), "bytes")
 
 
+def make_wire():
+    """wire-format blobs (oracle/pvw_wire.py; third-party encodings recalled -- parity unpinned) of the EX system"""
+    import pvw_wire as W
+    P = params("EX")
+    S = System(P, 2)
+    c1, c2 = S.encrypt()
+    u8 = lambda b: np.frombuffer(b, dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "EX_wire.npz"), ct1=u8(W.ciphertext_to_bytes(P, c1[1].tolist(), c2[1].tolist())),
+                        params=u8(W.params_to_bytes(P)), pk3=u8(W.public_key_to_bytes(P, S.B[3].tolist())),
+                        crs=u8(W.crs_to_bytes(P, S.A.tolist())))
+    print("EX_wire ok", os.path.getsize(os.path.join(HERE, "EX_wire.npz")), "bytes")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["wire"]:
+        make_wire()
+        sys.exit(0)
+    make_wire()
     make("EX", 3, "example")
     make("T16", 4, "u63")
     make("RAG", 3, "u63")

@@ -68,6 +68,23 @@ int main(int argc, char** argv) {
       good &= !partial.is_full();
       good &= fails_with("InvalidParameters", [&] { encrypt(all[0], partial, rng); });
     }
+    {
+      // tests/serialization.rs:233-295, :319-360: a ciphertext survives bincode byte for byte and still decrypts; a second
+      // key holder rebuilt from the serialised public-key rows and CRS produces identical bytes
+      auto bytes = serialize(cts[1]);
+      auto back = deserialize_ciphertext(bytes, global_pk, 0);          // overwrites slot 0 with dealer 1's ciphertext
+      good &= serialize(back) == bytes && back.c1() == cts[1].c1() && back.c2() == cts[1].c2();
+      good &= decrypt_party_value(back, parties[2].secret_key(), 2) == all[1][2];
+      GlobalPublicKey twin(crs);
+      deserialize_public_key_rows(twin, 0, num_parties, serialize_public_key_rows(global_pk, 0, num_parties));
+      good &= twin.is_full() && serialize_crs(twin) == serialize_crs(global_pk);
+      good &= twin.get_public_key(3) == global_pk.get_public_key(3);
+      bytes[bytes.size() - 1] ^= 1;                                      // embedded error bound changed
+      good &= fails_with("DeserializationError", [&] { deserialize_ciphertext(bytes, global_pk, 0); });
+      bytes.resize(bytes.size() - 10);
+      good &= fails_with("InsufficientData", [&] { deserialize_ciphertext(bytes, global_pk, 0); });
+      printf("serialised ciphertext: %zu bytes (raw residues %zu)\n", bytes.size() + 10, (size_t)(params->k + params->n) * params->poly_words() * 8);
+    }
     good &= fails_with("InvalidParameters", [&] { PvwParametersBuilder().set_parties(3).set_dimension(4).set_l(12).set_moduli(moduli).build_arc(); });
     printf("%s\n", good ? "ALL CHECKS PASSED" : "CHECK FAILED");
     return good ? 0 : 1;

@@ -33,6 +33,8 @@ class PvwError : public std::runtime_error {
       case PVW_ERR_ENCRYPTION: return "EncryptionError";
       case PVW_ERR_DECRYPTION: return "DecryptionError";
       case PVW_ERR_KEYGEN: return "KeyGenerationError";
+      case PVW_ERR_DESERIALIZATION: return "DeserializationError";
+      case PVW_ERR_INSUFFICIENT_DATA: return "InsufficientData";
       default: return "InternalError";
     }
   }
@@ -286,6 +288,58 @@ inline std::vector<uint64_t> decrypt_party_shares(const std::vector<PvwCiphertex
   std::vector<uint64_t> out(cts.size());
   std::lock_guard<std::mutex> g(cts[0].ctx->mu);
   cts[0].ctx->check(pvw_decrypt_batch(cts[0].ctx->get(), (uint32_t)cts.size(), slots.data(), 1, &pidx, sk.secret_coeffs.data(), out.data(), PVW_IO_HOST));
+  return out;
+}
+
+
+// ---- the crate's `serde` feature: bincode::serialize / bincode::deserialize of the polynomial-bearing types ----------
+// (encryption.rs:298-354, crs.rs:228-295, public_key.rs:471-519; byte layout in pvw_b200.h).  The bit packing runs on the
+// device where the data lives; only the wire bytes cross PCIe.
+inline pvw_wire_layout wire_layout(const Context& ctx) {
+  pvw_wire_layout w{};
+  ctx.check(pvw_wire_layout_get(ctx.get(), &w));
+  return w;
+}
+// bincode::serialize(&ciphertext)
+inline std::vector<uint8_t> serialize(const PvwCiphertext& ct) {
+  std::vector<uint8_t> out(wire_layout(*ct.ctx).ciphertext_bytes);
+  std::lock_guard<std::mutex> g(ct.ctx->mu);
+  ct.ctx->check(pvw_wire_ct_serialize(ct.ctx->get(), ct.slot, 1, out.data(), out.size(), PVW_IO_HOST));
+  return out;
+}
+// bincode::deserialize::<PvwCiphertext>(&bytes) into store slot `slot` of the key's context; the embedded parameters must be
+// the key's (the reference builds a fresh Arc<PvwParameters> from them instead)
+inline PvwCiphertext deserialize_ciphertext(const std::vector<uint8_t>& bytes, const GlobalPublicKey& pk, uint32_t slot) {
+  auto ctx = pk.context();
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->check(pvw_wire_ct_deserialize(ctx->get(), slot, 1, bytes.data(), bytes.size(), PVW_IO_HOST));
+  return PvwCiphertext{pk.params, ctx, slot};
+}
+// bincode::serialize(&global_pk.crs) and the rows of global_pk.matrix ([u64 k][k records] each: one PublicKey body)
+inline std::vector<uint8_t> serialize_crs(const GlobalPublicKey& pk) {
+  auto ctx = pk.context();
+  std::vector<uint8_t> out(wire_layout(*ctx).crs_bytes);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->check(pvw_wire_crs_serialize(ctx->get(), out.data(), out.size(), PVW_IO_HOST));
+  return out;
+}
+inline std::vector<uint8_t> serialize_public_key_rows(const GlobalPublicKey& pk, uint32_t row, uint32_t count) {
+  auto ctx = pk.context();
+  std::vector<uint8_t> out((size_t)count * wire_layout(*ctx).pk_row_bytes);
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->check(pvw_wire_pk_serialize_rows(ctx->get(), row, count, out.data(), PVW_IO_HOST));
+  return out;
+}
+inline void deserialize_public_key_rows(GlobalPublicKey& pk, uint32_t row, uint32_t count, const std::vector<uint8_t>& bytes) {
+  auto ctx = pk.context();
+  if (bytes.size() < (size_t)count * wire_layout(*ctx).pk_row_bytes) throw PvwError(PVW_ERR_INSUFFICIENT_DATA, "public key rows: buffer too short");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->check(pvw_wire_pk_deserialize_rows(ctx->get(), row, count, bytes.data(), PVW_IO_HOST));
+}
+// bincode::serialize(&*params)
+inline std::vector<uint8_t> serialize(const PvwParameters& p) {
+  std::vector<uint8_t> out(wire_layout(*p.probe).params_bytes);
+  p.probe->check(pvw_wire_params(p.probe->get(), out.data(), out.size()));
   return out;
 }
 

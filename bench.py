@@ -401,7 +401,7 @@ def run_b200(args):
         import pvw_oracle as O
         P = O.Params(n, k, l, moduli, psi=eng.psi)
         co = CO.COracle(P)
-        Dc = args.cpu_dealers
+        Dc = min(args.cpu_baseline_dealers, Dg)
         A_h = eng.crs_download()
         B_h = eng.pk_download_rows(0, n)
         r_h, e1_h, e2_h, m_h, sk_h = n_r[:Dc], n_e1[:Dc], n_e2[:Dc], n_m[:Dc], n_sk
@@ -465,7 +465,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dealers", type=int, default=256, help="dealers per GPU per step")
     ap.add_argument("--parties", type=int, default=N_PARTIES)
-    ap.add_argument("--cpu-dealers", type=int, default=16, help="dealers in the CPU sample")
+    ap.add_argument("--cpu-dealers", type=int, default=16, help="dealers per step of the --impl reference arm")
+    ap.add_argument("--cpu-baseline-dealers", type=int, default=64, help="dealers in the cpu_baseline sample (about 11 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

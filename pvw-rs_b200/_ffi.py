@@ -79,7 +79,7 @@ SIGNATURES = {
     "pvw_version": (C.c_char_p, []),
 }
 
-KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute", "wire"]
+KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute", "wire", "expand"]
 
 _lib = None
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpvw_b200.so")
-SOURCES = ["capi.cu", "ntt.cu", "mac.cu", "decode.cu", "wire.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "mac.cu", "decode.cu", "wire.cu", "imma.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]

@@ -21,6 +21,7 @@
 #include "hostparams.hpp"
 #include "crsgen.hpp"
 #include "kernels.cuh"
+#include "imma.cuh"
 
 using namespace pvw;
 
@@ -95,6 +96,12 @@ struct pvw_ctx {
   uint64_t prof_n[PVW_KERNEL_KINDS] = {0};
   double prof_bytes[PVW_KERNEL_KINDS] = {0};
   int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
+  // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
+  // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
+  int use_imma = 1;
+  int64_t imma_min_dealers = 8, imma_chunk_dealers = 512;
+  DevBuf As, Bs, Vx, shat_s;
+  bool As_valid = false, Bs_valid = false;
   int64_t decrypt_chunk_shares = 1 << 19;
   int64_t upload_chunk_bytes = 256ll << 20;
 
@@ -331,6 +338,51 @@ void gemm(pvw_ctx* c, GemmArgs a) {
   launch(c, PVW_KERNEL_MAC, bytes, [&] { launch_mac_gemm(a, c->gemm_impl, c->stream); });
 }
 
+// ---- tensor-core product (imma.cu) --------------------------------------------------------------------------------
+bool imma_wanted(const pvw_ctx* c, uint32_t rows, uint32_t D) {
+  return c->use_imma && D >= (uint32_t)c->imma_min_dealers && imma_shape_ok(rows, D, c->hp.k);
+}
+const u64* slot_major_A(pvw_ctx* c) {
+  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+  if (!c->As_valid) {
+    c->As.ensure((size_t)L * ell * k * k * 8);
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_slot_major(c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, k, k, L, ell, c->As.as<u64>(), (size_t)k * k, true, c->stream); });
+    c->As_valid = true;
+  }
+  return c->As.as<u64>();
+}
+const u64* slot_major_B(pvw_ctx* c) {
+  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+  if (!c->Bs_valid) {
+    c->Bs.ensure((size_t)L * ell * nrows * k * 8);
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_slot_major(c->B.as<u64>(), (size_t)nrows * k * ell, (size_t)k * ell, nrows, k, L, ell, c->Bs.as<u64>(), (size_t)nrows * k, true, c->stream); });
+    c->Bs_valid = true;
+  }
+  return c->Bs.as<u64>();
+}
+// V[sd*V_ds + limb*V_ls + j*ell + c] for dealers [d0, d0 + Dc) -> c->Vx (one chunk at a time)
+void imma_expand(pvw_ctx* c, const u64* V, size_t V_ds, size_t V_ls, uint32_t d0, uint32_t Dc, bool packed, const uint32_t* dmap) {
+  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+  const size_t plane = (size_t)Dc * IMMA_DIAGS * k * 8;
+  c->Vx.ensure((size_t)L * ell * plane);
+  const double bytes = (double)Dc * L * k * ell * 8.0 * (1 + IMMA_DIAGS);
+  launch(c, PVW_KERNEL_EXPAND, bytes, [&] {
+    launch_imma_expand(dmap ? V : V + (size_t)d0 * V_ds, V_ds, V_ls, ell, Dc, k, L, c->Vx.as<uint8_t>(), plane, packed, dmap ? dmap + d0 : nullptr, c->stream);
+  });
+}
+// one GEMM over the expanded chunk in c->Vx; `a` describes the whole product, dealers [d0, d0 + Dc) of it are computed
+void imma_gemm_chunk(pvw_ctx* c, ImmaArgs a, uint32_t d0, uint32_t Dc) {
+  a.Vx = c->Vx.as<uint8_t>();
+  a.Vx_plane = (size_t)Dc * IMMA_DIAGS * a.k * 8;
+  a.O += (size_t)d0 * a.O_ds;
+  if (a.V_dmap) a.V_dmap += d0; else if (a.S) a.S += (size_t)d0 * a.S_ds;
+  a.D = Dc;
+  const double bytes = (double)Dc * a.rows * (a.k + 1.0) * a.L * a.ell * 8.0;
+  bool ok = true;
+  launch(c, PVW_KERNEL_MAC, bytes, [&] { ok = launch_imma_gemm(a, c->stream); });
+  require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
+}
+
 void ensure_At(pvw_ctx* c) {
   if (c->At_valid) return;
   const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
@@ -412,7 +464,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->wire_tab, &c->wire_buf})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s})
     b->release();
   delete c;
 }
@@ -449,7 +501,7 @@ int pvw_crs_upload(pvw_ctx* c, const uint64_t* A, uint32_t flags) {
     c->A.ensure((size_t)L * kk * ell * 8);
     upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, flags, true);
     c->A_set = true;
-    c->At_valid = false;
+    c->At_valid = false; c->As_valid = false;
   });
 }
 int pvw_crs_download(pvw_ctx* c, uint64_t* A) {
@@ -483,7 +535,7 @@ int pvw_crs_generate_deterministic(pvw_ctx* c, const uint8_t seed[32], uint64_t*
     c->A.ensure((size_t)L * kk * ell * 8);
     upload_polys(c, A, kk, c->A.as<u64>(), kk * ell, PVW_IO_HOST, true);
     c->A_set = true;
-    c->At_valid = false;
+    c->At_valid = false; c->As_valid = false;
   });
 }
 int pvw_crs_generate_from_tag(pvw_ctx* c, const char* tag, uint64_t* A_out) {
@@ -498,6 +550,7 @@ static void ensure_B(pvw_ctx* c) {
   if (c->B.bytes >= bytes) return;
   c->B.ensure(bytes);
   CUDA_CHECK(cudaMemsetAsync(c->B.p, 0, bytes, c->stream));  // GlobalPublicKey::new fills with zero polys, public_key.rs:196-208
+  c->Bs_valid = false;
 }
 static void check_rows(pvw_ctx* c, uint32_t row, uint32_t count) {
   if ((uint64_t)row + count > c->hp.n)  // add_public_key: index >= n, public_key.rs:216-221
@@ -514,7 +567,7 @@ int pvw_pk_upload_rows(pvw_ctx* c, uint32_t row, uint32_t count, const uint64_t*
     ensure_B(c);
     const uint32_t k = c->hp.k, ell = c->hp.ell;
     upload_polys(c, B, (uint64_t)count * k, c->B.as<u64>() + (size_t)(row - c->row0) * k * ell, (size_t)c->nrows * k * ell, flags, true);
-    c->num_keys = std::max(c->num_keys, row + count);
+    c->num_keys = std::max(c->num_keys, row + count); c->Bs_valid = false;
   });
 }
 int pvw_pk_download_rows(pvw_ctx* c, uint32_t row, uint32_t count, uint64_t* B) {
@@ -557,7 +610,7 @@ int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk
     g.O = Brow; g.O_ls = (size_t)c->nrows * k * ell; g.O_ds = (size_t)k * ell; g.O_packed = 1;  // B is an operand of the c2 product
     g.rows = k; g.D = count; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
     gemm(c, g);
-    c->num_keys = std::max(c->num_keys, row + count);
+    c->num_keys = std::max(c->num_keys, row + count); c->Bs_valid = false;
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));  // host buffers may be reused by the caller
   });
 }
@@ -630,39 +683,67 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       d_e1 = (const long long*)stage_in(c, c->in_small2, e1 + (size_t)c1_lo * k * ell, (size_t)(c1_hi - c1_lo) * k * ell * 8, flags);
     const long long* d_e2 = (const long long*)stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags, c->ev[0]);
     const u64* d_m = (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]);
-    // r_hat[d][limb][j][ell]   (encryption.rs:147-154)
+    // r_hat[d][limb][j][ell]   (encryption.rs:147-154): operand form for the IMAD kernel, canonical for the tensor-core one
+    const bool imma = imma_wanted(c, nrows, D);
     c->rhat.ensure((size_t)D * w1 * 8);
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream, false, true); });
+    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream, false, !imma); });
     u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
-    if (c1_hi > c1_lo) {
-      const uint32_t Dc = c1_hi - c1_lo;
-      // c1 <- NTT(e1)   (encryption.rs:161-167), then c1 += A r_hat   (crs.rs:187-199, encryption.rs:171-173)
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)Dc * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream); });
-      GemmArgs g{};
-      g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
-      g.V = c->rhat.as<u64>() + (size_t)c1_lo * w1; g.V_ls = (size_t)k * ell; g.V_ds = w1;
-      g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_packed = 1;  // c1 is an operand of the decrypt product
-      g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
-      gemm(c, g);
-    }
-    {
-      // device inputs: c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
-      // host inputs:   c2 <- B r_hat first (it does not need e2 / m, whose copy is still in flight), then c2 += NTT(e2) + m g_hat
-      auto preload = [&](bool accumulate) {
-        launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream, accumulate); });
-      };
-      if (!host) preload(false);
+    // c1 <- NTT(e1)   (encryption.rs:161-167); c1 += A r_hat below   (crs.rs:187-199, encryption.rs:171-173)
+    if (c1_hi > c1_lo)
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)(c1_hi - c1_lo) * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream); });
+    // device inputs: c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
+    // host inputs:   c2 <- B r_hat first (it does not need e2 / m, whose copy is still in flight), then c2 += NTT(e2) + m g_hat
+    auto preload = [&](bool accumulate) {
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream, accumulate); });
+    };
+    if (!host) preload(false);
+    if (imma) {
+      // tensor-core product (imma.cu): every chunk of dealers is expanded once and serves both c1 and c2
+      ImmaArgs g1{}, g2{};
+      g1.M = slot_major_A(c); g1.M_plane = (size_t)k * k; g1.rows = k;
+      g1.O = c1; g1.O_ls = (size_t)k * ell; g1.O_ds = w1; g1.O_rs = ell; g1.O_cs = 1; g1.O_packed = 1; g1.mode = 0;
+      g2.M = slot_major_B(c); g2.M_plane = (size_t)nrows * k; g2.rows = nrows;
+      g2.O = c2; g2.O_ls = (size_t)nrows * ell; g2.O_ds = w2; g2.O_rs = ell; g2.O_cs = 1; g2.O_packed = 0; g2.mode = host ? 2 : 0;
+      g1.k = g2.k = k; g1.L = g2.L = L; g1.ell = g2.ell = ell; g1.lc = g2.lc = c->T.lc;
+      const uint32_t step = (uint32_t)std::max<int64_t>(16, c->imma_chunk_dealers);
+      for (uint32_t dc0 = 0; dc0 < D; dc0 += step) {
+        const uint32_t Dc = std::min(step, D - dc0);
+        imma_expand(c, c->rhat.as<u64>(), w1, (size_t)k * ell, dc0, Dc, false, nullptr);
+        const uint32_t lo = std::max(dc0, c1_lo), hi = std::min(dc0 + Dc, c1_hi);
+        if (hi > lo) {
+          // the c1 slice of this chunk: dealers [lo, hi) are rows [lo - dc0, hi - dc0) of the expanded chunk
+          ImmaArgs g = g1;
+          g.Vx = c->Vx.as<uint8_t>() + (size_t)(lo - dc0) * IMMA_DIAGS * k * 8;
+          g.Vx_plane = (size_t)Dc * IMMA_DIAGS * k * 8;
+          g.O += (size_t)lo * g.O_ds;
+          g.D = hi - lo;
+          bool ok = true;
+          launch(c, PVW_KERNEL_MAC, (double)g.D * k * (k + 1.0) * L * ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
+          require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
+        }
+        imma_gemm_chunk(c, g2, dc0, Dc);
+      }
+    } else {
+      if (c1_hi > c1_lo) {
+        const uint32_t Dc = c1_hi - c1_lo;
+        GemmArgs g{};
+        g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
+        g.V = c->rhat.as<u64>() + (size_t)c1_lo * w1; g.V_ls = (size_t)k * ell; g.V_ds = w1;
+        g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_packed = 1;  // c1 is an operand of the decrypt product
+        g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
+        gemm(c, g);
+      }
       GemmArgs g{};
       g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
       g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
       g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2;
       g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = host ? 2 : 0; g.lc = c->T.lc;
       gemm(c, g);
-      if (host) {
-        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
-        preload(true);
-      }
+    }
+    if (host) {
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+      preload(true);
     }
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -741,11 +822,15 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       c->outd.ensure((size_t)P * D * 8);
       d_out = c->outd.as<u64>();
     }
-    uint32_t Pc_max = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(P, c->decrypt_chunk_shares / std::max<uint32_t>(D, 1)));
-    c->shat.ensure((size_t)L * Pc_max * k * ell * 8);
-    c->z.ensure((size_t)D * L * Pc_max * ell * 8);
-    c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * D) * 8);   // sized for the largest chunk up front: growing a
-    c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * D) * 8);   // buffer mid-call would synchronise the device
+    // tensor-core product: dealers are processed in chunks (their c1 is expanded once per chunk, imma.cu), parties in chunks
+    // inside; the IMAD kernel takes all dealers at once
+    const bool imma = imma_wanted(c, P, D);
+    const uint32_t Dstep = imma ? (uint32_t)std::min<int64_t>(D, std::max<int64_t>(16, c->imma_chunk_dealers)) : D;
+    uint32_t Pc_max = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(P, c->decrypt_chunk_shares / std::max<uint32_t>(Dstep, 1)));
+    (imma ? c->shat_s : c->shat).ensure((size_t)L * Pc_max * k * ell * 8);
+    c->z.ensure((size_t)Dstep * L * Pc_max * ell * 8);
+    c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * Dstep) * 8);   // sized for the largest chunk up front: growing a
+    c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * Dstep) * 8);   // buffer mid-call would synchronise the device
     // host inputs: a short first chunk, so that little of the secret-key copy is exposed before the kernels start
     const uint32_t first = host ? std::max<uint32_t>(1, std::min<uint32_t>(Pc_max, std::max<uint32_t>(Pc_max / 8, 64))) : Pc_max;
     if (host) {  // every chunk's secret keys are queued now, in order, each with its own event: chunk i+1 arrives while chunk i computes
@@ -759,27 +844,49 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
         p0 += Pc;
       }
     }
-    uint32_t chunk_no = 0;
-    for (uint32_t p0 = 0; p0 < P; chunk_no++) {
-      const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
-      if (host) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[chunk_no], 0));
-      // s_hat[limb][p][j][ell]   (SecretKey::get_polynomial, secret_key.rs:98-112 -- once per party, not per ciphertext)
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream, false, true); });
-      // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274)
-      GemmArgs g{};
-      g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;
-      g.V = c->c1s.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell; g.V_dmap = d_slots;
-      g.O = c->z.as<u64>(); g.O_ls = (size_t)Pc * ell; g.O_ds = (size_t)L * Pc * ell;
-      g.S = c->c2s.as<u64>(); g.S_ls = (size_t)nrows * ell; g.S_ds = (size_t)L * nrows * ell; g.S_rowmap = c->idxp.as<uint32_t>() + p0;
-      g.rows = Pc; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
-      gemm(c, g);
-      decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, D, d_out + (size_t)p0 * D, D);
-      if (host) {  // this chunk's plaintexts go home while the next chunk computes
-        CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
-        CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev[3], 0));
-        CUDA_CHECK(cudaMemcpyAsync(out + (size_t)p0 * D, d_out + (size_t)p0 * D, (size_t)Pc * D * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    for (uint32_t dc0 = 0; dc0 < D; dc0 += Dstep) {
+      const uint32_t Dc = std::min(Dstep, D - dc0);
+      if (imma) imma_expand(c, c->c1s.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, dc0, Dc, true, d_slots);
+      uint32_t chunk_no = 0;
+      for (uint32_t p0 = 0; p0 < P; chunk_no++) {
+        const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
+        if (host && dc0 == 0) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[chunk_no], 0));
+        // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274), with
+        // s_hat = SecretKey::get_polynomial (secret_key.rs:98-112) computed once per party, not per ciphertext
+        if (imma) {
+          launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat_s.as<u64>(), 0, (size_t)Pc * k, c->stream, false, false, true); });
+          ImmaArgs g{};
+          g.M = c->shat_s.as<u64>(); g.M_plane = (size_t)Pc * k; g.rows = Pc;
+          g.O = c->z.as<u64>(); g.O_ls = (size_t)Pc * ell; g.O_ds = (size_t)L * Pc * ell; g.O_rs = ell; g.O_cs = 1;
+          g.S = c->c2s.as<u64>(); g.S_ls = (size_t)nrows * ell; g.S_ds = (size_t)L * nrows * ell; g.S_rowmap = c->idxp.as<uint32_t>() + p0;
+          g.V_dmap = d_slots;
+          g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
+          // O is chunk-local (dealer 0 of the chunk at z), S / the dealer map are global: shift them, not O
+          ImmaArgs gc = g;
+          gc.Vx = c->Vx.as<uint8_t>(); gc.Vx_plane = (size_t)Dc * IMMA_DIAGS * k * 8; gc.D = Dc;
+          if (gc.V_dmap) gc.V_dmap += dc0; else gc.S += (size_t)dc0 * gc.S_ds;
+          bool ok = true;
+          launch(c, PVW_KERNEL_MAC, (double)Dc * Pc * (k + 1.0) * L * ell * 8.0, [&] { ok = launch_imma_gemm(gc, c->stream); });
+          require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
+        } else {
+          launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream, false, true); });
+          GemmArgs g{};
+          g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;
+          g.V = c->c1s.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell; g.V_dmap = d_slots;
+          g.O = c->z.as<u64>(); g.O_ls = (size_t)Pc * ell; g.O_ds = (size_t)L * Pc * ell;
+          g.S = c->c2s.as<u64>(); g.S_ls = (size_t)nrows * ell; g.S_ds = (size_t)L * nrows * ell; g.S_rowmap = c->idxp.as<uint32_t>() + p0;
+          g.rows = Pc; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
+          gemm(c, g);
+        }
+        decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, Dc, d_out + (size_t)p0 * D + dc0, D);
+        if (host) {  // this chunk's plaintexts go home while the next chunk computes
+          CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
+          CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev[3], 0));
+          CUDA_CHECK(cudaMemcpy2DAsync(out + (size_t)p0 * D + dc0, (size_t)D * 8, d_out + (size_t)p0 * D + dc0, (size_t)D * 8, (size_t)Dc * 8, Pc,
+                                       cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        p0 += Pc;
       }
-      p0 += Pc;
     }
     if (host) {
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1015,7 +1122,7 @@ int pvw_wire_pk_deserialize_rows(pvw_ctx* c, uint32_t row, uint32_t count, const
       wire_unpack(c, dev + 8, z.row, k, rc, dst, (size_t)c->nrows * k * ell, (size_t)k * ell, true, true);
       if (host) CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
-    c->num_keys = std::max(c->num_keys, row + count);
+    c->num_keys = std::max(c->num_keys, row + count); c->Bs_valid = false;
   });
 }
 
@@ -1055,7 +1162,7 @@ int pvw_wire_crs_deserialize(pvw_ctx* c, const uint8_t* in, uint64_t len, uint32
     wire_err_check(c, "PvwCrs");
     wire_unpack(c, dev + 16, z.row, k, k, c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, true, true);
     c->A_set = true;
-    c->At_valid = false;
+    c->At_valid = false; c->As_valid = false;
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
 }
@@ -1101,6 +1208,9 @@ int pvw_ctx_synchronize(pvw_ctx* c) {
 void* pvw_ctx_stream(pvw_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
+  if (c && name && std::string(name) == "imma") { c->use_imma = value != 0; return PVW_OK; }
+  if (c && name && std::string(name) == "imma_min_dealers") { c->imma_min_dealers = std::max<int64_t>(1, value); return PVW_OK; }
+  if (c && name && std::string(name) == "imma_chunk_dealers") { c->imma_chunk_dealers = std::max<int64_t>(16, value); return PVW_OK; }
   return guarded(c, [&] {
     require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");
     std::string n(name);

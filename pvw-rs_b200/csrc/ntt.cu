@@ -10,7 +10,8 @@
 
 namespace pvw {
 
-template <int ELL, int MODE>  // MODE 0: store canonical, 1: accumulate into canonical, 2: store packed halves (operand form)
+template <int ELL, int MODE>  // MODE 0: store canonical, 1: accumulate into canonical, 2: store packed halves (operand form),
+                               // 3: store canonical in the slot-major form of the tensor-core path: out[(limb*ELL + c)*lstride + idx]
 __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
@@ -42,6 +43,11 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 #pragma unroll
     for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], mulmod_shoup(mr, s_g[t], s_g_sh[t], lc.q), lc.q);
   }
+  if (MODE == 3) {
+#pragma unroll
+    for (int t = 0; t < ELL; t++) out[((size_t)limb * ELL + t) * lstride + idx] = a[t];   // consecutive threads: consecutive words
+    return;
+  }
   uint64_t vec = idx / inner, j = idx % inner;
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
 #pragma unroll
@@ -58,12 +64,14 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 }
 
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out) {
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, bool slot_major) {
   if (count == 0) return;
   dim3 grid((unsigned)((count + 127) / 128), T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
-    if (accumulate)                                                                                                           \
+    if (slot_major)                                                                                                           \
+      ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+    else if (accumulate)                                                                                                           \
       ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
     else if (pack_out)                                                                                                        \
       ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \

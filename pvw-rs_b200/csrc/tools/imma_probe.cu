@@ -1,0 +1,122 @@
+// imma_probe.cu -- bring-up / measurement of the INT8 tensor-core form of the modular matrix product (tcgen05.mma kind::i8).
+//
+//   O[row][d] = sum_j M[row][j] * V[d][j]  (mod q),   M, V < 2^62
+// A 64-bit operand is its 8 little-endian bytes, so  M*V = sum_u 2^(8u) sum_{s+t=u} m_s v_t.  With the M row kept as it is
+// in memory (K'' = 8k bytes) and V expanded into 15 "diagonal" rows  Vx[(d,u)][(j,s)] = v_{u-s}(d,j)  (zero outside 0..7),
+// one u8 x u8 -> s32 GEMM  C[row][(d,u)] = sum_{(j,s)} M''[row][(j,s)] Vx[(d,u)][(j,s)]  yields the 15 diagonal sums of every
+// output in the TMEM lane of its row: the epilogue recombines them thread-locally into a 160-bit integer and reduces.
+//
+// usage: imma_probe [rows] [D] [k] [planes] [reps]      (rows % 256 == 0, D % 16 == 0, k % 16 == 0)
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../imma.cuh"
+
+using namespace pvw;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__global__ void fill_kernel(u64* p, size_t n, u64 q, u64 seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    u64 x = seed + i * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    p[i] = x % q;
+  }
+}
+// reference: plain modular dot products
+__global__ void ref_kernel(const u64* M, const u64* V, u64* O, uint32_t rows, uint32_t D, uint32_t k, LimbConst lc, uint32_t row_lim, uint32_t d_lim) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y, plane = blockIdx.z;
+  if (row >= row_lim || d >= d_lim) return;
+  const u64* m = M + ((size_t)plane * rows + row) * k;
+  const u64* v = V + ((size_t)plane * D + d) * k;
+  u64 acc = 0;
+  for (uint32_t j = 0; j < k; j++) acc = addmod(acc, mulmod(m[j], v[j], lc), lc.q);
+  O[((size_t)plane * D + d) * rows + row] = acc;
+}
+
+static LimbConst make_lc(u64 q) {
+  LimbConst c{};
+  c.q = q;
+  unsigned __int128 one = 1;
+  // floor(2^128 / q): long division
+  unsigned __int128 hi = (~(unsigned __int128)0) / q;   // floor((2^128 - 1) / q) == floor(2^128 / q) unless q | 2^128
+  c.mu_hi = (u64)(hi >> 64); c.mu_lo = (u64)hi;
+  c.mu64 = (u64)(((one << 64)) / q);
+  c.r128 = (u64)((((~(unsigned __int128)0) % q) + 1) % q);
+  return c;
+}
+
+int main(int argc, char** argv) {
+  const uint32_t rows = argc > 1 ? atoi(argv[1]) : 4096, D = argc > 2 ? atoi(argv[2]) : 256, k = argc > 3 ? atoi(argv[3]) : 256;
+  const uint32_t planes = argc > 4 ? atoi(argv[4]) : 8, reps = argc > 5 ? atoi(argv[5]) : 5;
+  const u64 q = 0x3ffffffffffffdc1ull;
+  const LimbConst lc = make_lc(q);
+  u64 *M, *V, *O, *Oref;
+  uint8_t* Vx;
+  LimbConst* dlc;
+  CK(cudaMalloc(&M, (size_t)planes * rows * k * 8));
+  CK(cudaMalloc(&V, (size_t)planes * D * k * 8));
+  CK(cudaMalloc(&Vx, (size_t)planes * D * 15 * k * 8));
+  CK(cudaMalloc(&O, (size_t)planes * D * rows * 8));
+  CK(cudaMalloc(&Oref, (size_t)planes * D * rows * 8));
+  CK(cudaMalloc(&dlc, planes * sizeof(LimbConst)));
+  {
+    std::vector<LimbConst> lcs(planes, lc);
+    CK(cudaMemcpy(dlc, lcs.data(), planes * sizeof(LimbConst), cudaMemcpyHostToDevice));
+  }
+  fill_kernel<<<1024, 256>>>(M, (size_t)planes * rows * k, q, 1);
+  fill_kernel<<<1024, 256>>>(V, (size_t)planes * D * k, q, 2);
+  CK(cudaMemset(O, 0xff, (size_t)planes * D * rows * 8));
+  // worst case rows: all residues q - 1 in row 0 / dealer 0 of plane 0
+  {
+    std::vector<u64> ones(k, q - 1);
+    CK(cudaMemcpy(M, ones.data(), k * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(V, ones.data(), k * 8, cudaMemcpyHostToDevice));
+  }
+  ImmaArgs a{};
+  a.M = M; a.M_plane = (size_t)rows * k; a.rows = rows; a.k = k; a.L = planes; a.ell = 1;   // plane = limb (ell = 1 view)
+  a.Vx = Vx; a.Vx_plane = (size_t)D * 15 * k * 8; a.D = D;
+  a.O = O; a.O_ds = rows; a.O_ls = (size_t)D * rows; a.O_rs = 1; a.O_cs = 0;
+  a.lc = dlc; a.mode = 2;
+  launch_imma_expand(V, k, (size_t)D * k, 1, D, k, planes, Vx, a.Vx_plane, false, nullptr, 0);
+  CK(cudaGetLastError());
+  if (!launch_imma_gemm(a, 0)) { printf("launch_imma_gemm: tensor map creation failed\n"); return 1; }
+  CK(cudaDeviceSynchronize());
+  // check a window against the reference
+  const uint32_t row_lim = rows < 512 ? rows : 512, d_lim = D < 48 ? D : 48;
+  ref_kernel<<<dim3((row_lim + 127) / 128, d_lim, planes), 128>>>(M, V, Oref, rows, D, k, lc, row_lim, d_lim);
+  CK(cudaDeviceSynchronize());
+  std::vector<u64> h((size_t)planes * D * rows), hr((size_t)planes * D * rows);
+  CK(cudaMemcpy(h.data(), O, h.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hr.data(), Oref, hr.size() * 8, cudaMemcpyDeviceToHost));
+  size_t bad = 0, checked = 0;
+  for (uint32_t p = 0; p < planes; p++)
+    for (uint32_t d = 0; d < d_lim; d++)
+      for (uint32_t r = 0; r < row_lim; r++) {
+        const size_t i = ((size_t)p * D + d) * rows + r;
+        checked++;
+        if (h[i] != hr[i]) { if (bad < 5) printf("mismatch plane %u d %u row %u: got %llx want %llx\n", p, d, r, h[i], hr[i]); bad++; }
+      }
+  printf("checked %zu outputs, %zu mismatches\n", checked, bad);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int pass = 0; pass < 2; pass++) {
+    CK(cudaEventRecord(e0));
+    for (uint32_t i = 0; i < reps; i++) {
+      if (pass == 1) launch_imma_expand(V, k, (size_t)D * k, 1, D, k, planes, Vx, a.Vx_plane, false, nullptr, 0);
+      else launch_imma_gemm(a, 0);
+    }
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double macs = (double)rows * D * k * planes * reps;
+    if (pass == 0) printf("imma_gemm: %.3f ms per launch, %.3e 62-bit MAC/s, %.1f int8 TOPS (dense, incl. zero diagonals)\n", ms / reps, macs / (ms * 1e-3), macs * 120 * 2 / (ms * 1e-3) / 1e12);
+    else printf("imma_expand: %.3f ms per launch (%.1f GB/s written)\n", ms / reps, (double)planes * D * 15 * k * 8 * reps / (ms * 1e-3) / 1e9);
+  }
+  return bad ? 2 : 0;
+}

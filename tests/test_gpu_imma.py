@@ -1,0 +1,111 @@
+"""GPU: the tensor-core form of the matrix product (csrc/imma.cu: tcgen05.mma kind::i8 on byte diagonals) against the oracle
+and against the IMAD kernel, bit-exact, through the C ABI.  The default build uses it whenever a call batches >= 8 dealers;
+here it is forced on for every batch size, with 16-dealer chunks so that the chunk loops run too."""
+import numpy as np
+import pytest
+
+import pvw_oracle as O
+from _cases import P128_MODULI, P256_MODULI, System, engine_kwargs, params
+
+pytestmark = pytest.mark.gpu
+
+# name -> oracle parameters: the shared sets with an even k, plus ragged ones (nothing divides a tile) for this kernel
+SETS = {
+    "EX": lambda: params("EX"),
+    "T16": lambda: params("T16"),
+    "VDs": lambda: params("VDs"),
+    "P128s": lambda: params("P128s"),
+    "P256s": lambda: params("P256s"),
+    "RAG2": lambda: O.Params(13, 6, 8, O.TEST_MODULI, error_bound_1=50, error_bound_2=50),
+    "L32b": lambda: O.Params(5, 4, 32, O.largest_ntt_primes(5), secret_variance=1.0),
+    "WIDE": lambda: O.Params(300, 18, 8, O.TEST_MODULI, error_bound_1=50, error_bound_2=50),   # two row tiles, k*8 = 144 bytes
+}
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import pvw_rs_b200
+    return pvw_rs_b200
+
+
+def forced(pkg, P, on=True, **over):
+    eng = pkg.Engine(**engine_kwargs(P, **over))
+    eng.set_option("imma", 1 if on else 0)
+    eng.set_option("imma_min_dealers", 1)
+    eng.set_option("imma_chunk_dealers", 16)
+    return eng
+
+
+def load(eng, S, cap):
+    eng.crs_upload(S.A)
+    eng.pk_upload_rows(eng.row0, S.B[eng.row0:eng.row0 + eng.nrows])
+    eng.ct_reserve(cap)
+    return eng
+
+
+@pytest.mark.parametrize("name,D", [("EX", 1), ("EX", 7), ("EX", 20), ("T16", 5), ("VDs", 3), ("RAG2", 19), ("L32b", 2), ("WIDE", 33),
+                                    ("P128s", 5), ("P128s", 33), ("P256s", 3)])
+def test_encrypt_decrypt_match_oracle_and_imad(pkg, name, D):
+    P = SETS[name]()
+    S = System(P, D, "u63")
+    c1, c2 = S.encrypt()
+    want = S.co.decrypt(S.sk, c1, c2)
+    eng = load(forced(pkg, P), S, D + 1)
+    launches0 = eng.launch_count
+    eng.encrypt_batch(1, S.m, S.r, S.e1, S.e2)
+    for d in range(D):
+        g1, g2 = eng.ct_download(1 + d)
+        assert (g1 == c1[d]).all(), f"c1 dealer {d}"
+        assert (g2 == c2[d]).all(), f"c2 dealer {d}"
+    slots = np.arange(1, D + 1, dtype=np.uint32)
+    got = eng.decrypt_batch(np.arange(P.n), S.sk, dealer_slots=slots)
+    assert (got == want).all()
+    if name != "L32b":
+        assert (got == S.m.T).all()
+    # the expansion kernel ran: this really was the tensor-core path
+    eng.set_option("profile", 2)
+    eng.decrypt_batch(np.arange(P.n), S.sk, dealer_slots=slots)
+    assert eng.profile()["expand"][1] >= 1
+    eng.set_option("profile", 0)
+    # permuted subsets of dealers and parties (examples/pvw_valid_dec.rs:198-210), identical on the IMAD kernel
+    ds = np.array(sorted(set([D, 1, 1 + D // 2])), dtype=np.uint32)[::-1].copy()
+    ps = np.array([P.n - 1, 0, P.n // 2], dtype=np.uint32)
+    sub = eng.decrypt_batch(ps, S.sk[ps], dealer_slots=ds)
+    assert (sub == want[np.ix_(ps, ds - 1)]).all()
+    ref = load(forced(pkg, P, on=False), S, D + 1)
+    ref.encrypt_batch(1, S.m, S.r, S.e1, S.e2)
+    assert (ref.decrypt_batch(ps, S.sk[ps], dealer_slots=ds) == sub).all()
+    assert launches0 < eng.launch_count
+
+
+def test_device_inputs_row_shards_and_dealer_slices(pkg):
+    """row-sharded contexts with c1 computed for a dealer slice only, CUDA-tensor inputs"""
+    import torch
+    P = SETS["WIDE"]()
+    D = 21
+    S = System(P, D, "u63")
+    c1, c2 = S.encrypt()
+    want = S.co.decrypt(S.sk, c1, c2)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+    for lo, hi, dlo, dhi in ((0, 130, 0, 9), (130, 300, 9, 21)):
+        eng = load(forced(pkg, P, row0=lo, nrows=hi - lo), S, D)
+        eng.encrypt_batch(0, dev(S.m[:, lo:hi]), dev(S.r), dev(S.e1), dev(S.e2[:, lo:hi]), c1_range=(dlo, dhi))
+        for d in range(D):
+            g1, g2 = eng.ct_download(d)
+            assert (g2 == c2[d, lo:hi]).all()
+            if dlo <= d < dhi:
+                assert (g1 == c1[d]).all()
+            else:
+                eng.ct_upload(d, c1=c1[d])
+        out = eng.decrypt_batch(np.arange(lo, hi), dev(S.sk[lo:hi]), D=D)
+        assert (out.cpu().numpy().view(np.uint64) == want[lo:hi]).all()
+
+
+def test_odd_k_falls_back_to_the_imad_kernel(pkg):
+    P = params("RAG")                                    # k = 5: rows of 40 bytes cannot be TMA sources
+    S = System(P, 9, "u63")
+    c1, c2 = S.encrypt()
+    eng = load(forced(pkg, P), S, 9)
+    eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)
+    assert all((eng.ct_download(d)[0] == c1[d]).all() and (eng.ct_download(d)[1] == c2[d]).all() for d in range(9))
+    assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=9) == S.m.T).all()

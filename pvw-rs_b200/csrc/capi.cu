@@ -697,14 +697,14 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     auto preload = [&](bool accumulate) {
       launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream, accumulate); });
     };
-    if (!host) preload(false);
+    if (!host && !imma) preload(false);
     if (imma) {
       // tensor-core product (imma.cu): every chunk of dealers is expanded once and serves both c1 and c2
       ImmaArgs g1{}, g2{};
       g1.M = slot_major_A(c); g1.M_plane = (size_t)k * k; g1.rows = k;
       g1.O = c1; g1.O_ls = (size_t)k * ell; g1.O_ds = w1; g1.O_rs = ell; g1.O_cs = 1; g1.O_packed = 1; g1.mode = 0;
       g2.M = slot_major_B(c); g2.M_plane = (size_t)nrows * k; g2.rows = nrows;
-      g2.O = c2; g2.O_ls = (size_t)nrows * ell; g2.O_ds = w2; g2.O_rs = ell; g2.O_cs = 1; g2.O_packed = 0; g2.mode = host ? 2 : 0;
+      g2.O = c2; g2.O_ls = (size_t)nrows * ell; g2.O_ds = w2; g2.O_rs = ell; g2.O_cs = 1; g2.O_packed = 0; g2.mode = 2;   // the product is stored alone; NTT(e2) + m g_hat is added afterwards with unit-stride accesses
       g1.k = g2.k = k; g1.L = g2.L = L; g1.ell = g2.ell = ell; g1.lc = g2.lc = c->T.lc;
       const uint32_t step = (uint32_t)std::max<int64_t>(16, c->imma_chunk_dealers);
       for (uint32_t dc0 = 0; dc0 < D; dc0 += step) {
@@ -741,10 +741,8 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = host ? 2 : 0; g.lc = c->T.lc;
       gemm(c, g);
     }
-    if (host) {
-      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
-      preload(true);
-    }
+    if (host) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+    if (host || imma) preload(true);
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
 }
@@ -775,11 +773,12 @@ int pvw_ct_c1_device_ptr(pvw_ctx* c, uint32_t slot, void** ptr, uint64_t* slot_s
   });
 }
 
-static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps) {
+static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps,
+                             size_t z_cs = 0, const DecodeSub* sub = nullptr) {
   const uint64_t S = (uint64_t)Pc * D;
   c->y.ensure(decode_scratch_words_y(c->T, S) * 8);
   c->X.ensure(decode_scratch_words_X(c->T, S) * 8);
-  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream); });
+  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream, z_cs, sub); });
   launch(c, PVW_KERNEL_CRT_LIFT, 0.0, [&] { launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream); });
   launch(c, PVW_KERNEL_DECODE_TAIL, 0.0, [&] { launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream); });
 }
@@ -855,18 +854,15 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
         // s_hat = SecretKey::get_polynomial (secret_key.rs:98-112) computed once per party, not per ciphertext
         if (imma) {
           launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat_s.as<u64>(), 0, (size_t)Pc * k, c->stream, false, false, true); });
+          // the product is stored alone, slot-major (lanes of a warp = consecutive parties: full-sector stores); c2 is
+          // subtracted by the decode kernel, which reads both with unit stride
           ImmaArgs g{};
           g.M = c->shat_s.as<u64>(); g.M_plane = (size_t)Pc * k; g.rows = Pc;
-          g.O = c->z.as<u64>(); g.O_ls = (size_t)Pc * ell; g.O_ds = (size_t)L * Pc * ell; g.O_rs = ell; g.O_cs = 1;
-          g.S = c->c2s.as<u64>(); g.S_ls = (size_t)nrows * ell; g.S_ds = (size_t)L * nrows * ell; g.S_rowmap = c->idxp.as<uint32_t>() + p0;
-          g.V_dmap = d_slots;
-          g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
-          // O is chunk-local (dealer 0 of the chunk at z), S / the dealer map are global: shift them, not O
-          ImmaArgs gc = g;
-          gc.Vx = c->Vx.as<uint8_t>(); gc.Vx_plane = (size_t)Dc * IMMA_DIAGS * k * 8; gc.D = Dc;
-          if (gc.V_dmap) gc.V_dmap += dc0; else gc.S += (size_t)dc0 * gc.S_ds;
+          g.O = c->z.as<u64>(); g.O_ls = (size_t)ell * Pc; g.O_ds = (size_t)L * ell * Pc; g.O_rs = 1; g.O_cs = Pc;
+          g.k = k; g.L = L; g.ell = ell; g.mode = 2; g.lc = c->T.lc;
+          g.Vx = c->Vx.as<uint8_t>(); g.Vx_plane = (size_t)Dc * IMMA_DIAGS * k * 8; g.D = Dc;
           bool ok = true;
-          launch(c, PVW_KERNEL_MAC, (double)Dc * Pc * (k + 1.0) * L * ell * 8.0, [&] { ok = launch_imma_gemm(gc, c->stream); });
+          launch(c, PVW_KERNEL_MAC, (double)Dc * Pc * (k + 1.0) * L * ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
           require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
         } else {
           launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream, false, true); });
@@ -878,7 +874,13 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
           g.rows = Pc; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
           gemm(c, g);
         }
-        decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, Dc, d_out + (size_t)p0 * D + dc0, D);
+        if (imma) {
+          DecodeSub sub{c->c2s.as<u64>(), (size_t)nrows * ell, (size_t)L * nrows * ell, c->idxp.as<uint32_t>() + p0, d_slots ? d_slots + dc0 : nullptr};
+          if (!d_slots) sub.S += (size_t)dc0 * sub.S_ds;
+          decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, Dc, d_out + (size_t)p0 * D + dc0, D, Pc, &sub);
+        } else {
+          decode_on_device(c, c->z.as<u64>(), (size_t)Pc * ell, (size_t)L * Pc * ell, Pc, Dc, d_out + (size_t)p0 * D + dc0, D);
+        }
         if (host) {  // this chunk's plaintexts go home while the next chunk computes
           CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
           CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev[3], 0));

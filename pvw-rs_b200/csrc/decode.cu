@@ -24,7 +24,8 @@ namespace pvw {
 template <int ELL>
 __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, uint32_t Pc, uint64_t S,
                                                          u64* __restrict__ y, const LimbConst* __restrict__ lcs,
-                                                         const u64* __restrict__ twi, const u64* __restrict__ twi_sh) {
+                                                         const u64* __restrict__ twi, const u64* __restrict__ twi_sh, size_t z_cs,
+                                                         const DecodeSub sub) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
   const uint32_t limb = blockIdx.y;
   if (threadIdx.x < ELL) {
@@ -37,12 +38,28 @@ __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__
   if (s >= S) return;
   const uint64_t d = s / Pc, p = s % Pc;
   u64 a[ELL];
-  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(z + d * z_ds + (size_t)limb * z_ls + p * ELL);
+  if (z_cs) {  // slot-major: consecutive threads read consecutive words of every slot plane
+    const u64* src = z + d * z_ds + (size_t)limb * z_ls + p;
 #pragma unroll
-  for (int t = 0; t < ELL / 2; t++) {
-    ulonglong2 v = src[t];
-    a[2 * t] = v.x;
-    a[2 * t + 1] = v.y;
+    for (int t = 0; t < ELL; t++) a[t] = src[(size_t)t * z_cs];
+  } else {
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(z + d * z_ds + (size_t)limb * z_ls + p * ELL);
+#pragma unroll
+    for (int t = 0; t < ELL / 2; t++) {
+      ulonglong2 v = src[t];
+      a[2 * t] = v.x;
+      a[2 * t + 1] = v.y;
+    }
+  }
+  if (sub.S) {  // noisy = <s, c1> - c2[party]   (decryption.rs:270-274)
+    const uint32_t sd = sub.dmap ? sub.dmap[d] : (uint32_t)d, srow = sub.rowmap ? sub.rowmap[p] : (uint32_t)p;
+    const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(sub.S + (size_t)sd * sub.S_ds + (size_t)limb * sub.S_ls + (size_t)srow * ELL);
+#pragma unroll
+    for (int t = 0; t < ELL / 2; t++) {
+      const ulonglong2 v = sp[t];
+      a[2 * t] = submod(a[2 * t], v.x, lc.q);
+      a[2 * t + 1] = submod(a[2 * t + 1], v.y, lc.q);
+    }
   }
   ntt_inverse_regs<ELL>(a, s_tw, s_tw_sh, lc.ninv, lc.ninv_sh, lc.q);
   const u64 q = lc.q;
@@ -58,14 +75,16 @@ __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__
   yo[(size_t)ELL * S] = mulmod_shoup(negmod(a[0], q), lc.qhinv, lc.qhinv_sh, q);            // z_0 * (-1), :52
 }
 
-void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st) {
+void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st, size_t z_cs,
+                       const DecodeSub* sub) {
   const uint64_t S = (uint64_t)Pc * D;
   if (S == 0) return;
   dim3 grid((unsigned)((S + 127) / 128), T.L);
+  const DecodeSub sb = sub ? *sub : DecodeSub{nullptr, 0, 0, nullptr, nullptr};
   switch (T.ell) {
-    case 8: decode_rns_kernel<8><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh); break;
-    case 16: decode_rns_kernel<16><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh); break;
-    case 32: decode_rns_kernel<32><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh); break;
+    case 8: decode_rns_kernel<8><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb); break;
+    case 16: decode_rns_kernel<16><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb); break;
+    case 32: decode_rns_kernel<32><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb); break;
   }
 }
 

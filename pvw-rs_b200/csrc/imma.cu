@@ -162,29 +162,46 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
     const uint32_t lg = warp & 3;
     const uint32_t limb = plane / g.ell, c = plane - limb * g.ell;
     const LimbConst lc = g.lc[limb];
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll 1
+    // the addend (mode 0: the pre-loaded O, mode 1: S) does not depend on the product: fetch all 32 of this thread's values
+    // while the MMAs run, so that the epilogue proper never waits for global memory
+    u64 pre[2][DT];
+    size_t o_row[2];
+    bool row_ok[2];
+#pragma unroll
     for (uint32_t t = 0; t < 2; t++) {
       const uint32_t row = row0 + t * 128 + lg * 32 + lane;
-      const bool row_ok = row < g.rows;
-      const size_t o_row = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
-      const uint32_t srow = (g.mode == 1 && row_ok) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
-#pragma unroll 1
+      row_ok[t] = row < g.rows;
+      o_row[t] = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
+      const uint32_t srow = (g.mode == 1 && row_ok[t]) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
+#pragma unroll
+      for (uint32_t dd = 0; dd < DT; dd++) {
+        const uint32_t d = d0 + dd;
+        u64 v = 0;
+        if (row_ok[t] && d < g.D) {
+          if (g.mode == 0) v = g.O[(size_t)d * g.O_ds + o_row[t]];
+          else if (g.mode == 1) {
+            const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
+            v = g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c];
+          }
+        }
+        pre[t][dd] = v;
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (uint32_t t = 0; t < 2; t++) {
+#pragma unroll
       for (uint32_t dd = 0; dd < DT; dd++) {
         uint32_t s[16];
         tc_ld16(tmem_base + ((lg * 32) << 16) + t * ACC_COLS + dd * IMMA_DIAGS, s);
         tc_ld_wait();
         const uint32_t d = d0 + dd;
-        if (row_ok && d < g.D) {
+        if (row_ok[t] && d < g.D) {
           u64 r = recombine(s, lc);
-          u64* o = g.O + (size_t)d * g.O_ds + o_row;
-          if (g.mode == 0) r = addmod(r, *o, lc.q);
-          else if (g.mode == 1) {
-            const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
-            r = submod(r, g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c], lc.q);
-          }
-          *o = g.O_packed ? pack_halves(r) : r;
+          if (g.mode == 0) r = addmod(r, pre[t][dd], lc.q);
+          else if (g.mode == 1) r = submod(r, pre[t][dd], lc.q);
+          g.O[(size_t)d * g.O_ds + o_row[t]] = g.O_packed ? pack_halves(r) : r;
         }
       }
     }

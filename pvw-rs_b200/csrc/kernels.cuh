@@ -79,7 +79,12 @@ size_t mac_gemm_launches(const GemmArgs& a);
 
 // ---- decode.cu ----------------------------------------------------------------------------------------------
 // share s' = d*Pc + p  (d < D, p < Pc).  z[d*z_ds + limb*z_ls + p*ell + c]  ->  y[(limb*(ell+1) + i)*S + s']
-void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st);
+// z_cs == 0: z[d*z_ds + limb*z_ls + p*ell + c]; else the slot-major form z[d*z_ds + limb*z_ls + c*z_cs + p] (tensor-core product).
+// sub (optional): the polynomial to subtract first -- z holds <s, c1> only and sub describes c2 (decryption.rs:270-274):
+//   S[sd*S_ds + limb*S_ls + srow*ell + c], sd = dmap ? dmap[d] : d, srow = rowmap ? rowmap[p] : p
+struct DecodeSub { const u64* S; size_t S_ls, S_ds; const uint32_t* rowmap; const uint32_t* dmap; };
+void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st,
+                       size_t z_cs = 0, const DecodeSub* sub = nullptr);
 // X[(i*NW + w)*S + s'] = CRT lift of y[.][i][s']
 void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st);
 // out[p*out_ps + d] for s' = d*Pc + p

@@ -53,6 +53,8 @@ static LimbConst make_lc(u64 q) {
 int main(int argc, char** argv) {
   const uint32_t rows = argc > 1 ? atoi(argv[1]) : 4096, D = argc > 2 ? atoi(argv[2]) : 256, k = argc > 3 ? atoi(argv[3]) : 256;
   const uint32_t planes = argc > 4 ? atoi(argv[4]) : 8, reps = argc > 5 ? atoi(argv[5]) : 5;
+  const uint32_t ell = argc > 6 ? atoi(argv[6]) : 1;     // > 1: the library's output layout O[d][limb][row][c] (timing only)
+  const int mode = argc > 7 ? atoi(argv[7]) : 2;
   const u64 q = 0x3ffffffffffffdc1ull;
   const LimbConst lc = make_lc(q);
   u64 *M, *V, *O, *Oref;
@@ -82,6 +84,9 @@ int main(int argc, char** argv) {
   a.Vx = Vx; a.Vx_plane = (size_t)D * 15 * k * 8; a.D = D;
   a.O = O; a.O_ds = rows; a.O_ls = (size_t)D * rows; a.O_rs = 1; a.O_cs = 0;
   a.lc = dlc; a.mode = 2;
+  ImmaArgs b = a;                                                        // timing variant
+  if (ell > 1) { b.L = planes / ell; b.ell = ell; b.O_ds = (size_t)b.L * rows * ell; b.O_ls = (size_t)rows * ell; b.O_rs = ell; b.O_cs = 1; }
+  b.mode = mode;
   launch_imma_expand(V, k, (size_t)D * k, 1, D, k, planes, Vx, a.Vx_plane, false, nullptr, 0);
   CK(cudaGetLastError());
   if (!launch_imma_gemm(a, 0)) { printf("launch_imma_gemm: tensor map creation failed\n"); return 1; }
@@ -108,7 +113,7 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e0));
     for (uint32_t i = 0; i < reps; i++) {
       if (pass == 1) launch_imma_expand(V, k, (size_t)D * k, 1, D, k, planes, Vx, a.Vx_plane, false, nullptr, 0);
-      else launch_imma_gemm(a, 0);
+      else launch_imma_gemm(b, 0);
     }
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());

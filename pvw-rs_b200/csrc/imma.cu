@@ -18,6 +18,7 @@
 //   CTA tile 256 rows x 16 dealers (240 MMA columns) x all of K; two M = 128 accumulators (2 x 256 TMEM columns) share every
 //   staged Vx tile; K advances 128 bytes per stage (one swizzle span = 4 MMAs of K = 32); 3 stages of 62 KB.
 //   warp 0: TMA producer, warp 1: TMEM allocation + MMA issue (one lane), warps 2-5: epilogue (one TMEM lane group each).
+//   Persistent: one CTA per SM walks the tile list; the smem ring keeps filling across tile boundaries.
 #include <cuda.h>
 
 #include <algorithm>
@@ -32,6 +33,7 @@ constexpr uint32_t RT = 256, DT = 16, NT = DT * IMMA_DIAGS, KC = 128, NS = 3;
 constexpr uint32_t A_BYTES = RT * KC, B_BYTES = NT * KC, B_SLOT = 32768, STAGE = A_BYTES + B_SLOT;
 constexpr uint32_t THREADS = 192;
 constexpr uint32_t SMEM_BYTES = NS * STAGE + 1024 /* alignment slack */ + 128 /* barriers, TMEM pointer */;
+static_assert(8 * (2 * NS + 2) + 4 <= 128, "barrier block too small");
 constexpr uint32_t TMEM_COLS = 512, ACC_COLS = 256;
 // instruction descriptor (kind::i8): D = s32 (bits 4-5 = 2), A and B unsigned 8-bit (bits 7-9, 10-12 = 0), both K-major
 // (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
@@ -103,19 +105,23 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128-byte swizzle wants 1024-byte aligned tiles
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + NS * STAGE);        // full[NS], empty[NS], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + NS * STAGE);        // full[NS], empty[NS], tmem_full, tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
   const uint32_t bar0 = base + NS * STAGE;
   auto full = [&](uint32_t s) { return bar0 + 8 * s; };
   auto empty = [&](uint32_t s) { return bar0 + 8 * (NS + s); };
-  const uint32_t tmem_full = bar0 + 8 * 2 * NS;
+  const uint32_t tmem_full = bar0 + 8 * 2 * NS, tmem_empty = tmem_full + 8;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t row0 = blockIdx.x * RT, d0 = blockIdx.y * DT, plane = blockIdx.z;
   const uint32_t nkb = (8 * g.k + KC - 1) / KC;
+  // persistent: CTA b takes tiles b, b + gridDim.x, ...; row tiles vary fastest, then dealer tiles, then planes, so the CTAs
+  // running at any moment share one plane's operands in L2.  The smem ring runs on across tiles: the next tile's first
+  // stages arrive while this tile's epilogue drains TMEM.
+  const uint32_t n_rt = (g.rows + RT - 1) / RT, n_dt = (g.D + DT - 1) / DT, total = n_rt * n_dt * g.L * g.ell;
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < NS; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, THREADS - 64);                                 // every epilogue thread arrives
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -131,77 +137,95 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      for (uint32_t kb = 0; kb < nkb; kb++) {
-        const uint32_t s = kb % NS, it = kb / NS;
-        mbar_wait(empty(s), (it & 1) ^ 1);                               // first pass over the ring: passes at once
-        mbar_expect_tx(full(s), A_BYTES + B_BYTES);
-        tma_load_3d(base + s * STAGE, &tmA, (int)(kb * KC), (int)row0, (int)plane, full(s));
-        tma_load_3d(base + s * STAGE + A_BYTES, &tmB, (int)(kb * KC), (int)(d0 * IMMA_DIAGS), (int)plane, full(s));
+      uint32_t kbg = 0;
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
+        for (uint32_t kb = 0; kb < nkb; kb++, kbg++) {
+          const uint32_t s = kbg % NS, it = kbg / NS;
+          mbar_wait(empty(s), (it & 1) ^ 1);                             // first pass over the ring: passes at once
+          mbar_expect_tx(full(s), A_BYTES + B_BYTES);
+          tma_load_3d(base + s * STAGE, &tmA, (int)(kb * KC), (int)(rt * RT), (int)plane, full(s));
+          tma_load_3d(base + s * STAGE + A_BYTES, &tmB, (int)(kb * KC), (int)(dt * DT * IMMA_DIAGS), (int)plane, full(s));
+        }
       }
     }
   } else if (warp == 1) {
-    for (uint32_t kb = 0; kb < nkb; kb++) {
-      const uint32_t s = kb % NS, it = kb / NS;
-      mbar_wait(full(s), it & 1);
+    uint32_t kbg = 0, i = 0;
+    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
+      mbar_wait(tmem_empty, (i & 1) ^ 1);                                // the epilogue has read the previous tile out of TMEM
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = base + s * STAGE, b_addr = a_addr + A_BYTES;
+      for (uint32_t kb = 0; kb < nkb; kb++, kbg++) {
+        const uint32_t s = kbg % NS, it = kbg / NS;
+        mbar_wait(full(s), it & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = base + s * STAGE, b_addr = a_addr + A_BYTES;
 #pragma unroll
-        for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
-          const uint64_t bdesc = umma_desc(b_addr + 32 * k4);
-          tc_mma_i8(tmem_base, umma_desc(a_addr + 32 * k4), bdesc, (kb | k4) != 0);
-          tc_mma_i8(tmem_base + ACC_COLS, umma_desc(a_addr + 128 * KC + 32 * k4), bdesc, (kb | k4) != 0);
+          for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
+            const uint64_t bdesc = umma_desc(b_addr + 32 * k4);
+            tc_mma_i8(tmem_base, umma_desc(a_addr + 32 * k4), bdesc, (kb | k4) != 0);
+            tc_mma_i8(tmem_base + ACC_COLS, umma_desc(a_addr + 128 * KC + 32 * k4), bdesc, (kb | k4) != 0);
+          }
+          tc_commit(empty(s));                                           // arrives when the MMAs above have read the stage
+          if (kb + 1 == nkb) tc_commit(tmem_full);
         }
-        tc_commit(empty(s));                                             // arrives when the MMAs above have read the stage
-        if (kb + 1 == nkb) tc_commit(tmem_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31; thread = one row of each accumulator
     const uint32_t lg = warp & 3;
-    const uint32_t limb = plane / g.ell, c = plane - limb * g.ell;
-    const LimbConst lc = g.lc[limb];
-    // the addend (mode 0: the pre-loaded O, mode 1: S) does not depend on the product: fetch all 32 of this thread's values
-    // while the MMAs run, so that the epilogue proper never waits for global memory
-    u64 pre[2][DT];
-    size_t o_row[2];
-    bool row_ok[2];
+    uint32_t i = 0;
+    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
+      const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
+      const uint32_t row0 = rt * RT, d0 = dt * DT;
+      const uint32_t limb = plane / g.ell, c = plane - limb * g.ell;
+      const LimbConst lc = g.lc[limb];
+      // the addend (mode 0: the pre-loaded O, mode 1: S) does not depend on the product: fetch all 32 of this thread's values
+      // while the MMAs run, so that the epilogue proper never waits for global memory
+      u64 pre[2][DT];
+      size_t o_row[2];
+      bool row_ok[2];
 #pragma unroll
-    for (uint32_t t = 0; t < 2; t++) {
-      const uint32_t row = row0 + t * 128 + lg * 32 + lane;
-      row_ok[t] = row < g.rows;
-      o_row[t] = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
-      const uint32_t srow = (g.mode == 1 && row_ok[t]) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
+      for (uint32_t t = 0; t < 2; t++) {
+        const uint32_t row = row0 + t * 128 + lg * 32 + lane;
+        row_ok[t] = row < g.rows;
+        o_row[t] = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
+        const uint32_t srow = (g.mode == 1 && row_ok[t]) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
 #pragma unroll
-      for (uint32_t dd = 0; dd < DT; dd++) {
-        const uint32_t d = d0 + dd;
-        u64 v = 0;
-        if (row_ok[t] && d < g.D) {
-          if (g.mode == 0) v = g.O[(size_t)d * g.O_ds + o_row[t]];
-          else if (g.mode == 1) {
-            const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
-            v = g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c];
+        for (uint32_t dd = 0; dd < DT; dd++) {
+          const uint32_t d = d0 + dd;
+          u64 v = 0;
+          if (g.mode != 2 && row_ok[t] && d < g.D) {
+            if (g.mode == 0) v = g.O[(size_t)d * g.O_ds + o_row[t]];
+            else {
+              const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
+              v = g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c];
+            }
           }
+          pre[t][dd] = v;
         }
-        pre[t][dd] = v;
       }
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+      mbar_wait(tmem_full, i & 1);
+      tc_fence_after();
 #pragma unroll
-    for (uint32_t t = 0; t < 2; t++) {
+      for (uint32_t t = 0; t < 2; t++) {
 #pragma unroll
-      for (uint32_t dd = 0; dd < DT; dd++) {
-        uint32_t s[16];
-        tc_ld16(tmem_base + ((lg * 32) << 16) + t * ACC_COLS + dd * IMMA_DIAGS, s);
-        tc_ld_wait();
-        const uint32_t d = d0 + dd;
-        if (row_ok[t] && d < g.D) {
-          u64 r = recombine(s, lc);
-          if (g.mode == 0) r = addmod(r, pre[t][dd], lc.q);
-          else if (g.mode == 1) r = submod(r, pre[t][dd], lc.q);
-          g.O[(size_t)d * g.O_ds + o_row[t]] = g.O_packed ? pack_halves(r) : r;
+        for (uint32_t dd = 0; dd < DT; dd++) {
+          uint32_t s[16];
+          tc_ld16(tmem_base + ((lg * 32) << 16) + t * ACC_COLS + dd * IMMA_DIAGS, s);
+          tc_ld_wait();
+          if (t == 1 && dd == DT - 1) {                                  // last read of this tile: hand TMEM back to the MMA warp
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
+          }
+          const uint32_t d = d0 + dd;
+          if (row_ok[t] && d < g.D) {
+            u64 r = recombine(s, lc);
+            if (g.mode == 0) r = addmod(r, pre[t][dd], lc.q);
+            else if (g.mode == 1) r = submod(r, pre[t][dd], lc.q);
+            g.O[(size_t)d * g.O_ds + o_row[t]] = g.O_packed ? pack_halves(r) : r;
+          }
         }
       }
     }
@@ -285,8 +309,12 @@ bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
   static const bool attr = (cudaFuncSetAttribute(imma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), true);
   (void)attr;
   cudaFuncSetAttribute(imma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  // per device
-  dim3 grid((a.rows + RT - 1) / RT, (a.D + DT - 1) / DT, (unsigned)planes);
-  imma_gemm_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t tiles = (uint64_t)((a.rows + RT - 1) / RT) * ((a.D + DT - 1) / DT) * planes;
+  if (tiles >= (1ull << 32)) return false;
+  imma_gemm_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
   return true;
 }
 

@@ -342,44 +342,32 @@ void gemm(pvw_ctx* c, GemmArgs a) {
 bool imma_wanted(const pvw_ctx* c, uint32_t rows, uint32_t D) {
   return c->use_imma && D >= (uint32_t)c->imma_min_dealers && imma_shape_ok(rows, D, c->hp.k);
 }
-const u64* slot_major_A(pvw_ctx* c) {
-  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
+// zero padding of the byte planes when k is not a multiple of 16 (imma_kp): only ever non-empty for toy parameter sets
+void planes_clear(pvw_ctx* c, DevBuf& buf, size_t bytes) {
+  buf.ensure(bytes);
+  if (imma_kp(c->hp.k) != c->hp.k) CUDA_CHECK(cudaMemsetAsync(buf.p, 0, bytes, c->stream));
+}
+const uint8_t* planes_A(pvw_ctx* c) {
+  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, kp = imma_kp(k);
   if (!c->As_valid) {
-    c->As.ensure((size_t)L * ell * k * k * 8);
-    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_slot_major(c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, k, k, L, ell, c->As.as<u64>(), (size_t)k * k, true, c->stream); });
+    planes_clear(c, c->As, (size_t)L * ell * k * 8 * kp);
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_planes_m(c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, k, k, L, ell, c->As.as<uint8_t>(), (size_t)k * 8 * kp, true, c->stream); });
     c->As_valid = true;
   }
-  return c->As.as<u64>();
+  return c->As.as<uint8_t>();
 }
-const u64* slot_major_B(pvw_ctx* c) {
-  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+const uint8_t* planes_B(pvw_ctx* c) {
+  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows, kp = imma_kp(k);
   if (!c->Bs_valid) {
-    c->Bs.ensure((size_t)L * ell * nrows * k * 8);
-    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_slot_major(c->B.as<u64>(), (size_t)nrows * k * ell, (size_t)k * ell, nrows, k, L, ell, c->Bs.as<u64>(), (size_t)nrows * k, true, c->stream); });
+    planes_clear(c, c->Bs, (size_t)L * ell * nrows * 8 * kp);
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_planes_m(c->B.as<u64>(), (size_t)nrows * k * ell, (size_t)k * ell, nrows, k, L, ell, c->Bs.as<uint8_t>(), (size_t)nrows * 8 * kp, true, c->stream); });
     c->Bs_valid = true;
   }
-  return c->Bs.as<u64>();
+  return c->Bs.as<uint8_t>();
 }
-// V[sd*V_ds + limb*V_ls + j*ell + c] for dealers [d0, d0 + Dc) -> c->Vx (one chunk at a time)
-void imma_expand(pvw_ctx* c, const u64* V, size_t V_ds, size_t V_ls, uint32_t d0, uint32_t Dc, bool packed, const uint32_t* dmap) {
-  const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
-  const size_t plane = (size_t)Dc * IMMA_DIAGS * k * 8;
-  c->Vx.ensure((size_t)L * ell * plane);
-  const double bytes = (double)Dc * L * k * ell * 8.0 * (1 + IMMA_DIAGS);
-  launch(c, PVW_KERNEL_EXPAND, bytes, [&] {
-    launch_imma_expand(dmap ? V : V + (size_t)d0 * V_ds, V_ds, V_ls, ell, Dc, k, L, c->Vx.as<uint8_t>(), plane, packed, dmap ? dmap + d0 : nullptr, c->stream);
-  });
-}
-// one GEMM over the expanded chunk in c->Vx; `a` describes the whole product, dealers [d0, d0 + Dc) of it are computed
-void imma_gemm_chunk(pvw_ctx* c, ImmaArgs a, uint32_t d0, uint32_t Dc) {
-  a.Vx = c->Vx.as<uint8_t>();
-  a.Vx_plane = (size_t)Dc * IMMA_DIAGS * a.k * 8;
-  a.O += (size_t)d0 * a.O_ds;
-  if (a.V_dmap) a.V_dmap += d0; else if (a.S) a.S += (size_t)d0 * a.S_ds;
-  a.D = Dc;
-  const double bytes = (double)Dc * a.rows * (a.k + 1.0) * a.L * a.ell * 8.0;
+void imma_launch(pvw_ctx* c, const ImmaArgs& g) {
   bool ok = true;
-  launch(c, PVW_KERNEL_MAC, bytes, [&] { ok = launch_imma_gemm(a, c->stream); });
+  launch(c, PVW_KERNEL_MAC, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
   require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
 }
 
@@ -683,10 +671,16 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       d_e1 = (const long long*)stage_in(c, c->in_small2, e1 + (size_t)c1_lo * k * ell, (size_t)(c1_hi - c1_lo) * k * ell * 8, flags);
     const long long* d_e2 = (const long long*)stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags, c->ev[0]);
     const u64* d_m = (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]);
-    // r_hat[d][limb][j][ell]   (encryption.rs:147-154): operand form for the IMAD kernel, canonical for the tensor-core one
+    // r_hat (encryption.rs:147-154): operand form [d][limb][j][ell] for the IMAD kernel, byte planes for the tensor-core one
     const bool imma = imma_wanted(c, nrows, D);
-    c->rhat.ensure((size_t)D * w1 * 8);
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream, false, !imma); });
+    const uint32_t kp = imma_kp(k);
+    if (imma) {
+      planes_clear(c, c->Vx, (size_t)L * ell * D * 8 * kp);
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->Vx.as<u64>(), kp, (size_t)D * 8 * kp, c->stream, false, false, 2); });
+    } else {
+      c->rhat.ensure((size_t)D * w1 * 8);
+      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream, false, true); });
+    }
     u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
     // c1 <- NTT(e1)   (encryption.rs:161-167); c1 += A r_hat below   (crs.rs:187-199, encryption.rs:171-173)
@@ -699,31 +693,21 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     };
     if (!host && !imma) preload(false);
     if (imma) {
-      // tensor-core product (imma.cu): every chunk of dealers is expanded once and serves both c1 and c2
-      ImmaArgs g1{}, g2{};
-      g1.M = slot_major_A(c); g1.M_plane = (size_t)k * k; g1.rows = k;
-      g1.O = c1; g1.O_ls = (size_t)k * ell; g1.O_ds = w1; g1.O_rs = ell; g1.O_cs = 1; g1.O_packed = 1; g1.mode = 0;
-      g2.M = slot_major_B(c); g2.M_plane = (size_t)nrows * k; g2.rows = nrows;
-      g2.O = c2; g2.O_ls = (size_t)nrows * ell; g2.O_ds = w2; g2.O_rs = ell; g2.O_cs = 1; g2.O_packed = 0; g2.mode = 2;   // the product is stored alone; NTT(e2) + m g_hat is added afterwards with unit-stride accesses
-      g1.k = g2.k = k; g1.L = g2.L = L; g1.ell = g2.ell = ell; g1.lc = g2.lc = c->T.lc;
-      const uint32_t step = (uint32_t)std::max<int64_t>(16, c->imma_chunk_dealers);
-      for (uint32_t dc0 = 0; dc0 < D; dc0 += step) {
-        const uint32_t Dc = std::min(step, D - dc0);
-        imma_expand(c, c->rhat.as<u64>(), w1, (size_t)k * ell, dc0, Dc, false, nullptr);
-        const uint32_t lo = std::max(dc0, c1_lo), hi = std::min(dc0 + Dc, c1_hi);
-        if (hi > lo) {
-          // the c1 slice of this chunk: dealers [lo, hi) are rows [lo - dc0, hi - dc0) of the expanded chunk
-          ImmaArgs g = g1;
-          g.Vx = c->Vx.as<uint8_t>() + (size_t)(lo - dc0) * IMMA_DIAGS * k * 8;
-          g.Vx_plane = (size_t)Dc * IMMA_DIAGS * k * 8;
-          g.O += (size_t)lo * g.O_ds;
-          g.D = hi - lo;
-          bool ok = true;
-          launch(c, PVW_KERNEL_MAC, (double)g.D * k * (k + 1.0) * L * ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
-          require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
-        }
-        imma_gemm_chunk(c, g2, dc0, Dc);
+      // tensor-core product (imma.cu) on the byte planes of A / B (built once) and of r_hat (written by the NTT kernel)
+      ImmaArgs g{};
+      g.Vb = c->Vx.as<uint8_t>(); g.Vb_plane = (size_t)D * 8 * kp; g.Vb_D = D;
+      g.k = k; g.L = L; g.ell = ell; g.lc = c->T.lc;
+      if (c1_hi > c1_lo) {
+        g.Mb = planes_A(c); g.Mb_plane = (size_t)k * 8 * kp; g.rows = k;
+        g.d_first = c1_lo; g.D = c1_hi - c1_lo;
+        g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
+        imma_launch(c, g);
       }
+      // the product is stored alone; NTT(e2) + m g_hat is added afterwards with unit-stride accesses
+      g.Mb = planes_B(c); g.Mb_plane = (size_t)nrows * 8 * kp; g.rows = nrows;
+      g.d_first = 0; g.D = D;
+      g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2; g.O_rs = ell; g.O_cs = 1; g.O_packed = 0; g.mode = 2;
+      imma_launch(c, g);
     } else {
       if (c1_hi > c1_lo) {
         const uint32_t Dc = c1_hi - c1_lo;
@@ -825,8 +809,9 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     // inside; the IMAD kernel takes all dealers at once
     const bool imma = imma_wanted(c, P, D);
     const uint32_t Dstep = imma ? (uint32_t)std::min<int64_t>(D, std::max<int64_t>(16, c->imma_chunk_dealers)) : D;
+    const uint32_t kp = imma_kp(k);
     uint32_t Pc_max = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(P, c->decrypt_chunk_shares / std::max<uint32_t>(Dstep, 1)));
-    (imma ? c->shat_s : c->shat).ensure((size_t)L * Pc_max * k * ell * 8);
+    if (imma) planes_clear(c, c->shat_s, (size_t)L * ell * Pc_max * 8 * kp); else c->shat.ensure((size_t)L * Pc_max * k * ell * 8);
     c->z.ensure((size_t)Dstep * L * Pc_max * ell * 8);
     c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * Dstep) * 8);   // sized for the largest chunk up front: growing a
     c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * Dstep) * 8);   // buffer mid-call would synchronise the device
@@ -845,7 +830,13 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     }
     for (uint32_t dc0 = 0; dc0 < D; dc0 += Dstep) {
       const uint32_t Dc = std::min(Dstep, D - dc0);
-      if (imma) imma_expand(c, c->c1s.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, dc0, Dc, true, d_slots);
+      if (imma) {  // byte planes of this chunk's c1 (the store holds the operand form)
+        planes_clear(c, c->Vx, (size_t)L * ell * Dc * 8 * kp);
+        launch(c, PVW_KERNEL_EXPAND, (double)Dc * L * k * ell * 16.0, [&] {
+          launch_imma_planes_v(d_slots ? c->c1s.as<u64>() : c->c1s.as<u64>() + (size_t)dc0 * L * k * ell, (size_t)L * k * ell, (size_t)k * ell, ell, Dc, k, L,
+                               c->Vx.as<uint8_t>(), (size_t)Dc * 8 * kp, true, d_slots ? d_slots + dc0 : nullptr, c->stream);
+        });
+      }
       uint32_t chunk_no = 0;
       for (uint32_t p0 = 0; p0 < P; chunk_no++) {
         const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
@@ -853,17 +844,15 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
         // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274), with
         // s_hat = SecretKey::get_polynomial (secret_key.rs:98-112) computed once per party, not per ciphertext
         if (imma) {
-          launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat_s.as<u64>(), 0, (size_t)Pc * k, c->stream, false, false, true); });
+          launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, c->stream, false, false, 1); });
           // the product is stored alone, slot-major (lanes of a warp = consecutive parties: full-sector stores); c2 is
           // subtracted by the decode kernel, which reads both with unit stride
           ImmaArgs g{};
-          g.M = c->shat_s.as<u64>(); g.M_plane = (size_t)Pc * k; g.rows = Pc;
+          g.Mb = c->shat_s.as<uint8_t>(); g.Mb_plane = (size_t)Pc * 8 * kp; g.rows = Pc;
+          g.Vb = c->Vx.as<uint8_t>(); g.Vb_plane = (size_t)Dc * 8 * kp; g.Vb_D = Dc; g.d_first = 0; g.D = Dc;
           g.O = c->z.as<u64>(); g.O_ls = (size_t)ell * Pc; g.O_ds = (size_t)L * ell * Pc; g.O_rs = 1; g.O_cs = Pc;
           g.k = k; g.L = L; g.ell = ell; g.mode = 2; g.lc = c->T.lc;
-          g.Vx = c->Vx.as<uint8_t>(); g.Vx_plane = (size_t)Dc * IMMA_DIAGS * k * 8; g.D = Dc;
-          bool ok = true;
-          launch(c, PVW_KERNEL_MAC, (double)Dc * Pc * (k + 1.0) * L * ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
-          require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
+          imma_launch(c, g);
         } else {
           launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream, false, true); });
           GemmArgs g{};

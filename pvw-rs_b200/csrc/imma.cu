@@ -4,24 +4,27 @@
 //
 // Batched over dealers the product is a GEMM per plane and, on the CUDA cores, bound by the integer pipe (mac.cu: three
 // IMAD.WIDE per 62-bit multiply-accumulate, 2.8e12 MAC/s ceiling).  Exact integer GEMMs are what the INT8 tensor cores do:
-// a 64-bit operand IS its 8 little-endian bytes, so
-//     M * V = sum_{u=0..14} 2^(8u) * sum_{s+t=u} m_s * v_t .
-// The M row is used as it lies in memory (K axis = its 8k bytes); V is expanded once per batch into 15 "diagonal" rows
-//     Vx[(d,u)][8j + s] = v_{u-s}(d, j)       (0 outside 0..7)
-// and ONE u8 x u8 -> s32 GEMM  C[row][(d,u)] = sum_{(j,s)} M''[row][(j,s)] * Vx[(d,u)][(j,s)]  delivers the 15 diagonal sums
-// of every output (each < 8 k 255^2 < 2^31 for k <= 4096) in the TMEM lane of its row: the epilogue thread that owns the
-// lane recombines them into one 160-bit integer and reduces it -- no cross-lane traffic, no re-layout of the big operand.
-// 120 int8 multiply-accumulates per 62-bit one (64 would do with both operands in byte planes, at the price of an
-// 8-lane shuffle reduction of multi-word integers in the epilogue).
+// with m_s, v_t the little-endian bytes of the operands,
+//     M * V = sum_{u=0..14} 2^(8u) * S_u ,      S_u = sum_{s+t=u} sum_j m_s(j) v_t(j)   (< 8 k 255^2 < 2^31 for k <= 4096).
+// Both operands are stored as byte planes.  For one tile (128 rows x DT dealers) the B operand is the tile of V's byte
+// planes, rows (t, d) -- 8*DT rows, resident in shared memory for the whole K loop -- and for every byte plane s of M one
+// chain of MMAs  D[:, DT*s .. DT*s + 8*DT) += M_s * B^T  runs on a WINDOW of the accumulator that starts DT*s columns in:
+// row (t, d) of B lands in column DT*(s+t) + d, so the 64 byte products of every output add up, in place, to its 15
+// diagonal sums S_u at columns DT*u + d.  64 int8 multiply-accumulates per 62-bit one, no expanded operand, no zero
+// padding in the GEMM.  The epilogue thread that owns a TMEM lane (= a row) reads the 15 sums of each dealer,
+// recombines them into one 160-bit integer and reduces it: no cross-lane traffic.
+// (First version, kept in git history: V expanded into 15 diagonal rows, M rows used as they lie in memory -- 120 int8
+//  MACs per 62-bit one and 15x the V bytes; 8.4e12 MAC/s, bound by the L2 -> shared-memory traffic of the expanded operand.)
 //
-// Kernel shape (the canonical Blackwell GEMM: TMA -> 128B-swizzled smem ring -> tcgen05.mma -> TMEM -> tcgen05.ld epilogue):
-//   CTA tile 256 rows x 16 dealers (240 MMA columns) x all of K; two M = 128 accumulators (2 x 256 TMEM columns) share every
-//   staged Vx tile; K advances 128 bytes per stage (one swizzle span = 4 MMAs of K = 32); 3 stages of 62 KB.
-//   warp 0: TMA producer, warp 1: TMEM allocation + MMA issue (one lane), warps 2-5: epilogue (one TMEM lane group each).
-//   Persistent: one CTA per SM walks the tile list; the smem ring keeps filling across tile boundaries.
+// Kernel shape: persistent, one CTA per SM, warp specialised --
+//   warp 0: TMA producer (B tile once per output tile, then the (s, K-chunk) tiles of M through a ring of 16 KB stages),
+//   warp 1: TMEM allocation + MMA issue (one lane), warps 2-9: epilogue (two warps per TMEM lane group, half the dealers each).
+// A window that starts DT*s columns in touches DT columns no earlier MMA has written: on the first K step of plane s >= 1 the
+// MMA is issued in two parts, N = 7*DT accumulating and N = DT (the t = 7 rows of B) overwriting, so TMEM never needs clearing.
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "imma.cuh"
 
@@ -29,15 +32,12 @@ namespace pvw {
 
 namespace {
 
-constexpr uint32_t RT = 256, DT = 16, NT = DT * IMMA_DIAGS, KC = 128, NS = 3;
-constexpr uint32_t A_BYTES = RT * KC, B_BYTES = NT * KC, B_SLOT = 32768, STAGE = A_BYTES + B_SLOT;
-constexpr uint32_t THREADS = 192;
-constexpr uint32_t SMEM_BYTES = NS * STAGE + 1024 /* alignment slack */ + 128 /* barriers, TMEM pointer */;
-static_assert(8 * (2 * NS + 2) + 4 <= 128, "barrier block too small");
-constexpr uint32_t TMEM_COLS = 512, ACC_COLS = 256;
-// instruction descriptor (kind::i8): D = s32 (bits 4-5 = 2), A and B unsigned 8-bit (bits 7-9, 10-12 = 0), both K-major
-// (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
-constexpr uint32_t IDESC = (2u << 4) | ((NT >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t RT = 128, KC = 128, A_STAGE = RT * KC;
+constexpr uint32_t EPI_WARPS = 8, THREADS = 64 + 32 * EPI_WARPS;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t SMEM_LIMIT = 227 * 1024;
+constexpr uint32_t MAX_STAGES = 8;
+constexpr uint32_t BAR_BYTES = 256;
 
 #define IMMA_DEV __device__ __forceinline__
 
@@ -46,6 +46,7 @@ IMMA_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.i
 IMMA_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+IMMA_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 IMMA_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok, spins = 0;
   do {
@@ -54,74 +55,81 @@ IMMA_DEV void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!ok && ++spins > (1u << 26)) __trap();  // never hang the device: a lost barrier becomes a launch error
   } while (!ok);
 }
-IMMA_DEV void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+IMMA_DEV void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 IMMA_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 IMMA_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 IMMA_DEV void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, M = 128, N = NT, K = 32
-IMMA_DEV void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, M = 128, N from the instruction descriptor, K = 32
+IMMA_DEV void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
-}
-// 16 consecutive columns of this thread's TMEM lane
-IMMA_DEV void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                 "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr) : "memory");
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 IMMA_DEV void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100)
 IMMA_DEV uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// instruction descriptor (kind::i8): D = s32 (bits 4-5 = 2), A and B unsigned 8-bit (bits 7-9, 10-12 = 0), both K-major
+// (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__host__ __device__ constexpr uint32_t idesc_n(uint32_t n) { return (2u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
 
-// sum_u s[u] * 2^(8u)  mod q   (s[u] < 2^32; the true value is < k * 2^124, so the fifth word stays small)
-IMMA_DEV u64 recombine(const uint32_t (&s)[16], const LimbConst& lc) {
+// W = sum_u s[u] * 2^(8u) as five 32-bit words (s[u] < 2^32; the true value is < k * 2^124, so the fifth word stays small)
+IMMA_DEV void combine160(const uint32_t (&s)[IMMA_DIAGS], uint32_t (&w)[5]) {
   // diagonals u = r mod 4 are word aligned among themselves: X_r = (s[r], s[4+r], s[8+r], s[12+r]) as a 128-bit integer, and the
   // value is X_0 + (X_1 << 8) + (X_2 << 16) + (X_3 << 24)
-  uint32_t w[5];
   u64 acc = 0;
 #pragma unroll
   for (int i = 0; i < 5; i++) {
     const uint32_t c0 = i < 4 ? s[4 * i] : 0u, c1 = i < 4 ? s[4 * i + 1] : 0u, c2 = i < 4 ? s[4 * i + 2] : 0u, c3 = i < 3 ? s[4 * i + 3] : 0u;
-    const uint32_t p1 = i > 0 ? s[4 * i - 3] : 0u, p2 = i > 0 ? s[4 * i - 2] : 0u, p3 = (i > 0 && i < 4) ? s[4 * i - 1] : 0u;   // s[15] is the next dealer's column
+    const uint32_t p1 = i > 0 ? s[4 * i - 3] : 0u, p2 = i > 0 ? s[4 * i - 2] : 0u, p3 = (i > 0 && i < 4) ? s[4 * i - 1] : 0u;
     acc += (u64)c0 + __funnelshift_l(p1, c1, 8) + __funnelshift_l(p2, c2, 16) + __funnelshift_l(p3, c3, 24);
     w[i] = (uint32_t)acc;
     acc >>= 32;
   }
+}
+IMMA_DEV u64 reduce160(const uint32_t (&w)[5], const LimbConst& lc) {
   const u64 lo = ((u64)w[1] << 32) | w[0], hi = ((u64)w[3] << 32) | w[2];
   const u64 h = reduce128(reduce64((u64)w[4], lc), hi, lc);
   return reduce128(h, lo, lc);
 }
+IMMA_DEV void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 
+// DT dealers per tile: 32 (k <= 512: B tile 8*32 rows x k bytes <= 128 KB) or 16 (k <= 1024)
+template <uint32_t DT>
 __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                               const ImmaArgs g) {
+                                                               const ImmaArgs g, const uint32_t nstages, const uint32_t nbuf) {
+  constexpr uint32_t NB = 8 * DT;                 // rows of the B tile = MMA columns per window
+  constexpr uint32_t B_CHUNK = NB * KC;           // one K-chunk of the B tile (multiple of 1024 bytes)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128-byte swizzle wants 1024-byte aligned tiles
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + NS * STAGE);        // full[NS], empty[NS], tmem_full, tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
-  const uint32_t bar0 = base + NS * STAGE;
-  auto full = [&](uint32_t s) { return bar0 + 8 * s; };
-  auto empty = [&](uint32_t s) { return bar0 + 8 * (NS + s); };
-  const uint32_t tmem_full = bar0 + 8 * 2 * NS, tmem_empty = tmem_full + 8;
+  const uint32_t kp = imma_kp(g.k), nkc = (kp + KC - 1) / KC;
+  const uint32_t b_bytes = nkc * B_CHUNK;                               // one B tile (all of K); nbuf of them (1 or 2)
+  const uint32_t b_base = base, a_base = base + nbuf * b_bytes, bar0 = a_base + nstages * A_STAGE;
+  uint8_t* gen = smem_raw + (bar0 - smem_u32(smem_raw));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 8 * (2 * MAX_STAGES + 6));
+  auto a_full = [&](uint32_t s) { return bar0 + 8 * s; };
+  auto a_empty = [&](uint32_t s) { return bar0 + 8 * (MAX_STAGES + s); };
+  auto b_full = [&](uint32_t b) { return bar0 + 8 * (2 * MAX_STAGES + b); };
+  auto b_empty = [&](uint32_t b) { return bar0 + 8 * (2 * MAX_STAGES + 2 + b); };
+  const uint32_t tmem_full = bar0 + 8 * (2 * MAX_STAGES + 4), tmem_empty = tmem_full + 8;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t nkb = (8 * g.k + KC - 1) / KC;
   // persistent: CTA b takes tiles b, b + gridDim.x, ...; row tiles vary fastest, then dealer tiles, then planes, so the CTAs
-  // running at any moment share one plane's operands in L2.  The smem ring runs on across tiles: the next tile's first
-  // stages arrive while this tile's epilogue drains TMEM.
+  // running at any moment share one plane's operands in L2
   const uint32_t n_rt = (g.rows + RT - 1) / RT, n_dt = (g.D + DT - 1) / DT, total = n_rt * n_dt * g.L * g.ell;
 
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < NS; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (uint32_t s = 0; s < nstages; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (uint32_t b = 0; b < 2; b++) { mbar_init(b_full(b), 1); mbar_init(b_empty(b), 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, THREADS - 64);                                 // every epilogue thread arrives
+    mbar_init(tmem_empty, 32 * EPI_WARPS);                               // every epilogue thread arrives
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -137,95 +145,105 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t kbg = 0;
-      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      uint32_t stg = 0, i = 0;
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
         const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
-        for (uint32_t kb = 0; kb < nkb; kb++, kbg++) {
-          const uint32_t s = kbg % NS, it = kbg / NS;
-          mbar_wait(empty(s), (it & 1) ^ 1);                             // first pass over the ring: passes at once
-          mbar_expect_tx(full(s), A_BYTES + B_BYTES);
-          tma_load_3d(base + s * STAGE, &tmA, (int)(kb * KC), (int)(rt * RT), (int)plane, full(s));
-          tma_load_3d(base + s * STAGE + A_BYTES, &tmB, (int)(kb * KC), (int)(dt * DT * IMMA_DIAGS), (int)plane, full(s));
-        }
+        const uint32_t bb = i % nbuf, bit = i / nbuf;
+        mbar_wait(b_empty(bb), (bit & 1) ^ 1);                           // the MMAs of the tile that used this B buffer are done
+        mbar_expect_tx(b_full(bb), b_bytes);
+        for (uint32_t kc = 0; kc < nkc; kc++)
+          tma_load_4d(b_base + bb * b_bytes + kc * B_CHUNK, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
+        for (uint32_t s = 0; s < 8; s++)
+          for (uint32_t kc = 0; kc < nkc; kc++, stg++) {
+            const uint32_t st = stg % nstages, it = stg / nstages;
+            mbar_wait(a_empty(st), (it & 1) ^ 1);                        // first pass over the ring: passes at once
+            mbar_expect_tx(a_full(st), A_STAGE);
+            tma_load_4d(a_base + st * A_STAGE, &tmA, (int)(kc * KC), (int)s, (int)(rt * RT), (int)plane, a_full(st));
+          }
       }
     }
   } else if (warp == 1) {
-    uint32_t kbg = 0, i = 0;
+    uint32_t stg = 0, i = 0;
     for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
+      const uint32_t bb = i % nbuf, bit = i / nbuf;
       mbar_wait(tmem_empty, (i & 1) ^ 1);                                // the epilogue has read the previous tile out of TMEM
+      mbar_wait(b_full(bb), bit & 1);
       tc_fence_after();
-      for (uint32_t kb = 0; kb < nkb; kb++, kbg++) {
-        const uint32_t s = kbg % NS, it = kbg / NS;
-        mbar_wait(full(s), it & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = base + s * STAGE, b_addr = a_addr + A_BYTES;
+      for (uint32_t s = 0; s < 8; s++)
+        for (uint32_t kc = 0; kc < nkc; kc++, stg++) {
+          const uint32_t st = stg % nstages, it = stg / nstages;
+          mbar_wait(a_full(st), it & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * b_bytes + kc * B_CHUNK, d_addr = tmem_base + DT * s;
 #pragma unroll
-          for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
-            const uint64_t bdesc = umma_desc(b_addr + 32 * k4);
-            tc_mma_i8(tmem_base, umma_desc(a_addr + 32 * k4), bdesc, (kb | k4) != 0);
-            tc_mma_i8(tmem_base + ACC_COLS, umma_desc(a_addr + 128 * KC + 32 * k4), bdesc, (kb | k4) != 0);
+            for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
+              const uint64_t adesc = umma_desc(a_addr + 32 * k4);
+              if (kc | k4) tc_mma_i8(d_addr, adesc, umma_desc(b_addr + 32 * k4), idesc_n(NB), 1);
+              else if (s == 0) tc_mma_i8(d_addr, adesc, umma_desc(b_addr), idesc_n(NB), 0);
+              else {  // columns DT*(s+7) .. +DT are new to this window: their first product overwrites
+                tc_mma_i8(d_addr, adesc, umma_desc(b_addr), idesc_n(7 * DT), 1);
+                tc_mma_i8(d_addr + 7 * DT, adesc, umma_desc(b_addr + 7 * DT * KC), idesc_n(DT), 0);
+              }
+            }
+            tc_commit(a_empty(st));                                      // arrives when the MMAs above have read the stage
           }
-          tc_commit(empty(s));                                           // arrives when the MMAs above have read the stage
-          if (kb + 1 == nkb) tc_commit(tmem_full);
+          __syncwarp();
         }
-        __syncwarp();
-      }
+      if (lane == 0) { tc_commit(b_empty(bb)); tc_commit(tmem_full); }
+      __syncwarp();
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31; thread = one row of each accumulator
-    const uint32_t lg = warp & 3;
+    // epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31; thread = one row; the two warps of a lane group split the dealers
+    const uint32_t lg = warp & 3, half = (warp - 2) >> 2;
     uint32_t i = 0;
     for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
       const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
-      const uint32_t row0 = rt * RT, d0 = dt * DT;
+      const uint32_t row = rt * RT + lg * 32 + lane, d0 = dt * DT;
       const uint32_t limb = plane / g.ell, c = plane - limb * g.ell;
       const LimbConst lc = g.lc[limb];
-      // the addend (mode 0: the pre-loaded O, mode 1: S) does not depend on the product: fetch all 32 of this thread's values
-      // while the MMAs run, so that the epilogue proper never waits for global memory
-      u64 pre[2][DT];
-      size_t o_row[2];
-      bool row_ok[2];
-#pragma unroll
-      for (uint32_t t = 0; t < 2; t++) {
-        const uint32_t row = row0 + t * 128 + lg * 32 + lane;
-        row_ok[t] = row < g.rows;
-        o_row[t] = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
-        const uint32_t srow = (g.mode == 1 && row_ok[t]) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
-#pragma unroll
-        for (uint32_t dd = 0; dd < DT; dd++) {
-          const uint32_t d = d0 + dd;
-          u64 v = 0;
-          if (g.mode != 2 && row_ok[t] && d < g.D) {
-            if (g.mode == 0) v = g.O[(size_t)d * g.O_ds + o_row[t]];
-            else {
-              const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
-              v = g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c];
-            }
-          }
-          pre[t][dd] = v;
-        }
-      }
+      const bool row_ok = row < g.rows;
+      const size_t o_row = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
+      const uint32_t srow = (g.mode == 1 && row_ok) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
       mbar_wait(tmem_full, i & 1);
       tc_fence_after();
+      if (g.mode == 3) {                                                 // timing probe: MMA / load pipeline without an epilogue
+        tc_fence_before();
+        mbar_arrive(tmem_empty);
+        continue;
+      }
+      // phase 1 (TMEM is busy): this thread's DT/2 dealers, four at a time -- 15 diagonal sums each -> one 160-bit integer
+      constexpr uint32_t ND = DT / 2;
+      uint32_t W[ND][5];
 #pragma unroll
-      for (uint32_t t = 0; t < 2; t++) {
+      for (uint32_t q4 = 0; q4 < ND / 4; q4++) {
+        uint32_t v[IMMA_DIAGS][4];
 #pragma unroll
-        for (uint32_t dd = 0; dd < DT; dd++) {
-          uint32_t s[16];
-          tc_ld16(tmem_base + ((lg * 32) << 16) + t * ACC_COLS + dd * IMMA_DIAGS, s);
-          tc_ld_wait();
-          if (t == 1 && dd == DT - 1) {                                  // last read of this tile: hand TMEM back to the MMA warp
-            tc_fence_before();
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty) : "memory");
+        for (uint32_t u = 0; u < IMMA_DIAGS; u++) tc_ld4(tmem_base + ((lg * 32) << 16) + DT * u + half * ND + q4 * 4, v[u]);
+        tc_ld_wait();
+#pragma unroll
+        for (uint32_t dd = 0; dd < 4; dd++) {
+          uint32_t s[IMMA_DIAGS];
+#pragma unroll
+          for (uint32_t u = 0; u < IMMA_DIAGS; u++) s[u] = v[u][dd];
+          combine160(s, W[q4 * 4 + dd]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty);                                           // TMEM goes back to the MMA warp: the next tile starts
+      // phase 2 (overlaps the next tile's MMAs): reduce and store
+#pragma unroll
+      for (uint32_t dd = 0; dd < ND; dd++) {
+        const uint32_t d = d0 + half * ND + dd;
+        if (row_ok && d < g.D) {
+          u64 r = reduce160(W[dd], lc);
+          u64* o = g.O + (size_t)d * g.O_ds + o_row;
+          if (g.mode == 0) r = addmod(r, *o, lc.q);
+          else if (g.mode == 1) {
+            const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
+            r = submod(r, g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c], lc.q);
           }
-          const uint32_t d = d0 + dd;
-          if (row_ok[t] && d < g.D) {
-            u64 r = recombine(s, lc);
-            if (g.mode == 0) r = addmod(r, pre[t][dd], lc.q);
-            else if (g.mode == 1) r = submod(r, pre[t][dd], lc.q);
-            g.O[(size_t)d * g.O_ds + o_row[t]] = g.O_packed ? pack_halves(r) : r;
-          }
+          *o = g.O_packed ? pack_halves(r) : r;
         }
       }
     }
@@ -238,33 +256,32 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
   }
 }
 
-// Vx rows of one (dealer, limb): thread = (j, c) with c fastest (the read is one contiguous run)
-__global__ void __launch_bounds__(256) imma_expand_kernel(const u64* __restrict__ V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t k,
-                                                          uint8_t* __restrict__ Vx, size_t Vx_plane, int packed, const uint32_t* __restrict__ dmap) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y, limb = blockIdx.z;
-  if (e >= k * ell) return;
-  const uint32_t j = e / ell, c = e - j * ell;
-  const uint32_t sd = dmap ? dmap[d] : d;
-  u64 v = V[(size_t)sd * V_ds + (size_t)limb * V_ls + e];
-  if (packed) v = unpack_halves(v);
-  // R = v with its bytes reversed: row u of the expansion is R >> 8(7-u) for u <= 7 and R << 8(u-7) above
-  const u64 R = ((u64)__byte_perm((uint32_t)v, 0, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0, 0x0123);
-  u64* out = reinterpret_cast<u64*>(Vx + (size_t)(limb * ell + c) * Vx_plane) + (size_t)d * IMMA_DIAGS * k + j;
-#pragma unroll
-  for (uint32_t u = 0; u < IMMA_DIAGS; u++) out[(size_t)u * k] = u <= 7 ? R >> (8 * (7 - u)) : R << (8 * (u - 7));
-}
-
-// one CTA per (row, limb): thread = output element (c, j), j fastest
-__global__ void __launch_bounds__(256) imma_slot_major_kernel(const u64* __restrict__ M, size_t M_ls, size_t M_rs, uint32_t k, uint32_t ell,
-                                                              u64* __restrict__ out, size_t out_plane, int packed) {
-  const uint32_t row = blockIdx.x, limb = blockIdx.y;
+// one CTA per (row, limb): thread = (c, j) with j fastest -> the byte stores of a warp fill one sector of one plane
+__global__ void __launch_bounds__(256) imma_planes_m_kernel(const u64* __restrict__ M, size_t M_ls, size_t M_rs, uint32_t k, uint32_t ell,
+                                                            uint8_t* __restrict__ Mb, size_t Mb_plane, int packed) {
+  const uint32_t row = blockIdx.x, limb = blockIdx.y, kp = imma_kp(k);
   const u64* src = M + (size_t)limb * M_ls + (size_t)row * M_rs;
   for (uint32_t t = threadIdx.x; t < k * ell; t += blockDim.x) {
     const uint32_t c = t / k, j = t - c * k;
     u64 v = src[(size_t)j * ell + c];
     if (packed) v = unpack_halves(v);
-    out[(size_t)(limb * ell + c) * out_plane + (size_t)row * k + j] = v;
+    uint8_t* out = Mb + (size_t)(limb * ell + c) * Mb_plane + (size_t)row * 8 * kp + j;
+#pragma unroll
+    for (uint32_t s = 0; s < 8; s++) out[(size_t)s * kp] = (uint8_t)(v >> (8 * s));
   }
+}
+// grid (., D, L): thread = (c, j) of one dealer and limb, j fastest
+__global__ void __launch_bounds__(256) imma_planes_v_kernel(const u64* __restrict__ V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t k,
+                                                            uint8_t* __restrict__ Vb, size_t Vb_plane, int packed, const uint32_t* __restrict__ dmap) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y, limb = blockIdx.z, D = gridDim.y, kp = imma_kp(k);
+  if (e >= k * ell) return;
+  const uint32_t c = e / k, j = e - c * k;
+  const uint32_t sd = dmap ? dmap[d] : d;
+  u64 v = V[(size_t)sd * V_ds + (size_t)limb * V_ls + (size_t)j * ell + c];
+  if (packed) v = unpack_halves(v);
+  uint8_t* out = Vb + (size_t)(limb * ell + c) * Vb_plane + (size_t)d * kp + j;
+#pragma unroll
+  for (uint32_t t = 0; t < 8; t++) out[(size_t)t * D * kp] = (uint8_t)(v >> (8 * t));
 }
 
 typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -281,54 +298,65 @@ encode_fn tensor_map_encoder() {
   }
   return encode;
 }
-// u8 tensor [planes][nrows][kbytes], box = 128 bytes x box_rows x 1, 128-byte swizzle, out-of-range elements read as zero
-bool make_map(CUtensorMap* tm, const void* base, uint64_t kbytes, uint64_t nrows, uint64_t planes, uint64_t plane_stride_bytes, uint32_t box_rows) {
+// 4D u8 tensor, innermost dimension contiguous, 128-byte swizzle, out-of-range elements read as zero
+bool make_map(CUtensorMap* tm, const void* base, const cuuint64_t (&dims)[4], const cuuint64_t (&strides)[3], const cuuint32_t (&box)[4]) {
   encode_fn encode = tensor_map_encoder();
-  if (!encode || ((uintptr_t)base & 15) || (kbytes & 15) || (plane_stride_bytes & 15)) return false;
-  const cuuint64_t dims[3] = {kbytes, nrows, planes};
-  const cuuint64_t strides[2] = {kbytes, plane_stride_bytes};
-  const cuuint32_t box[3] = {KC, box_rows, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (!encode || ((uintptr_t)base & 15)) return false;
+  for (cuuint64_t s : strides) if (s & 15) return false;
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  static const int promo = getenv("PVW_IMMA_L2PROMO") ? atoi(getenv("PVW_IMMA_L2PROMO")) : 3;   // experiment knob: 0 none, 1 64B, 2 128B, 3 256B
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace
-
-bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
-  // 8 * k * 255^2 must fit the signed 32-bit accumulator; global strides must be multiples of 16 bytes
-  return rows > 0 && D > 0 && k >= 2 && k % 2 == 0 && k <= 4096;
-}
-
-bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
-  if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
+template <uint32_t DT>
+bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
+  const uint32_t kp = imma_kp(a.k), nkc = (kp + KC - 1) / KC;
+  const uint64_t planes = (uint64_t)a.L * a.ell;
   CUtensorMap tmA, tmB;
-  const uint64_t kbytes = 8ull * a.k, planes = (uint64_t)a.L * a.ell;
-  if (!make_map(&tmA, a.M, kbytes, a.rows, planes, a.M_plane * 8, RT)) return false;
-  if (!make_map(&tmB, a.Vx, kbytes, (uint64_t)a.D * IMMA_DIAGS, planes, a.Vx_plane, NT)) return false;
-  static const bool attr = (cudaFuncSetAttribute(imma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), true);
-  (void)attr;
-  cudaFuncSetAttribute(imma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  // per device
+  // M byte planes: [plane][row][s][kp]; box = 128 bytes of one plane s of 128 rows
+  if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
+  // V byte planes: [plane][t][d][kp]; box = 128 bytes of DT dealers of all 8 planes t -> rows (t, d) of the B tile
+  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
+  const uint32_t b_bytes = nkc * 8 * DT * KC;
+  if (b_bytes + 2 * A_STAGE + 1024 + BAR_BYTES > SMEM_LIMIT) return false;
+  // two B buffers (the next tile's B arrives during this tile's MMAs) when at least four ring stages still fit
+  const uint32_t nbuf = (2 * b_bytes + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 2 : 1;
+  const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - nbuf * b_bytes) / A_STAGE);
+  const uint32_t smem = nbuf * b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
+  auto kern = imma_gemm_kernel<DT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);  // per device
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint64_t tiles = (uint64_t)((a.rows + RT - 1) / RT) * ((a.D + DT - 1) / DT) * planes;
   if (tiles >= (1ull << 32)) return false;
-  imma_gemm_kernel<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  kern<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, smem, st>>>(tmA, tmB, a, nstages, nbuf);
   return true;
 }
 
-void launch_imma_expand(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vx, size_t Vx_plane,
-                        bool packed, const uint32_t* dmap, cudaStream_t st) {
-  if (D == 0) return;
-  dim3 grid((k * ell + 255) / 256, D, L);
-  imma_expand_kernel<<<grid, 256, 0, st>>>(V, V_ds, V_ls, ell, k, Vx, Vx_plane, packed ? 1 : 0, dmap);
+}  // namespace
+
+bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
+  // the B tile (8 * DT rows x kp bytes) must leave room for the M ring; 8 * k * 255^2 fits the signed 32-bit accumulator
+  return rows > 0 && D > 0 && k >= 1 && k <= 1024;
 }
 
-void launch_imma_slot_major(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, u64* out,
-                            size_t out_plane, bool packed, cudaStream_t st) {
+bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
+  if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
+  return imma_kp(a.k) <= 512 ? launch_dt<32>(a, st) : launch_dt<16>(a, st);
+}
+
+void launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb,
+                          size_t Mb_plane, bool packed, cudaStream_t st) {
   if (rows == 0) return;
-  imma_slot_major_kernel<<<dim3(rows, L), 256, 0, st>>>(M, M_ls, M_rs, k, ell, out, out_plane, packed ? 1 : 0);
+  imma_planes_m_kernel<<<dim3(rows, L), 256, 0, st>>>(M, M_ls, M_rs, k, ell, Mb, Mb_plane, packed ? 1 : 0);
+}
+
+void launch_imma_planes_v(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vb, size_t Vb_plane,
+                          bool packed, const uint32_t* dmap, cudaStream_t st) {
+  if (D == 0 || D > 65535) return;   // grid.y carries the dealer count (callers chunk dealers far below the limit)
+  imma_planes_v_kernel<<<dim3((k * ell + 255) / 256, D, L), 256, 0, st>>>(V, V_ds, V_ls, ell, k, Vb, Vb_plane, packed ? 1 : 0, dmap);
 }
 
 }  // namespace pvw

@@ -11,7 +11,7 @@
 namespace pvw {
 
 template <int ELL, int MODE>  // MODE 0: store canonical, 1: accumulate into canonical, 2: store packed halves (operand form),
-                               // 3: store canonical in the slot-major form of the tensor-core path: out[(limb*ELL + c)*lstride + idx]
+                               // 3 / 4: store the byte planes the tensor-core path reads (imma.cuh), M side / dealer side
 __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
@@ -43,9 +43,19 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 #pragma unroll
     for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], mulmod_shoup(mr, s_g[t], s_g_sh[t], lc.q), lc.q);
   }
-  if (MODE == 3) {
+  if (MODE == 3 || MODE == 4) {
+    // idx = r*inner + j (inner = k): r is a matrix row (MODE 3) or a dealer (MODE 4); vstride = kp, lstride = plane stride in bytes.
+    // Consecutive threads hold consecutive j: every byte store of a warp fills one sector of one plane.
+    const uint64_t r = idx / inner, j = idx % inner, kp = vstride;
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (size_t)limb * ELL * lstride;
+    const size_t first = MODE == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;        // byte plane 0
+    const size_t step = MODE == 3 ? kp : (size_t)(count / inner) * kp;                  // to the next byte plane
 #pragma unroll
-    for (int t = 0; t < ELL; t++) out[((size_t)limb * ELL + t) * lstride + idx] = a[t];   // consecutive threads: consecutive words
+    for (int t = 0; t < ELL; t++) {
+      uint8_t* o = o8 + (size_t)t * lstride + first;
+#pragma unroll
+      for (int b = 0; b < 8; b++) o[(size_t)b * step] = (uint8_t)(a[t] >> (8 * b));
+    }
     return;
   }
   uint64_t vec = idx / inner, j = idx % inner;
@@ -64,13 +74,15 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 }
 
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, bool slot_major) {
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes) {
   if (count == 0) return;
   dim3 grid((unsigned)((count + 127) / 128), T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
-    if (slot_major)                                                                                                           \
+    if (planes == 1)                                                                                                          \
       ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+    else if (planes == 2)                                                                                                     \
+      ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
     else if (accumulate)                                                                                                           \
       ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
     else if (pack_out)                                                                                                        \

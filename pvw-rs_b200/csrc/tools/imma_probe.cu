@@ -1,10 +1,8 @@
 // imma_probe.cu -- bring-up / measurement of the INT8 tensor-core form of the modular matrix product (tcgen05.mma kind::i8).
 //
 //   O[row][d] = sum_j M[row][j] * V[d][j]  (mod q),   M, V < 2^62
-// A 64-bit operand is its 8 little-endian bytes, so  M*V = sum_u 2^(8u) sum_{s+t=u} m_s v_t.  With the M row kept as it is
-// in memory (K'' = 8k bytes) and V expanded into 15 "diagonal" rows  Vx[(d,u)][(j,s)] = v_{u-s}(d,j)  (zero outside 0..7),
-// one u8 x u8 -> s32 GEMM  C[row][(d,u)] = sum_{(j,s)} M''[row][(j,s)] Vx[(d,u)][(j,s)]  yields the 15 diagonal sums of every
-// output in the TMEM lane of its row: the epilogue recombines them thread-locally into a 160-bit integer and reduces.
+// A 64-bit operand is its 8 little-endian bytes, so  M*V = sum_u 2^(8u) sum_{s+t=u} m_s v_t: byte-plane GEMMs accumulated on
+// overlapping windows of the TMEM accumulator (imma.cu); the epilogue recombines the 15 diagonal sums of every output.
 //
 // usage: imma_probe [rows] [D] [k] [planes] [reps]      (rows % 256 == 0, D % 16 == 0, k % 16 == 0)
 #include <cuda.h>
@@ -58,11 +56,15 @@ int main(int argc, char** argv) {
   const u64 q = 0x3ffffffffffffdc1ull;
   const LimbConst lc = make_lc(q);
   u64 *M, *V, *O, *Oref;
-  uint8_t* Vx;
+  uint8_t *Vb, *Mb;
   LimbConst* dlc;
   CK(cudaMalloc(&M, (size_t)planes * rows * k * 8));
   CK(cudaMalloc(&V, (size_t)planes * D * k * 8));
-  CK(cudaMalloc(&Vx, (size_t)planes * D * 15 * k * 8));
+  const uint32_t kp = imma_kp(k);
+  CK(cudaMalloc(&Vb, (size_t)planes * D * 8 * kp));
+  CK(cudaMalloc(&Mb, (size_t)planes * rows * 8 * kp));
+  CK(cudaMemset(Vb, 0, (size_t)planes * D * 8 * kp));
+  CK(cudaMemset(Mb, 0, (size_t)planes * rows * 8 * kp));
   CK(cudaMalloc(&O, (size_t)planes * D * rows * 8));
   CK(cudaMalloc(&Oref, (size_t)planes * D * rows * 8));
   CK(cudaMalloc(&dlc, planes * sizeof(LimbConst)));
@@ -80,14 +82,15 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(V, ones.data(), k * 8, cudaMemcpyHostToDevice));
   }
   ImmaArgs a{};
-  a.M = M; a.M_plane = (size_t)rows * k; a.rows = rows; a.k = k; a.L = planes; a.ell = 1;   // plane = limb (ell = 1 view)
-  a.Vx = Vx; a.Vx_plane = (size_t)D * 15 * k * 8; a.D = D;
+  a.Mb = Mb; a.Mb_plane = (size_t)rows * 8 * kp; a.rows = rows; a.k = k; a.L = planes; a.ell = 1;   // plane = limb (ell = 1 view)
+  a.Vb = Vb; a.Vb_plane = (size_t)D * 8 * kp; a.Vb_D = D; a.d_first = 0; a.D = D;
   a.O = O; a.O_ds = rows; a.O_ls = (size_t)D * rows; a.O_rs = 1; a.O_cs = 0;
   a.lc = dlc; a.mode = 2;
   ImmaArgs b = a;                                                        // timing variant
   if (ell > 1) { b.L = planes / ell; b.ell = ell; b.O_ds = (size_t)b.L * rows * ell; b.O_ls = (size_t)rows * ell; b.O_rs = ell; b.O_cs = 1; }
   b.mode = mode;
-  launch_imma_expand(V, k, (size_t)D * k, 1, D, k, planes, Vx, a.Vx_plane, false, nullptr, 0);
+  launch_imma_planes_v(V, k, (size_t)D * k, 1, D, k, planes, Vb, a.Vb_plane, false, nullptr, 0);
+  launch_imma_planes_m(M, (size_t)rows * k, k, rows, k, planes, 1, Mb, a.Mb_plane, false, 0);
   CK(cudaGetLastError());
   if (!launch_imma_gemm(a, 0)) { printf("launch_imma_gemm: tensor map creation failed\n"); return 1; }
   CK(cudaDeviceSynchronize());
@@ -112,7 +115,7 @@ int main(int argc, char** argv) {
   for (int pass = 0; pass < 2; pass++) {
     CK(cudaEventRecord(e0));
     for (uint32_t i = 0; i < reps; i++) {
-      if (pass == 1) launch_imma_expand(V, k, (size_t)D * k, 1, D, k, planes, Vx, a.Vx_plane, false, nullptr, 0);
+      if (pass == 1) launch_imma_planes_v(V, k, (size_t)D * k, 1, D, k, planes, Vb, a.Vb_plane, false, nullptr, 0);
       else launch_imma_gemm(b, 0);
     }
     CK(cudaEventRecord(e1));
@@ -120,8 +123,8 @@ int main(int argc, char** argv) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double macs = (double)rows * D * k * planes * reps;
-    if (pass == 0) printf("imma_gemm: %.3f ms per launch, %.3e 62-bit MAC/s, %.1f int8 TOPS (dense, incl. zero diagonals)\n", ms / reps, macs / (ms * 1e-3), macs * 120 * 2 / (ms * 1e-3) / 1e12);
-    else printf("imma_expand: %.3f ms per launch (%.1f GB/s written)\n", ms / reps, (double)planes * D * 15 * k * 8 * reps / (ms * 1e-3) / 1e9);
+    if (pass == 0) printf("imma_gemm: %.3f ms per launch, %.3e 62-bit MAC/s, %.1f int8 TOPS\n", ms / reps, macs / (ms * 1e-3), macs * 64 * 2 / (ms * 1e-3) / 1e12);
+    else printf("imma_planes_v: %.3f ms per launch (%.1f GB/s written)\n", ms / reps, (double)planes * D * 8 * kp * reps / (ms * 1e-3) / 1e9);
   }
   return bad ? 2 : 0;
 }

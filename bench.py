@@ -373,26 +373,45 @@ def run_b200(args):
     log2l = l.bit_length() - 1
     ntt_mulmods = polys * L * ((l // 2) * log2l) + args.steps * D * nrows * L * l        # butterflies + m * g_hat
     ntt_rate = ntt_mulmods / (ntt_ms * 1e-3) if ntt_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "mac_gemm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback", "traffic": traffic,
+    # The batched product runs on the INT8 tensor cores (csrc/imma.cu): 64 u8 x u8 multiply-accumulates per 62-bit one, so the
+    # kernel's roof is the tensor pipe.  Peak: kind::i8 issues K = 32 per instruction where bf16 issues K = 16 at the same
+    # cadence, i.e. twice the dense bf16 rate; MEASURED_PEAKS.json holds the measured cuBLAS bf16 figure (sustained one: the
+    # kernel is timed inside a long step), else the nominal 2 x 2250 TFLOP/s.
+    imma_on = os.environ.get("PVW_OPTS", "").replace(" ", "").find("imma=0") < 0
+    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
+    int8_peak = 2.0 * bf16
+    int8_ops = mac_rate * 64 * 2 / 1e12
+    hbm_view = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "what": "SURVEY 8d algorithmic bytes (one operand row read per (dealer, row) + one polynomial written) over the kernel "
+                        "time: > 1 because dealers are batched -- every staged tile serves 32 dealers from shared memory"}
+    if imma_on:
+        roofline = {"bound": "tensor", "kernel": "mac_gemm (imma_gemm_kernel: tcgen05.mma kind::i8)", "achieved": int8_ops, "peak": int8_peak,
+                    "unit": "TOP/s (u8 x u8 -> s32, dense)", "frac": int8_ops / int8_peak,
+                    "peak_source": ("2 x measured cuBLAS bf16 (MEASURED_PEAKS.json, sustained)" if peaks else "2 x nominal dense bf16 (fallback)"),
+                    "traffic": traffic, "ops_per_launch": mac_rate * 128 * (mac_ms * 1e-3) / max(mac_n, 1),
+                    "int8_macs_per_62bit_mac": 64}
+    else:
+        roofline = {"bound": "hbm", "kernel": "mac_gemm (IMAD kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback", "traffic": traffic}
+    roofline.update({
                 "launches_per_step": mac_n / args.steps, "avg_launch_ms": mac_ms / max(mac_n, 1),
-                "algorithmic_bytes_per_launch": mac_bytes / max(mac_n, 1),
+                "algorithmic_bytes_per_launch": mac_bytes / max(mac_n, 1), "hbm_algorithmic": hbm_view,
                 "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": round(mac_ms / ms_total, 4),
                 "ntt": {"kernel": "ntt_small", "achieved": ntt_rate, "peak": shoup_peak, "unit": "Shoup modular multiplies/s",
                         "frac": (ntt_rate / shoup_peak) if shoup_peak else None,
                         "what": "forward butterflies + gadget multiplies of r, e1, e2, sk per step over the kernel's event time; peak = "
                                 "register-resident mulmod_shoup loop (profiles/r01_int_peaks.json)"},
                 "single_call": {"what": "D = 1 (one reference-style encrypt call / one all-party decrypt pass): HBM-bound matrix-vector "
-                                        "form of the same kernel, L2 flushed between calls, rows = %d" % nrows,
+                                        "form on the CUDA cores (mac.cu), L2 flushed between calls, rows = %d" % nrows,
                                 **{kname: dict(v, frac=v["achieved_GBps"] / peak) for kname, v in (single or {}).items()}},
                 "modmuladds_per_s": mac_rate,
                 "integer_pipe": {"achieved": mac_rate, "peak": int_peak, "unit": "62-bit modular multiply-accumulates/s",
                                  "frac": (mac_rate / int_peak) if int_peak else None,
-                                 "peak_source": "measured on B200 with csrc/tools/int_peaks.cu (3 IMAD.WIDE + carries per MAC, register "
-                                                "resident; profiles/r01_int_peaks.json)"},
-                "note": "dealer tiling re-uses each B / c1 tile from shared memory for several dealers, so the kernel is bound by the "
-                        "fma-heavy integer pipe (3 IMAD.WIDE per 62-bit multiply-accumulate, ncu sm__pipe_fmaheavy 75 %) and moves far "
-                        "fewer DRAM bytes (`traffic`) than the algorithmic figure; frac > 1 is therefore possible (DESIGN.md 4)"}
+                                 "peak_source": "ceiling of the CUDA-core form (3 IMAD.WIDE + carries per MAC, csrc/tools/int_peaks.cu, "
+                                                "profiles/r01_int_peaks.json): the tensor-core kernel is measured against it for scale"},
+                "note": "batched encrypt / decrypt multiply on the INT8 tensor cores: operands are byte planes, the 64 byte products of a "
+                        "62-bit multiply accumulate on overlapping windows of the TMEM accumulator into 15 diagonal sums, recombined and "
+                        "reduced exactly in the epilogue (DESIGN.md 4); PVW_OPTS=imma=0 runs the CUDA-core kernel instead"})
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample -------------------------------------------------
     cpu = None

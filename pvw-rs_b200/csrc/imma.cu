@@ -18,7 +18,10 @@
 //
 // Kernel shape: persistent, one CTA per SM, warp specialised --
 //   warp 0: TMA producer (B tile once per output tile, then the (s, K-chunk) tiles of M through a ring of 16 KB stages),
-//   warp 1: TMEM allocation + MMA issue (one lane), warps 2-9: epilogue (two warps per TMEM lane group, half the dealers each).
+//   warp 1: TMEM allocation + MMA issue (one lane), warps 2-9: epilogue (two warps per TMEM lane group, half the dealers each):
+//   phase 1 turns the 15 sums of each dealer into five 32-bit words and hands TMEM back, phase 2 (reduction, stores) runs
+//   under the next tile's MMAs.  Measured alternative (not kept): reading diagonal u as soon as plane u has completed and
+//   freeing its columns at once -- the interleaved tcgen05.ld slow the MMA stream down (2.49 ms against 2.29 ms per launch).
 // A window that starts DT*s columns in touches DT columns no earlier MMA has written: on the first K step of plane s >= 1 the
 // MMA is issued in two parts, N = 7*DT accumulating and N = DT (the t = 7 rows of B) overwriting, so TMEM never needs clearing.
 #include <cuda.h>

@@ -7,7 +7,7 @@
 // with m_s, v_t the little-endian bytes of the operands,
 //     M * V = sum_{u=0..14} 2^(8u) * S_u ,      S_u = sum_{s+t=u} sum_j m_s(j) v_t(j)   (< 8 k 255^2 < 2^31 for k <= 4096).
 // Both operands are stored as byte planes.  For one tile (128 rows x DT dealers) the B operand is the tile of V's byte
-// planes, rows (t, d) -- 8*DT rows, resident in shared memory for the whole K loop -- and for every byte plane s of M one
+// planes, rows (t, d) -- 8*DT rows, one 128-byte K-chunk at a time in shared memory -- and for every byte plane s of M one
 // chain of MMAs  D[:, DT*s .. DT*s + 8*DT) += M_s * B^T  runs on a WINDOW of the accumulator that starts DT*s columns in:
 // row (t, d) of B lands in column DT*(s+t) + d, so the 64 byte products of every output add up, in place, to its 15
 // diagonal sums S_u at columns DT*u + d.  64 int8 multiply-accumulates per 62-bit one, no expanded operand, no zero
@@ -17,7 +17,8 @@
 //  MACs per 62-bit one and 15x the V bytes; 8.4e12 MAC/s, bound by the L2 -> shared-memory traffic of the expanded operand.)
 //
 // Kernel shape: persistent, one CTA per SM, warp specialised --
-//   warp 0: TMA producer (B tile once per output tile, then the (s, K-chunk) tiles of M through a ring of 16 KB stages),
+//   warp 0: TMA producer (per K-chunk: the B chunk into one of two 32 KB slots, then the eight (plane s, chunk) tiles of M
+//           through a ring of ten 16 KB stages),
 //   warp 1: TMEM allocation + MMA issue (one lane), warps 2-9: epilogue (two warps per TMEM lane group, half the dealers each):
 //   phase 1 turns the 15 sums of each dealer into five 32-bit words and hands TMEM back, phase 2 (reduction, stores) runs
 //   under the next tile's MMAs.  Measured alternative (not kept): reading diagonal u as soon as plane u has completed and
@@ -39,7 +40,7 @@ constexpr uint32_t RT = 128, KC = 128, A_STAGE = RT * KC;
 constexpr uint32_t EPI_WARPS = 8, THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SMEM_LIMIT = 227 * 1024;
-constexpr uint32_t MAX_STAGES = 8;
+constexpr uint32_t MAX_STAGES = 10;
 constexpr uint32_t BAR_BYTES = 256;
 
 #define IMMA_DEV __device__ __forceinline__
@@ -105,17 +106,16 @@ IMMA_DEV void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 
-// DT dealers per tile: 32 (k <= 512: B tile 8*32 rows x k bytes <= 128 KB) or 16 (k <= 1024)
+// DT dealers per tile (32: 15 * 32 = 480 of the 512 TMEM columns)
 template <uint32_t DT>
 __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                               const ImmaArgs g, const uint32_t nstages, const uint32_t nbuf) {
+                                                               const ImmaArgs g, const uint32_t nstages) {
   constexpr uint32_t NB = 8 * DT;                 // rows of the B tile = MMA columns per window
   constexpr uint32_t B_CHUNK = NB * KC;           // one K-chunk of the B tile (multiple of 1024 bytes)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128-byte swizzle wants 1024-byte aligned tiles
   const uint32_t kp = imma_kp(g.k), nkc = (kp + KC - 1) / KC;
-  const uint32_t b_bytes = nkc * B_CHUNK;                               // one B tile (all of K); nbuf of them (1 or 2)
-  const uint32_t b_base = base, a_base = base + nbuf * b_bytes, bar0 = a_base + nstages * A_STAGE;
+  const uint32_t b_base = base, a_base = base + 2 * B_CHUNK, bar0 = a_base + nstages * A_STAGE;   // two B chunk slots, then the M ring
   uint8_t* gen = smem_raw + (bar0 - smem_u32(smem_raw));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 8 * (2 * MAX_STAGES + 6));
   auto a_full = [&](uint32_t s) { return bar0 + 8 * s; };
@@ -148,37 +148,39 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t stg = 0, i = 0;
-      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
+      uint32_t stg = 0, bcnt = 0;
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
-        const uint32_t bb = i % nbuf, bit = i / nbuf;
-        mbar_wait(b_empty(bb), (bit & 1) ^ 1);                           // the MMAs of the tile that used this B buffer are done
-        mbar_expect_tx(b_full(bb), b_bytes);
-        for (uint32_t kc = 0; kc < nkc; kc++)
-          tma_load_4d(b_base + bb * b_bytes + kc * B_CHUNK, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
-        for (uint32_t s = 0; s < 8; s++)
-          for (uint32_t kc = 0; kc < nkc; kc++, stg++) {
+        for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
+          // K-chunk kc of the B tile (all 8 byte planes of the DT dealers) into one of the two chunk slots, then the eight
+          // (plane s, chunk kc) tiles of M that multiply it
+          const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
+          mbar_wait(b_empty(bb), (bit & 1) ^ 1);                         // the MMAs that read this slot two chunks ago are done
+          mbar_expect_tx(b_full(bb), B_CHUNK);
+          tma_load_4d(b_base + bb * B_CHUNK, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
+          for (uint32_t s = 0; s < 8; s++, stg++) {
             const uint32_t st = stg % nstages, it = stg / nstages;
             mbar_wait(a_empty(st), (it & 1) ^ 1);                        // first pass over the ring: passes at once
             mbar_expect_tx(a_full(st), A_STAGE);
             tma_load_4d(a_base + st * A_STAGE, &tmA, (int)(kc * KC), (int)s, (int)(rt * RT), (int)plane, a_full(st));
           }
+        }
       }
     }
   } else if (warp == 1) {
-    uint32_t stg = 0, i = 0;
+    uint32_t stg = 0, bcnt = 0, i = 0;
     for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
-      const uint32_t bb = i % nbuf, bit = i / nbuf;
       mbar_wait(tmem_empty, (i & 1) ^ 1);                                // the epilogue has read the previous tile out of TMEM
-      mbar_wait(b_full(bb), bit & 1);
       tc_fence_after();
-      for (uint32_t s = 0; s < 8; s++)
-        for (uint32_t kc = 0; kc < nkc; kc++, stg++) {
+      for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
+        const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
+        mbar_wait(b_full(bb), bit & 1);
+        for (uint32_t s = 0; s < 8; s++, stg++) {
           const uint32_t st = stg % nstages, it = stg / nstages;
           mbar_wait(a_full(st), it & 1);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * b_bytes + kc * B_CHUNK, d_addr = tmem_base + DT * s;
+            const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * B_CHUNK, d_addr = tmem_base + DT * s;
 #pragma unroll
             for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
               const uint64_t adesc = umma_desc(a_addr + 32 * k4);
@@ -190,10 +192,12 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
               }
             }
             tc_commit(a_empty(st));                                      // arrives when the MMAs above have read the stage
+            if (s == 7) tc_commit(b_empty(bb));
           }
           __syncwarp();
         }
-      if (lane == 0) { tc_commit(b_empty(bb)); tc_commit(tmem_full); }
+      }
+      if (lane == 0) tc_commit(tmem_full);
       __syncwarp();
     }
   } else {
@@ -321,12 +325,10 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
   // V byte planes: [plane][t][d][kp]; box = 128 bytes of DT dealers of all 8 planes t -> rows (t, d) of the B tile
   if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
-  const uint32_t b_bytes = nkc * 8 * DT * KC;
-  if (b_bytes + 2 * A_STAGE + 1024 + BAR_BYTES > SMEM_LIMIT) return false;
-  // two B buffers (the next tile's B arrives during this tile's MMAs) when at least four ring stages still fit
-  const uint32_t nbuf = (2 * b_bytes + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 2 : 1;
-  const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - nbuf * b_bytes) / A_STAGE);
-  const uint32_t smem = nbuf * b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
+  (void)nkc;
+  const uint32_t b_bytes = 2 * 8 * DT * KC;                              // two K-chunk slots of the B tile
+  const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE);
+  const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
   auto kern = imma_gemm_kernel<DT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);  // per device
   int dev = 0, sms = 0;
@@ -334,20 +336,20 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint64_t tiles = (uint64_t)((a.rows + RT - 1) / RT) * ((a.D + DT - 1) / DT) * planes;
   if (tiles >= (1ull << 32)) return false;
-  kern<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, smem, st>>>(tmA, tmB, a, nstages, nbuf);
+  kern<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, smem, st>>>(tmA, tmB, a, nstages);
   return true;
 }
 
 }  // namespace
 
 bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
-  // the B tile (8 * DT rows x kp bytes) must leave room for the M ring; 8 * k * 255^2 fits the signed 32-bit accumulator
-  return rows > 0 && D > 0 && k >= 1 && k <= 1024;
+  // 8 * k * 255^2 must fit the signed 32-bit accumulator
+  return rows > 0 && D > 0 && k >= 1 && k <= 4096;
 }
 
 bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
   if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
-  return imma_kp(a.k) <= 512 ? launch_dt<32>(a, st) : launch_dt<16>(a, st);
+  return launch_dt<32>(a, st);
 }
 
 void launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb,

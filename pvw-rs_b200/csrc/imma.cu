@@ -327,7 +327,8 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
   (void)nkc;
   const uint32_t b_bytes = 2 * 8 * DT * KC;                              // two K-chunk slots of the B tile
-  const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE);
+  static const uint32_t stage_cap = getenv("PVW_IMMA_STAGES") ? (uint32_t)atoi(getenv("PVW_IMMA_STAGES")) : MAX_STAGES;   // experiment knob
+  const uint32_t nstages = std::max(2u, std::min<uint32_t>(std::min(stage_cap, MAX_STAGES), (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
   auto kern = imma_gemm_kernel<DT>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);  // per device

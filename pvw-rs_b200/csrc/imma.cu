@@ -156,11 +156,15 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
           // (plane s, chunk kc) tiles of M that multiply it
           const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
           mbar_wait(b_empty(bb), (bit & 1) ^ 1);                         // the MMAs that read this slot two chunks ago are done
-          mbar_expect_tx(b_full(bb), B_CHUNK);
-          tma_load_4d(b_base + bb * B_CHUNK, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
+          if (g.mode >= 4 && bcnt >= 2) mbar_arrive(b_full(bb));         // timing probe: operands stay as loaded the first time
+          else {
+            mbar_expect_tx(b_full(bb), B_CHUNK);
+            tma_load_4d(b_base + bb * B_CHUNK, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
+          }
           for (uint32_t s = 0; s < 8; s++, stg++) {
             const uint32_t st = stg % nstages, it = stg / nstages;
             mbar_wait(a_empty(st), (it & 1) ^ 1);                        // first pass over the ring: passes at once
+            if (g.mode >= 4 && stg >= nstages) { mbar_arrive(a_full(st)); continue; }
             mbar_expect_tx(a_full(st), A_STAGE);
             tma_load_4d(a_base + st * A_STAGE, &tmA, (int)(kc * KC), (int)s, (int)(rt * RT), (int)plane, a_full(st));
           }
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
           mbar_wait(a_full(st), it & 1);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * B_CHUNK, d_addr = tmem_base + DT * s;
+            const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * B_CHUNK, d_addr = tmem_base + (g.mode == 5 ? 0 : DT * s);  // mode 5: timing probe, no windows
 #pragma unroll
             for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
               const uint64_t adesc = umma_desc(a_addr + 32 * k4);
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
       const uint32_t srow = (g.mode == 1 && row_ok) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
       mbar_wait(tmem_full, i & 1);
       tc_fence_after();
-      if (g.mode == 3) {                                                 // timing probe: MMA / load pipeline without an epilogue
+      if (g.mode >= 3) {                                                 // timing probes: MMA / load pipeline without an epilogue
         tc_fence_before();
         mbar_arrive(tmem_empty);
         continue;
@@ -350,7 +354,8 @@ bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
 
 bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
   if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
-  return launch_dt<32>(a, st);
+  static const int dt = getenv("PVW_IMMA_DT") ? atoi(getenv("PVW_IMMA_DT")) : 32;   // experiment knob
+  return dt == 16 ? launch_dt<16>(a, st) : launch_dt<32>(a, st);
 }
 
 void launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb,

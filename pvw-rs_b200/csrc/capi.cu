@@ -98,7 +98,7 @@ struct pvw_ctx {
   int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
   // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
-  int use_imma = 1;
+  int use_imma = 1, imma_pair = 0;
   int64_t imma_min_dealers = 8, imma_chunk_dealers = 512;
   DevBuf As, Bs, Vx, shat_s;
   bool As_valid = false, Bs_valid = false;
@@ -365,7 +365,8 @@ const uint8_t* planes_B(pvw_ctx* c) {
   }
   return c->Bs.as<uint8_t>();
 }
-void imma_launch(pvw_ctx* c, const ImmaArgs& g) {
+void imma_launch(pvw_ctx* c, ImmaArgs g) {
+  g.pair = c->imma_pair;
   bool ok = true;
   launch(c, PVW_KERNEL_MAC, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
   require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
@@ -1200,6 +1201,7 @@ void* pvw_ctx_stream(pvw_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
   if (c && name && std::string(name) == "imma") { c->use_imma = value != 0; return PVW_OK; }
+  if (c && name && std::string(name) == "imma_pair") { c->imma_pair = value != 0; return PVW_OK; }
   if (c && name && std::string(name) == "imma_min_dealers") { c->imma_min_dealers = std::max<int64_t>(1, value); return PVW_OK; }
   if (c && name && std::string(name) == "imma_chunk_dealers") { c->imma_chunk_dealers = std::max<int64_t>(16, value); return PVW_OK; }
   return guarded(c, [&] {

@@ -267,6 +267,202 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-SM form (tcgen05.mma.cta_group::2) -- MEASURED ALTERNATIVE, off by default (option "imma_pair" / PVW_IMMA_PAIR=1).
+// The MMA stream of the single-CTA kernel runs at ~195-215 cycles per instruction whatever N (128 or 256) and whether or
+// not anything is loaded (probe modes 3-5), i.e. 59 % of the nominal int8 rate.  If the shared-memory operand fetch (4 KB
+// of A + 8 KB of B per instruction) were the cause, a CTA pair sharing one M = 256 MMA would help: each CTA stages its own
+// 128 rows of M and HALF of the B tile (byte planes t = 4*rank .. 4*rank+3 of the DT dealers), 8 KB per SM and instruction.
+// It does not: the pair kernel is bit-exact and exactly as fast (2.37 ms per c2 launch against 2.36 ms), so the stream is
+// at what this part sustains under tensor load -- the same 60 % of nominal that MEASURED_PEAKS.json records for cuBLAS bf16
+// (1 355 of 2 250 TFLOP/s sustained).  The leader CTA issues the MMAs for both;
+// TMA loads of both CTAs complete on the leader's full barriers, tcgen05.commit multicasts the empty / done barriers to both.
+// The N = 7*DT + DT split of the first K step does not exist here (B is split evenly between the CTAs), so the epilogue
+// clears the upper columns (diagonals 8..14) with tcgen05.st after reading them.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA rank 0 of the pair
+
+IMMA_DEV uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+IMMA_DEV void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+IMMA_DEV void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+IMMA_DEV void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+IMMA_DEV void tc_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+IMMA_DEV void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+IMMA_DEV void tc_st8_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+IMMA_DEV void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// M = 256 (two CTAs x 128 lanes): M >> 4 = 16 at bits 24-28
+__host__ __device__ constexpr uint32_t idesc2_n(uint32_t n) { return (2u << 4) | ((n >> 3) << 17) | ((256u >> 4) << 24); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+imma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ImmaArgs g, const uint32_t nstages) {
+  constexpr uint32_t DT = 32, NB = 8 * DT, B_HALF = (NB / 2) * KC;      // this CTA's half of one K-chunk of the B tile: 16 KB
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kp = imma_kp(g.k), nkc = (kp + KC - 1) / KC;
+  const uint32_t b_base = base, a_base = base + 2 * B_HALF, bar0 = a_base + nstages * A_STAGE;
+  uint8_t* gen = smem_raw + (bar0 - smem_u32(smem_raw));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 8 * (2 * MAX_STAGES + 6));
+  auto a_full = [&](uint32_t s) { return bar0 + 8 * s; };
+  auto a_empty = [&](uint32_t s) { return bar0 + 8 * (MAX_STAGES + s); };
+  auto b_full = [&](uint32_t b) { return bar0 + 8 * (2 * MAX_STAGES + b); };
+  auto b_empty = [&](uint32_t b) { return bar0 + 8 * (2 * MAX_STAGES + 2 + b); };
+  const uint32_t tmem_full = bar0 + 8 * (2 * MAX_STAGES + 4), tmem_empty = tmem_full + 8;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rank = cluster_rank();
+  const bool leader = rank == 0;
+  // pair tile = 256 rows x DT dealers x plane; the pair b / 2 walks pair tiles b/2, b/2 + gridDim.x/2, ...
+  const uint32_t n_rt = (g.rows + 2 * RT - 1) / (2 * RT), n_dt = (g.D + DT - 1) / DT, total = n_rt * n_dt * g.L * g.ell;
+  const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < nstages; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (uint32_t b = 0; b < 2; b++) { mbar_init(b_full(b), 1); mbar_init(b_empty(b), 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 2 * 32 * EPI_WARPS);                           // the epilogue threads of BOTH CTAs arrive on the leader's
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                                    // barrier inits and TMEM of both CTAs are visible
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stg = 0, bcnt = 0;
+      for (uint32_t tile = pair; tile < total; tile += npairs) {
+        const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
+        for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
+          const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
+          mbar_wait(b_empty(bb), (bit & 1) ^ 1);
+          if (leader) mbar_expect_tx(b_full(bb), 2 * B_HALF);            // both halves complete on the leader's barrier
+          tma_load_4d_2sm(b_base + bb * B_HALF, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), (int)(4 * rank), (int)plane, b_full(bb) & PEER_MASK);
+          for (uint32_t s = 0; s < 8; s++, stg++) {
+            const uint32_t st = stg % nstages, it = stg / nstages;
+            mbar_wait(a_empty(st), (it & 1) ^ 1);
+            if (leader) mbar_expect_tx(a_full(st), 2 * A_STAGE);
+            tma_load_4d_2sm(a_base + st * A_STAGE, &tmA, (int)(kc * KC), (int)s, (int)(rt * 2 * RT + rank * RT), (int)plane, a_full(st) & PEER_MASK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      uint32_t stg = 0, bcnt = 0, i = 0;
+      for (uint32_t tile = pair; tile < total; tile += npairs, i++) {
+        mbar_wait(tmem_empty, i & 1);                                    // both epilogues have read and cleared the previous tile (phase 0: the initial clearing)
+        tc_fence_after();
+        for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
+          const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
+          mbar_wait(b_full(bb), bit & 1);
+          for (uint32_t s = 0; s < 8; s++, stg++) {
+            const uint32_t st = stg % nstages, it = stg / nstages;
+            mbar_wait(a_full(st), it & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * B_HALF, d_addr = tmem_base + DT * s;
+#pragma unroll
+              for (uint32_t k4 = 0; k4 < KC / 32; k4++)
+                tc_mma_i8_2sm(d_addr, umma_desc(a_addr + 32 * k4), umma_desc(b_addr + 32 * k4), idesc2_n(NB), (kc | k4 | s) != 0);
+              tc_commit_2sm(a_empty(st));
+              if (s == 7) tc_commit_2sm(b_empty(bb));
+            }
+            __syncwarp();
+          }
+        }
+        if (lane == 0) tc_commit_2sm(tmem_full);
+        __syncwarp();
+      }
+    }
+  } else {
+    const uint32_t lg = warp & 3, half = (warp - 2) >> 2;
+    // diagonals 8..14 start from zero in every tile (the first MMA of a tile only overwrites the window of plane 0)
+    for (uint32_t col = 8 * DT + half * 8; col < IMMA_DIAGS * DT; col += 16) tc_st8_zero(tmem_base + ((lg * 32) << 16) + col);
+    tc_st_wait();
+    tc_fence_before();
+    mbar_arrive_cluster(tmem_empty & PEER_MASK);
+    uint32_t i = 0;
+    for (uint32_t tile = pair; tile < total; tile += npairs, i++) {
+      const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
+      const uint32_t row = rt * 2 * RT + rank * RT + lg * 32 + lane, d0 = dt * DT;
+      const uint32_t limb = plane / g.ell, c = plane - limb * g.ell;
+      const LimbConst lc = g.lc[limb];
+      const bool row_ok = row < g.rows;
+      const size_t o_row = (size_t)limb * g.O_ls + (size_t)row * g.O_rs + (size_t)c * g.O_cs;
+      const uint32_t srow = (g.mode == 1 && row_ok) ? (g.S_rowmap ? g.S_rowmap[row] : row) : 0;
+      mbar_wait(tmem_full, i & 1);
+      tc_fence_after();
+      constexpr uint32_t ND = DT / 2;
+      uint32_t W[ND][5];
+#pragma unroll
+      for (uint32_t q4 = 0; q4 < ND / 4; q4++) {
+        uint32_t v[IMMA_DIAGS][4];
+#pragma unroll
+        for (uint32_t u = 0; u < IMMA_DIAGS; u++) tc_ld4(tmem_base + ((lg * 32) << 16) + DT * u + half * ND + q4 * 4, v[u]);
+        tc_ld_wait();
+#pragma unroll
+        for (uint32_t dd = 0; dd < 4; dd++) {
+          uint32_t s[IMMA_DIAGS];
+#pragma unroll
+          for (uint32_t u = 0; u < IMMA_DIAGS; u++) s[u] = v[u][dd];
+          combine160(s, W[q4 * 4 + dd]);
+        }
+      }
+      // clear this thread's part of diagonals 8..14 for the next tile, then hand TMEM back
+#pragma unroll
+      for (uint32_t u = 8; u < IMMA_DIAGS; u++) {
+        tc_st8_zero(tmem_base + ((lg * 32) << 16) + DT * u + half * ND);
+        tc_st8_zero(tmem_base + ((lg * 32) << 16) + DT * u + half * ND + 8);
+      }
+      tc_st_wait();
+      tc_fence_before();
+      mbar_arrive_cluster(tmem_empty & PEER_MASK);
+      if (g.mode >= 3) continue;
+#pragma unroll
+      for (uint32_t dd = 0; dd < ND; dd++) {
+        const uint32_t d = d0 + half * ND + dd;
+        if (row_ok && d < g.D) {
+          u64 r = reduce160(W[dd], lc);
+          u64* o = g.O + (size_t)d * g.O_ds + o_row;
+          if (g.mode == 0) r = addmod(r, *o, lc.q);
+          else if (g.mode == 1) {
+            const uint32_t sd = g.V_dmap ? g.V_dmap[d] : d;
+            r = submod(r, g.S[(size_t)sd * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c], lc.q);
+          }
+          *o = g.O_packed ? pack_halves(r) : r;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // one CTA per (row, limb): thread = (c, j) with j fastest -> the byte stores of a warp fill one sector of one plane
 __global__ void __launch_bounds__(256) imma_planes_m_kernel(const u64* __restrict__ M, size_t M_ls, size_t M_rs, uint32_t k, uint32_t ell,
                                                             uint8_t* __restrict__ Mb, size_t Mb_plane, int packed) {
@@ -345,6 +541,28 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   return true;
 }
 
+
+bool launch_pair(const ImmaArgs& a, cudaStream_t st) {
+  const uint32_t kp = imma_kp(a.k);
+  const uint64_t planes = (uint64_t)a.L * a.ell;
+  CUtensorMap tmA, tmB;
+  if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
+  // each CTA of the pair loads four of the eight byte planes t of the DT dealers
+  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, 32, 4, 1})) return false;
+  const uint32_t b_bytes = 2 * 4 * 32 * KC;
+  const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE);
+  const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
+  cudaFuncSetAttribute(imma_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t tiles = (uint64_t)((a.rows + 2 * RT - 1) / (2 * RT)) * ((a.D + 31) / 32) * planes;
+  if (tiles >= (1ull << 32)) return false;
+  const unsigned pairs = (unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms / 2, 1));
+  imma_gemm2_kernel<<<2 * pairs, THREADS, smem, st>>>(tmA, tmB, a, nstages);
+  return true;
+}
+
 }  // namespace
 
 bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
@@ -354,7 +572,9 @@ bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
 
 bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
   if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
-  static const int dt = getenv("PVW_IMMA_DT") ? atoi(getenv("PVW_IMMA_DT")) : 32;   // experiment knob
+  static const int dt = getenv("PVW_IMMA_DT") ? atoi(getenv("PVW_IMMA_DT")) : 32;   // experiment knobs
+  static const int pair = getenv("PVW_IMMA_PAIR") ? atoi(getenv("PVW_IMMA_PAIR")) : 0;
+  if (pair || a.pair) return launch_pair(a, st);
   return dt == 16 ? launch_dt<16>(a, st) : launch_dt<32>(a, st);
 }
 

@@ -30,6 +30,7 @@ struct ImmaArgs {
   uint32_t rows, D, k, L, ell;
   int mode, O_packed;
   const LimbConst* lc;   // [L]
+  int pair;              // 1: the two-SM form (tcgen05.mma.cta_group::2 on CTA pairs) -- measured, not faster; default 0
 };
 // false when the shape cannot be served (tensor-map creation failed): the caller must have checked imma_shape_ok
 bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st);

@@ -101,6 +101,21 @@ def test_device_inputs_row_shards_and_dealer_slices(pkg):
         assert (out.cpu().numpy().view(np.uint64) == want[lo:hi]).all()
 
 
+@pytest.mark.parametrize("name,D", [("EX", 20), ("WIDE", 33), ("P128s", 33), ("L32b", 2)])
+def test_two_sm_form_matches(pkg, name, D):
+    """option imma_pair: the same product with tcgen05.mma.cta_group::2 on CTA pairs (measured alternative, off by default)"""
+    P = SETS[name]()
+    S = System(P, D, "u63")
+    c1, c2 = S.encrypt()
+    eng = load(forced(pkg, P), S, D)
+    eng.set_option("imma_pair", 1)
+    eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)
+    for d in range(D):
+        g1, g2 = eng.ct_download(d)
+        assert (g1 == c1[d]).all() and (g2 == c2[d]).all(), f"dealer {d}"
+    assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=D) == S.co.decrypt(S.sk, c1, c2)).all()
+
+
 def test_odd_k_falls_back_to_the_imad_kernel(pkg):
     P = params("RAG")                                    # k = 5: rows of 40 bytes cannot be TMA sources
     S = System(P, 9, "u63")

@@ -45,7 +45,10 @@ typedef enum {
   PVW_ERR_INSUFFICIENT_DATA = -9   /* PvwError::InsufficientData    errors.rs:62 (wire buffer too short)          */
 } pvw_status;
 
-enum { PVW_IO_HOST = 0u, PVW_IO_DEVICE = 1u };
+enum { PVW_IO_HOST = 0u, PVW_IO_DEVICE = 1u,
+       /* pvw_encrypt_batch only: compute just c1 (dealers c1_lo..c1_hi) or just c2, so that a multi-GPU host layer can start the
+          all-gather of the c1 slices while the (much larger) c2 product runs; m / e2 may be NULL with C1_ONLY, e1 with C2_ONLY */
+       PVW_ENC_C1_ONLY = 2u, PVW_ENC_C2_ONLY = 4u };
 
 /* Replaces PvwParametersBuilder::build (src/params/parameters.rs:117-195) + fhe-math Context::new.
  * Same validation: n > 0, k > 0, ell a power of two >= 8, moduli prime, < 2^62, = 1 mod 2*ell, distinct,

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libpvw_b200.so")
 
 PVW_OK = 0
 PVW_IO_HOST, PVW_IO_DEVICE = 0, 1
+PVW_ENC_C1_ONLY, PVW_ENC_C2_ONLY = 2, 4
 STATUS_NAMES = {
     0: "Ok", -1: "InvalidParameters", -2: "DimensionMismatch", -3: "IndexOutOfBounds", -4: "EncryptionError",
     -5: "DecryptionError", -6: "KeyGenerationError", -7: "InternalError", -8: "DeserializationError", -9: "InsufficientData",

@@ -651,8 +651,11 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     if (D == 0) return;
     const HostParams& hp = c->hp;
     const uint32_t L = hp.L, k = hp.k, ell = hp.ell, nrows = c->nrows;
-    require(m && r && e2, PVW_ERR_INVALID_PARAMETERS, "null argument");
+    require(!((flags & PVW_ENC_C1_ONLY) && (flags & PVW_ENC_C2_ONLY)), PVW_ERR_INVALID_PARAMETERS, "C1_ONLY and C2_ONLY exclude each other");
     require(c1_lo <= c1_hi && c1_hi <= D, PVW_ERR_INVALID_PARAMETERS, "bad c1 dealer range");
+    const bool do_c2 = !(flags & PVW_ENC_C1_ONLY);
+    if (flags & PVW_ENC_C2_ONLY) c1_lo = c1_hi = 0;
+    require(r && (!do_c2 || (m && e2)), PVW_ERR_INVALID_PARAMETERS, "null argument");
     require(c1_lo == c1_hi || e1 != nullptr, PVW_ERR_INVALID_PARAMETERS, "e1 is null");
     require(c->A_set, PVW_ERR_INVALID_PARAMETERS, "CRS has not been uploaded");
     // encryption.rs:117-121: is_full() <=> num_keys >= n ; restricted to this shard: every local row below num_keys
@@ -670,8 +673,8 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     const long long* d_e1 = nullptr;
     if (c1_hi > c1_lo)
       d_e1 = (const long long*)stage_in(c, c->in_small2, e1 + (size_t)c1_lo * k * ell, (size_t)(c1_hi - c1_lo) * k * ell * 8, flags);
-    const long long* d_e2 = (const long long*)stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags, c->ev[0]);
-    const u64* d_m = (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]);
+    const long long* d_e2 = do_c2 ? (const long long*)stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags, c->ev[0]) : nullptr;
+    const u64* d_m = do_c2 ? (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]) : nullptr;
     // r_hat (encryption.rs:147-154): operand form [d][limb][j][ell] for the IMAD kernel, byte planes for the tensor-core one
     const bool imma = imma_wanted(c, nrows, D);
     const uint32_t kp = imma_kp(k);
@@ -692,7 +695,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     auto preload = [&](bool accumulate) {
       launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream, accumulate); });
     };
-    if (!host && !imma) preload(false);
+    if (!host && !imma && do_c2) preload(false);
     if (imma) {
       // tensor-core product (imma.cu) on the byte planes of A / B (built once) and of r_hat (written by the NTT kernel)
       ImmaArgs g{};
@@ -704,11 +707,12 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
         imma_launch(c, g);
       }
-      // the product is stored alone; NTT(e2) + m g_hat is added afterwards with unit-stride accesses
-      g.Mb = planes_B(c); g.Mb_plane = (size_t)nrows * 8 * kp; g.rows = nrows;
-      g.d_first = 0; g.D = D;
-      g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2; g.O_rs = ell; g.O_cs = 1; g.O_packed = 0; g.mode = 2;
-      imma_launch(c, g);
+      if (do_c2) {  // the product is stored alone; NTT(e2) + m g_hat is added afterwards with unit-stride accesses
+        g.Mb = planes_B(c); g.Mb_plane = (size_t)nrows * 8 * kp; g.rows = nrows;
+        g.d_first = 0; g.D = D;
+        g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2; g.O_rs = ell; g.O_cs = 1; g.O_packed = 0; g.mode = 2;
+        imma_launch(c, g);
+      }
     } else {
       if (c1_hi > c1_lo) {
         const uint32_t Dc = c1_hi - c1_lo;
@@ -719,15 +723,17 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
         gemm(c, g);
       }
-      GemmArgs g{};
-      g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
-      g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
-      g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2;
-      g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = host ? 2 : 0; g.lc = c->T.lc;
-      gemm(c, g);
+      if (do_c2) {
+        GemmArgs g{};
+        g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
+        g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
+        g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2;
+        g.rows = nrows; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = host ? 2 : 0; g.lc = c->T.lc;
+        gemm(c, g);
+      }
     }
-    if (host) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
-    if (host || imma) preload(true);
+    if (host && do_c2) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+    if ((host || imma) && do_c2) preload(true);
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
 }

@@ -239,22 +239,27 @@ class Engine:
         self._check(self.lib.pvw_ct_reserve(self.h, capacity))
         self.capacity = capacity
 
-    def encrypt_batch(self, slot0: int, m, r, e1, e2, c1_range=None):
-        """m [D][nrows] u64; r, e1 [D][k][l] i64; e2 [D][nrows][l] i64 -- all host or all device"""
-        D = int(m.shape[0])
+    def encrypt_batch(self, slot0: int, m, r, e1, e2, c1_range=None, part: str = "both"):
+        """m [D][nrows] u64; r, e1 [D][k][l] i64; e2 [D][nrows][l] i64 -- all host or all device.
+        part: "both", or "c1" / "c2" alone (PVW_ENC_C1_ONLY / PVW_ENC_C2_ONLY: a multi-GPU host layer all-gathers the c1 slices
+        while the c2 product runs); m / e2 may be None with "c1", e1 with "c2"."""
+        D = int(r.shape[0])
         lo, hi = (0, D) if c1_range is None else c1_range
-        am = _Arg(m, np.uint64, (D, self.nrows), "m")
+        pflag = {"both": 0, "c1": _ffi.PVW_ENC_C1_ONLY, "c2": _ffi.PVW_ENC_C2_ONLY}[part]
+        am = _Arg(m, np.uint64, (D, self.nrows), "m") if m is not None else None
         ar = _Arg(r, np.int64, (D, self.k, self.l), "r")
-        ae2 = _Arg(e2, np.int64, (D, self.nrows, self.l), "e2")
+        ae2 = _Arg(e2, np.int64, (D, self.nrows, self.l), "e2") if e2 is not None else None
         ae1 = _Arg(e1, np.int64, (D, self.k, self.l), "e1") if e1 is not None else None
+        if part != "c1" and (am is None or ae2 is None):
+            raise PvwError("InvalidParameters", "m and e2 are required")
         devs = {a.device for a in (am, ar, ae2, ae1) if a is not None}
         if len(devs) != 1:
             raise PvwError("InvalidParameters", "inputs must be all host or all device arrays")
         on_device = devs.pop()
         if on_device:
             self._before_device_call()
-        self._check(self.lib.pvw_encrypt_batch(self.h, slot0, D, lo, hi, am.ptr, ar.ptr, ae1.ptr if ae1 else None, ae2.ptr,
-                                               _ffi.PVW_IO_DEVICE if on_device else 0))
+        self._check(self.lib.pvw_encrypt_batch(self.h, slot0, D, lo, hi, am.ptr if am else None, ar.ptr, ae1.ptr if ae1 else None,
+                                               ae2.ptr if ae2 else None, (_ffi.PVW_IO_DEVICE if on_device else 0) | pflag))
         if on_device:
             self._after_device_call()
 

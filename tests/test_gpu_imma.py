@@ -89,7 +89,11 @@ def test_device_inputs_row_shards_and_dealer_slices(pkg):
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
     for lo, hi, dlo, dhi in ((0, 130, 0, 9), (130, 300, 9, 21)):
         eng = load(forced(pkg, P, row0=lo, nrows=hi - lo), S, D)
-        eng.encrypt_batch(0, dev(S.m[:, lo:hi]), dev(S.r), dev(S.e1), dev(S.e2[:, lo:hi]), c1_range=(dlo, dhi))
+        if lo == 0:
+            eng.encrypt_batch(0, dev(S.m[:, lo:hi]), dev(S.r), dev(S.e1), dev(S.e2[:, lo:hi]), c1_range=(dlo, dhi))
+        else:   # the two halves separately (PVW_ENC_C1_ONLY / PVW_ENC_C2_ONLY), as the multi-GPU step issues them
+            eng.encrypt_batch(0, None, dev(S.r), dev(S.e1), None, c1_range=(dlo, dhi), part="c1")
+            eng.encrypt_batch(0, dev(S.m[:, lo:hi]), dev(S.r), None, dev(S.e2[:, lo:hi]), part="c2")
         for d in range(D):
             g1, g2 = eng.ct_download(d)
             assert (g2 == c2[d, lo:hi]).all()

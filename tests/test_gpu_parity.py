@@ -199,7 +199,11 @@ def test_ciphertext_upload_roundtrip_and_row_sharding(pkg):
         lo, hi = bounds[g], bounds[g + 1]
         eng = _loaded(pkg, S, D, row0=lo, nrows=hi - lo)
         dlo, dhi = (0, 2) if g == 0 else (2, 4) if g == 1 else (4, 5)
-        eng.encrypt_batch(0, S.m[:, lo:hi], S.r, S.e1, S.e2[:, lo:hi], c1_range=(dlo, dhi))
+        if g == 1:   # c1 and c2 in separate calls (PVW_ENC_C1_ONLY / PVW_ENC_C2_ONLY), host inputs
+            eng.encrypt_batch(0, None, S.r, S.e1, None, c1_range=(dlo, dhi), part="c1")
+            eng.encrypt_batch(0, S.m[:, lo:hi], S.r, None, S.e2[:, lo:hi], part="c2")
+        else:
+            eng.encrypt_batch(0, S.m[:, lo:hi], S.r, S.e1, S.e2[:, lo:hi], c1_range=(dlo, dhi))
         for d in range(D):
             g1, g2 = eng.ct_download(d)
             assert (g2 == c2[d, lo:hi]).all()

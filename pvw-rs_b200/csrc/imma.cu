@@ -107,15 +107,20 @@ IMMA_DEV void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 }
 
 // DT dealers per tile (32: 15 * 32 = 480 of the 512 TMEM columns)
-template <uint32_t DT>
+template <uint32_t DT, bool RES>
 __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const ImmaArgs g, const uint32_t nstages) {
+  constexpr uint32_t resident = RES ? 1u : 0u;
+  // resident != 0: a B slot holds the whole B tile (all K-chunks) and the loop runs plane-major (s outer, K-chunk inner): one B
+  // load per tile, the next tile's B arrives during this tile's MMAs -- used when two such slots fit (k <= 256 at DT = 32).
+  // resident == 0: a B slot holds one K-chunk and the loop runs chunk-major; shared memory does not depend on k.
   constexpr uint32_t NB = 8 * DT;                 // rows of the B tile = MMA columns per window
   constexpr uint32_t B_CHUNK = NB * KC;           // one K-chunk of the B tile (multiple of 1024 bytes)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // 128-byte swizzle wants 1024-byte aligned tiles
   const uint32_t kp = imma_kp(g.k), nkc = (kp + KC - 1) / KC;
-  const uint32_t b_base = base, a_base = base + 2 * B_CHUNK, bar0 = a_base + nstages * A_STAGE;   // two B chunk slots, then the M ring
+  const uint32_t bunit = resident ? nkc * B_CHUNK : B_CHUNK;            // bytes of one B slot; two slots, then the M ring
+  const uint32_t b_base = base, a_base = base + 2 * bunit, bar0 = a_base + nstages * A_STAGE;
   uint8_t* gen = smem_raw + (bar0 - smem_u32(smem_raw));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 8 * (2 * MAX_STAGES + 6));
   auto a_full = [&](uint32_t s) { return bar0 + 8 * s; };
@@ -148,57 +153,92 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t stg = 0, bcnt = 0;
+      uint32_t st = 0, ph = 1, bcnt = 0, loaded = 0;                      // ph: parity to wait for on the empty barriers
       for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
-        for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
-          // K-chunk kc of the B tile (all 8 byte planes of the DT dealers) into one of the two chunk slots, then the eight
-          // (plane s, chunk kc) tiles of M that multiply it
+        auto load_b = [&](uint32_t kc0, uint32_t kc1) {                  // K-chunks [kc0, kc1) of the B tile into the next B slot
           const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
-          mbar_wait(b_empty(bb), (bit & 1) ^ 1);                         // the MMAs that read this slot two chunks ago are done
+          mbar_wait(b_empty(bb), (bit & 1) ^ 1);                         // the MMAs that read this slot two fills ago are done
           if (g.mode >= 4 && bcnt >= 2) mbar_arrive(b_full(bb));         // timing probe: operands stay as loaded the first time
           else {
-            mbar_expect_tx(b_full(bb), B_CHUNK);
-            tma_load_4d(b_base + bb * B_CHUNK, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
+            mbar_expect_tx(b_full(bb), bunit);
+            for (uint32_t kc = kc0; kc < kc1; kc++)
+              tma_load_4d(b_base + bb * bunit + (RES ? kc * B_CHUNK : 0u), &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), 0, (int)plane, b_full(bb));
           }
-          for (uint32_t s = 0; s < 8; s++, stg++) {
-            const uint32_t st = stg % nstages, it = stg / nstages;
-            mbar_wait(a_empty(st), (it & 1) ^ 1);                        // first pass over the ring: passes at once
-            if (g.mode >= 4 && stg >= nstages) { mbar_arrive(a_full(st)); continue; }
+          bcnt++;
+        };
+        auto load_a = [&](uint32_t s, uint32_t kc) {
+          mbar_wait(a_empty(st), ph);                                    // first pass over the ring: passes at once
+          if (g.mode >= 4 && loaded >= nstages) mbar_arrive(a_full(st));
+          else {
             mbar_expect_tx(a_full(st), A_STAGE);
             tma_load_4d(a_base + st * A_STAGE, &tmA, (int)(kc * KC), (int)s, (int)(rt * RT), (int)plane, a_full(st));
+            loaded++;
+          }
+          if (++st == nstages) { st = 0; ph ^= 1; }
+        };
+        if (RES) {
+          load_b(0, nkc);
+          for (uint32_t s = 0; s < 8; s++)
+            for (uint32_t kc = 0; kc < nkc; kc++) load_a(s, kc);
+        } else {
+          for (uint32_t kc = 0; kc < nkc; kc++) {
+            load_b(kc, kc + 1);
+            for (uint32_t s = 0; s < 8; s++) load_a(s, kc);
           }
         }
       }
     }
   } else if (warp == 1) {
-    uint32_t stg = 0, bcnt = 0, i = 0;
+    uint32_t st = 0, ph = 0, bcnt = 0, i = 0;
+    const uint32_t a_lo = (a_base & 0x3FFFFu) >> 4, b_lo = (b_base & 0x3FFFFu) >> 4;
     for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
       mbar_wait(tmem_empty, (i & 1) ^ 1);                                // the epilogue has read the previous tile out of TMEM
       tc_fence_after();
-      for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
-        const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
-        mbar_wait(b_full(bb), bit & 1);
-        for (uint32_t s = 0; s < 8; s++, stg++) {
-          const uint32_t st = stg % nstages, it = stg / nstages;
-          mbar_wait(a_full(st), it & 1);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * B_CHUNK, d_addr = tmem_base + (g.mode == 5 ? 0 : DT * s);  // mode 5: timing probe, no windows
+      // The issuing lane is a single thread running scalar code between the MMAs: measured, the MMA stream is paced by THIS
+      // loop, not by the tensor pipe or the loads (a version with two integer divisions per stage ran 25 % slower).  So: ring
+      // position and phase are counters, descriptors are base + offset in their 14-bit address field, nothing is divided.
+      constexpr uint64_t DESC_HI = ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      uint32_t bb = 0;
+      auto step = [&](uint32_t s, uint32_t kc) {
+        mbar_wait(a_full(st), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = DESC_HI | (uint64_t)(a_lo + st * (A_STAGE >> 4));
+          const uint64_t bdesc = DESC_HI | (uint64_t)(b_lo + bb * (bunit >> 4) + (RES ? kc * (B_CHUNK >> 4) : 0u));
+          const uint32_t d_addr = tmem_base + DT * s;
+          if (kc != 0) {
 #pragma unroll
-            for (uint32_t k4 = 0; k4 < KC / 32; k4++) {
-              const uint64_t adesc = umma_desc(a_addr + 32 * k4);
-              if (kc | k4) tc_mma_i8(d_addr, adesc, umma_desc(b_addr + 32 * k4), idesc_n(NB), 1);
-              else if (s == 0) tc_mma_i8(d_addr, adesc, umma_desc(b_addr), idesc_n(NB), 0);
-              else {  // columns DT*(s+7) .. +DT are new to this window: their first product overwrites
-                tc_mma_i8(d_addr, adesc, umma_desc(b_addr), idesc_n(7 * DT), 1);
-                tc_mma_i8(d_addr + 7 * DT, adesc, umma_desc(b_addr + 7 * DT * KC), idesc_n(DT), 0);
-              }
+            for (uint32_t k4 = 0; k4 < KC / 32; k4++) tc_mma_i8(d_addr, adesc + 2 * k4, bdesc + 2 * k4, idesc_n(NB), 1);
+          } else {
+            if (s == 0) tc_mma_i8(d_addr, adesc, bdesc, idesc_n(NB), 0);
+            else {  // columns DT*(s+7) .. +DT are new to this window: their first product overwrites
+              tc_mma_i8(d_addr, adesc, bdesc, idesc_n(7 * DT), 1);
+              tc_mma_i8(d_addr + 7 * DT, adesc, bdesc + (7 * DT * KC >> 4), idesc_n(DT), 0);
             }
-            tc_commit(a_empty(st));                                      // arrives when the MMAs above have read the stage
-            if (s == 7) tc_commit(b_empty(bb));
+#pragma unroll
+            for (uint32_t k4 = 1; k4 < KC / 32; k4++) tc_mma_i8(d_addr, adesc + 2 * k4, bdesc + 2 * k4, idesc_n(NB), 1);
           }
-          __syncwarp();
+          tc_commit(a_empty(st));                                        // arrives when the MMAs above have read the stage
+        }
+        __syncwarp();
+        if (++st == nstages) { st = 0; ph ^= 1; }
+      };
+      auto next_b = [&]() {
+        bb = bcnt & 1;
+        mbar_wait(b_full(bb), (bcnt >> 1) & 1);
+        bcnt++;
+      };
+      if (RES) {
+        next_b();
+        for (uint32_t s = 0; s < 8; s++)
+          for (uint32_t kc = 0; kc < nkc; kc++) step(s, kc);
+        if (lane == 0) tc_commit(b_empty(bb));
+      } else {
+        for (uint32_t kc = 0; kc < nkc; kc++) {
+          next_b();
+          for (uint32_t s = 0; s < 8; s++) step(s, kc);
+          if (lane == 0) tc_commit(b_empty(bb));
         }
       }
       if (lane == 0) tc_commit(tmem_full);
@@ -525,12 +565,14 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
   // V byte planes: [plane][t][d][kp]; box = 128 bytes of DT dealers of all 8 planes t -> rows (t, d) of the B tile
   if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
-  (void)nkc;
-  const uint32_t b_bytes = 2 * 8 * DT * KC;                              // two K-chunk slots of the B tile
+  // two whole B tiles resident when at least four ring stages still fit (k <= 256 at DT = 32), else two K-chunk slots
+  const uint32_t b_tile = nkc * 8 * DT * KC;
+  const uint32_t resident = (2 * b_tile + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 1u : 0u;
+  const uint32_t b_bytes = resident ? 2 * b_tile : 2 * 8 * DT * KC;
   static const uint32_t stage_cap = getenv("PVW_IMMA_STAGES") ? (uint32_t)atoi(getenv("PVW_IMMA_STAGES")) : MAX_STAGES;   // experiment knob
   const uint32_t nstages = std::max(2u, std::min<uint32_t>(std::min(stage_cap, MAX_STAGES), (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
-  auto kern = imma_gemm_kernel<DT>;
+  auto kern = resident ? imma_gemm_kernel<DT, true> : imma_gemm_kernel<DT, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);  // per device
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);

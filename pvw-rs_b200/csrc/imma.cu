@@ -73,6 +73,13 @@ IMMA_DEV void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp, chosen by the hardware: the form under which ptxas keeps the single-thread tcgen05 issue
+// code on the uniform datapath (a plain `lane == 0` branch wraps every UTCIMMA in an ELECT / BRA.U.ANY loop)
+IMMA_DEV bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 IMMA_DEV void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (SBO), version 1 (sm_100)
 IMMA_DEV uint64_t umma_desc(uint32_t saddr) {
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
       auto step = [&](uint32_t s, uint32_t kc) {
         mbar_wait(a_full(st), ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t adesc = DESC_HI | (uint64_t)(a_lo + st * (A_STAGE >> 4));
           const uint64_t bdesc = DESC_HI | (uint64_t)(b_lo + bb * (bunit >> 4) + (RES ? kc * (B_CHUNK >> 4) : 0u));
           const uint32_t d_addr = tmem_base + DT * s;

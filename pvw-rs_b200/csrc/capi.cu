@@ -100,7 +100,7 @@ struct pvw_ctx {
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
   int use_imma = 1, imma_pair = 0;
   int64_t imma_min_dealers = 8, imma_chunk_dealers = 512;
-  DevBuf As, Bs, Vx, shat_s;
+  DevBuf As, Bs, Vx, shat_s, prod;
   bool As_valid = false, Bs_valid = false;
   int64_t decrypt_chunk_shares = 1 << 19;
   int64_t upload_chunk_bytes = 256ll << 20;
@@ -453,7 +453,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
     b->release();
   delete c;
 }
@@ -707,11 +707,25 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
         imma_launch(c, g);
       }
-      if (do_c2) {  // the product is stored alone; NTT(e2) + m g_hat is added afterwards with unit-stride accesses
+      if (do_c2) {
+        // The product goes to a slot-major scratch (lanes of a warp = consecutive parties: full-sector stores), a chunk of
+        // dealers at a time; the NTT kernel then writes c2 = NTT(e2) + m g_hat + product in the store layout, reading the product
+        // with unit stride.  (Storing 8-byte results straight into the store layout, 64 bytes apart, cost 10 GB of DRAM traffic
+        // per launch in partial-sector writes and fills and made the launch DRAM-bound.)
         g.Mb = planes_B(c); g.Mb_plane = (size_t)nrows * 8 * kp; g.rows = nrows;
-        g.d_first = 0; g.D = D;
-        g.O = c2; g.O_ls = (size_t)nrows * ell; g.O_ds = w2; g.O_rs = ell; g.O_cs = 1; g.O_packed = 0; g.mode = 2;
-        imma_launch(c, g);
+        g.O_ls = (size_t)ell * nrows; g.O_ds = (size_t)L * ell * nrows; g.O_rs = 1; g.O_cs = nrows; g.O_packed = 0; g.mode = 2;
+        const uint32_t step = (uint32_t)std::min<int64_t>(D, std::max<int64_t>(16, c->imma_chunk_dealers));
+        c->prod.ensure((size_t)step * w2 * 8);
+        for (uint32_t dc0 = 0; dc0 < D; dc0 += step) {
+          const uint32_t Dc = std::min(step, D - dc0);
+          g.d_first = dc0; g.D = Dc; g.O = c->prod.as<u64>();
+          imma_launch(c, g);
+          if (host && dc0 == 0) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));   // e2 / m arrive under the first product
+          launch(c, PVW_KERNEL_NTT, 0.0, [&] {
+            launch_ntt_small(c->T, d_e2 + (size_t)dc0 * nrows * ell, d_m + (size_t)dc0 * nrows, (uint64_t)Dc * nrows, nrows, c2 + (size_t)dc0 * w2, w2,
+                             (size_t)nrows * ell, c->stream, false, false, 0, c->prod.as<u64>());
+          });
+        }
       }
     } else {
       if (c1_hi > c1_lo) {
@@ -732,8 +746,10 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         gemm(c, g);
       }
     }
-    if (host && do_c2) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
-    if ((host || imma) && do_c2) preload(true);
+    if (host && do_c2 && !imma) {
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
+      preload(true);
+    }
     if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
 }

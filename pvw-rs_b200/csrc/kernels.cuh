@@ -46,7 +46,9 @@ struct DevTables {
 //   value = NTT(rns(coef[idx]))[c] (+ (m[idx] as i64 mod q) * gadget_hat[limb][c] when m != nullptr)
 // pack_out: write the 31-bit-halves operand form (modarith.cuh pack_halves) that the multiply-accumulate kernel reads
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false, bool pack_out = false, int planes = 0);
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false, bool pack_out = false, int planes = 0,
+                      const u64* addend = nullptr);
+// addend: out = value + addend[(vec*L + limb)*ell*inner + c*inner + j], the slot-major product of the tensor-core kernel
 // planes 1 / 2: write the byte planes of the tensor-core product (imma.cuh), matrix-row side (Mb) / dealer side (Vb); then
 // inner = k, vstride = kp (bytes per plane row), lstride = plane stride in bytes, out is a byte buffer
 // generic strided block copy:  out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c],  c < blk

@@ -11,12 +11,14 @@
 namespace pvw {
 
 template <int ELL, int MODE>  // MODE 0: store canonical, 1: accumulate into canonical, 2: store packed halves (operand form),
-                               // 3 / 4: store the byte planes the tensor-core path reads (imma.cuh), M side / dealer side
+                               // 3 / 4: store the byte planes the tensor-core path reads (imma.cuh), M side / dealer side,
+                               // 5: store canonical value + addend, the addend in the slot-major form the tensor-core product writes:
+                               //    addend[(vec*L + limb)*ELL*inner + c*inner + j]   (unit stride across the threads of a warp)
 __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
                                                         const u64* __restrict__ tw_sh, const u64* __restrict__ gadget_hat,
-                                                        const u64* __restrict__ gadget_hat_sh) {
+                                                        const u64* __restrict__ gadget_hat_sh, const u64* __restrict__ addend) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL], s_g[ELL], s_g_sh[ELL];
   const uint32_t limb = blockIdx.y;
   if (threadIdx.x < ELL) {
@@ -60,6 +62,11 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   }
   uint64_t vec = idx / inner, j = idx % inner;
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
+  if (MODE == 5) {
+    const u64* ad = addend + ((size_t)vec * gridDim.y + limb) * ELL * inner + j;
+#pragma unroll
+    for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], ad[(size_t)t * inner], lc.q);
+  }
 #pragma unroll
   for (int t = 0; t < ELL / 2; t++) {
     if (MODE == 1) {  // out += value (the matrix product was stored first; host-pointer encrypt overlaps the e2 / m copy with it)
@@ -74,21 +81,23 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 }
 
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes) {
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes, const u64* addend) {
   if (count == 0) return;
   dim3 grid((unsigned)((count + 127) / 128), T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
-    if (planes == 1)                                                                                                          \
-      ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+    if (addend)                                                                                                               \
+      ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+    else if (planes == 1)                                                                                                     \
+      ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
     else if (planes == 2)                                                                                                     \
-      ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+      ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
     else if (accumulate)                                                                                                           \
-      ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+      ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
     else if (pack_out)                                                                                                        \
-      ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+      ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
     else                                                                                                                      \
-      ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh);  \
+      ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
     break;
   switch (T.ell) {
     PVW_NTT_CASE(8)

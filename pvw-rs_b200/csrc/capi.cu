@@ -131,6 +131,7 @@ void upload_tables(pvw_ctx* c) {
   size_t o_tw = put(hp.tw.data(), (size_t)L * ell), o_tws = put(hp.tw_sh.data(), (size_t)L * ell);
   size_t o_twi = put(hp.twi.data(), (size_t)L * ell), o_twis = put(hp.twi_sh.data(), (size_t)L * ell);
   size_t o_g = put(hp.gadget_hat.data(), (size_t)L * ell), o_gs = put(hp.gadget_hat_sh.data(), (size_t)L * ell);
+  size_t o_dc = put(hp.dec_c.data(), (size_t)L * 4);
   std::vector<uint64_t> qhat_t((size_t)L * NWT, 0), qsh_t((size_t)LB * (NWT + 1), 0);
   for (uint32_t j = 0; j < L; j++) memcpy(&qhat_t[(size_t)j * NWT], &hp.qhat[(size_t)j * NW], (size_t)NW * 8);
   for (uint32_t b = 0; b < LB; b++) memcpy(&qsh_t[(size_t)b * (NWT + 1)], &hp.Qsh[(size_t)b * (NW + 1)], (size_t)(NW + 1) * 8);
@@ -147,7 +148,7 @@ void upload_tables(pvw_ctx* c) {
   const u64* base = c->tables.as<u64>();
   DevTables& T = c->T;
   T.lc = reinterpret_cast<const LimbConst*>(base + o_lc);
-  T.tw = base + o_tw; T.tw_sh = base + o_tws; T.twi = base + o_twi; T.twi_sh = base + o_twis; T.gadget_hat = base + o_g; T.gadget_hat_sh = base + o_gs;
+  T.tw = base + o_tw; T.tw_sh = base + o_tws; T.twi = base + o_twi; T.twi_sh = base + o_twis; T.gadget_hat = base + o_g; T.gadget_hat_sh = base + o_gs; T.dec_c = base + o_dc;
   T.qhat = base + o_qhat; T.Qsh = base + o_qsh;
   T.Qw = base + o_Q; T.halfQ = base + o_hQ; T.Mw = base + o_M; T.halfM = base + o_hM; T.Dw = base + o_D;
   T.divM_v = base + o_dM; T.div2D_v = base + o_d2D;

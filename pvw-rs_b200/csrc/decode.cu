@@ -25,7 +25,7 @@ template <int ELL>
 __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, uint32_t Pc, uint64_t S,
                                                          u64* __restrict__ y, const LimbConst* __restrict__ lcs,
                                                          const u64* __restrict__ twi, const u64* __restrict__ twi_sh, size_t z_cs,
-                                                         const DecodeSub sub) {
+                                                         const DecodeSub sub, const u64* __restrict__ dec_c) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
   const uint32_t limb = blockIdx.y;
   if (threadIdx.x < ELL) {
@@ -61,18 +61,22 @@ __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__
       a[2 * t + 1] = submod(a[2 * t + 1], v.y, lc.q);
     }
   }
-  ntt_inverse_regs<ELL>(a, s_tw, s_tw_sh, lc.ninv, lc.ninv_sh, lc.q);
+  // a' = ell * INTT(z): the scale ell^-1 and the CRT factor (Q/q)^-1 are folded into the two multipliers
+  //   c1 = Delta * ell^-1 * (Q/q)^-1,  c2 = ell^-1 * (Q/q)^-1      (33 Shoup multiplies per thread instead of 42)
+  ntt_inverse_unscaled_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
   const u64 q = lc.q;
+  const u64 c1 = dec_c[4 * limb], c1_sh = dec_c[4 * limb + 1], c2 = dec_c[4 * limb + 2], c2_sh = dec_c[4 * limb + 3];
   u64* yo = y + ((size_t)limb * (ELL + 1)) * S + s;
-  u64 last = 0;
+  u64 last = 0, p2 = mulmod_shoup(a[0], c2, c2_sh, q);                                      // a_0 * (Q/q)^-1
+  yo[(size_t)ELL * S] = negmod(p2, q);                                                       // z_0 * (-1), decryption.rs:52
 #pragma unroll
   for (int i = 0; i < ELL - 1; i++) {
-    u64 tmp = submod(mulmod_shoup(a[i], lc.delta, lc.delta_sh, q), a[i + 1], q);           // decryption.rs:25
-    last = (i == 0) ? tmp : addmod(mulmod_shoup(last, lc.delta, lc.delta_sh, q), tmp, q);  // decryption.rs:30-33
-    yo[(size_t)i * S] = mulmod_shoup(tmp, lc.qhinv, lc.qhinv_sh, q);
+    p2 = mulmod_shoup(a[i + 1], c2, c2_sh, q);
+    const u64 tmp = submod(mulmod_shoup(a[i], c1, c1_sh, q), p2, q);                          // (z_i * Delta - z_{i+1}) (Q/q)^-1, decryption.rs:25
+    last = (i == 0) ? tmp : addmod(mulmod_shoup(last, lc.delta, lc.delta_sh, q), tmp, q);    // Horner, decryption.rs:30-33
+    yo[(size_t)i * S] = tmp;
   }
-  yo[(size_t)(ELL - 1) * S] = mulmod_shoup(last, lc.qhinv, lc.qhinv_sh, q);
-  yo[(size_t)ELL * S] = mulmod_shoup(negmod(a[0], q), lc.qhinv, lc.qhinv_sh, q);            // z_0 * (-1), :52
+  yo[(size_t)(ELL - 1) * S] = last;
 }
 
 void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st, size_t z_cs,
@@ -82,9 +86,9 @@ void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_d
   dim3 grid((unsigned)((S + 127) / 128), T.L);
   const DecodeSub sb = sub ? *sub : DecodeSub{nullptr, 0, 0, nullptr, nullptr};
   switch (T.ell) {
-    case 8: decode_rns_kernel<8><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb); break;
-    case 16: decode_rns_kernel<16><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb); break;
-    case 32: decode_rns_kernel<32><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb); break;
+    case 8: decode_rns_kernel<8><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c); break;
+    case 16: decode_rns_kernel<16><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c); break;
+    case 32: decode_rns_kernel<32><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c); break;
   }
 }
 

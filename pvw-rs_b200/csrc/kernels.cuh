@@ -24,6 +24,7 @@ struct DevTables {
   const u64* twi_sh;
   const u64* gadget_hat;   // [L][ell] NTT([1, D, .., D^(l-1)] mod q) (parameters.rs:288-308)
   const u64* gadget_hat_sh;  //        Shoup companions
+  const u64* dec_c;        // [L][4] multipliers of decode_rns (hostparams.hpp dec_c)
   // CRT lift
   const u64* qhat;         // [L][NWT]   Q/q_j, zero padded to the template width
   const u64* Qsh;          // [LB][NWT+1] Q << b

@@ -27,6 +27,29 @@ PVW_DEV void ntt_forward_regs(u64 (&a)[ELL], const u64* tw, const u64* tw_sh, u6
   }
 }
 
+// the Gentleman-Sande passes without the final scale by ell^-1 (callers that multiply the result anyway fold it in)
+template <int ELL>
+PVW_DEV void ntt_inverse_unscaled_regs(u64 (&a)[ELL], const u64* twi, const u64* twi_sh, u64 q) {
+  int t = 1;
+#pragma unroll
+  for (int m = ELL; m > 1; m >>= 1) {
+    const int h = m >> 1;
+    int j1 = 0;
+#pragma unroll
+    for (int i = 0; i < h; i++) {
+      const u64 s = twi[h + i], s_sh = twi_sh[h + i];
+#pragma unroll
+      for (int j = j1; j < j1 + t; j++) {
+        u64 u = a[j], v = a[j + t];
+        a[j] = addmod(u, v, q);
+        a[j + t] = mulmod_shoup(submod(u, v, q), s, s_sh, q);
+      }
+      j1 += 2 * t;
+    }
+    t <<= 1;
+  }
+}
+
 template <int ELL>
 PVW_DEV void ntt_inverse_regs(u64 (&a)[ELL], const u64* twi, const u64* twi_sh, u64 ninv, u64 ninv_sh, u64 q) {
   int t = 1;

@@ -61,22 +61,23 @@ __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__
       a[2 * t + 1] = submod(a[2 * t + 1], v.y, lc.q);
     }
   }
-  // a' = ell * INTT(z): the scale ell^-1 and the CRT factor (Q/q)^-1 are folded into the two multipliers
-  //   c1 = Delta * ell^-1 * (Q/q)^-1,  c2 = ell^-1 * (Q/q)^-1      (33 Shoup multiplies per thread instead of 42)
+  // a' = ell * INTT(z): the scale ell^-1 is folded into the two multipliers c1 = Delta * ell^-1, c2 = ell^-1.  The small values
+  // (tmp_i, -z_0) are stored as plain residues -- the short lift verifies its candidate against them without a multiply;
+  // only `last`, which always takes the full CRT lift, is pre-multiplied by (Q/q)^-1.
   ntt_inverse_unscaled_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
   const u64 q = lc.q;
   const u64 c1 = dec_c[4 * limb], c1_sh = dec_c[4 * limb + 1], c2 = dec_c[4 * limb + 2], c2_sh = dec_c[4 * limb + 3];
   u64* yo = y + ((size_t)limb * (ELL + 1)) * S + s;
-  u64 last = 0, p2 = mulmod_shoup(a[0], c2, c2_sh, q);                                      // a_0 * (Q/q)^-1
+  u64 last = 0, p2 = mulmod_shoup(a[0], c2, c2_sh, q);                                      // z_0
   yo[(size_t)ELL * S] = negmod(p2, q);                                                       // z_0 * (-1), decryption.rs:52
 #pragma unroll
   for (int i = 0; i < ELL - 1; i++) {
     p2 = mulmod_shoup(a[i + 1], c2, c2_sh, q);
-    const u64 tmp = submod(mulmod_shoup(a[i], c1, c1_sh, q), p2, q);                          // (z_i * Delta - z_{i+1}) (Q/q)^-1, decryption.rs:25
+    const u64 tmp = submod(mulmod_shoup(a[i], c1, c1_sh, q), p2, q);                          // z_i * Delta - z_{i+1}, decryption.rs:25
     last = (i == 0) ? tmp : addmod(mulmod_shoup(last, lc.delta, lc.delta_sh, q), tmp, q);    // Horner, decryption.rs:30-33
     yo[(size_t)i * S] = tmp;
   }
-  yo[(size_t)(ELL - 1) * S] = last;
+  yo[(size_t)(ELL - 1) * S] = mulmod_shoup(last, lc.qhinv, lc.qhinv_sh, q);
 }
 
 void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st, size_t z_cs,
@@ -192,8 +193,8 @@ PVW_DEV bool short_lift(const u64* __restrict__ y, size_t ystride, uint32_t L, c
 #pragma unroll
     for (int w = 1; w < SW; w++) r = r >= q ? r - q : r;
     if (neg) r = r ? q - r : 0;
-    const u64 v = mulmod_shoup(y[(size_t)j * ystride], cj[2], cj[3], q);
-    ok = ok && (r == v);
+    const u64 yj = y[(size_t)j * ystride];                                                  // the plain residue decode_rns stored
+    ok = ok & (r == yj);
   }
   return ok;
 }
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y
 #pragma unroll
   for (int w = 0; w < N; w++) acc[w] = 0;
   for (uint32_t j = 0; j < L; j++) {
-    const u64 yv = y[((size_t)j * ellp1 + i) * S + s];
+    u64 yv = y[((size_t)j * ellp1 + i) * S + s];
+    if (i + 2 != ellp1) yv = mulmod_shoup(yv, T.lc[j].qhinv, T.lc[j].qhinv_sh, T.lc[j].q);   // every value but `last` arrives as a plain residue
     u32 q[W];
     const uint2* row = reinterpret_cast<const uint2*>(s_q + (size_t)j * W);
 #pragma unroll

@@ -192,7 +192,7 @@ struct HostParams {
   uint32_t n = 0, k = 0, ell = 0, L = 0, logell = 0;
   float secret_variance = 0.5f; uint64_t b1 = 100, b2 = 200;
   std::vector<uint64_t> moduli, psi;
-  std::vector<uint64_t> dec_c;   // [L][4]: Delta * ell^-1 * (Q/q)^-1 mod q, its Shoup companion, ell^-1 * (Q/q)^-1, companion
+  std::vector<uint64_t> dec_c;   // [L][4]: Delta * ell^-1 mod q, its Shoup companion, ell^-1, companion
   BigU Q, delta, delta_pow;                 // parameters.rs:151-163
   uint32_t NW = 0;                           // words of Q
   std::vector<LimbConst> lc;                 // [L]
@@ -288,8 +288,8 @@ struct HostParams {
       BigU qh = BigU::divmod_small(Q, q, nullptr);
       qh.to_words(&qhat[(size_t)j * NW], NW);
       c.qhinv = h_powmod(qh.mod_small(q), q - 2, q); c.qhinv_sh = h_shoup(c.qhinv, q);
-      {  // decode_rns works on the unscaled inverse NTT and folds ell^-1 and (Q/q)^-1 into its two multipliers
-        const uint64_t c2 = h_mulmod(c.ninv, c.qhinv, q), c1 = h_mulmod(c.delta, c2, q);
+      {  // decode_rns works on the unscaled inverse NTT and folds ell^-1 into its two multipliers
+        const uint64_t c2 = c.ninv, c1 = h_mulmod(c.delta, c2, q);
         dec_c.push_back(c1); dec_c.push_back(h_shoup(c1, q)); dec_c.push_back(c2); dec_c.push_back(h_shoup(c2, q));
       }
       uint64_t psi_inv = h_powmod(psi[j], q - 2, q);
@@ -343,7 +343,7 @@ struct HostParams {
           BigU h = BigU::divmod_small(Qs2, q, nullptr);
           h.to_words(&sh_qhat[(size_t)j * shortSW], shortSW);
           const uint64_t inv = h_powmod(h.mod_small(q), q - 2, q);
-          sh_c[j] = h_mulmod(sh_v[j], inv, q); sh_c_sh[j] = h_shoup(sh_c[j], q);
+          sh_c[j] = inv; sh_c_sh[j] = h_shoup(sh_c[j], q);   // the small values reach the lift as plain residues (decode.cu)
         }
       }
     }

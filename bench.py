@@ -391,7 +391,7 @@ def run_b200(args):
                     "unit": "TOP/s (u8 x u8 -> s32, dense)", "frac": int8_ops / int8_peak,
                     "peak_source": ("2 x measured cuBLAS bf16 (MEASURED_PEAKS.json, sustained)" if peaks else "2 x nominal dense bf16 (fallback)"),
                     "frac_of_nominal_4500_TOPs": int8_ops / 4500.0,
-                    "ncu_tensor_pipe_pct_of_peak": "45 % (sm__ops_path_tensor_op_utcimma_src_int8, c2 launch, profiles/r01_imma_gemm_ncu_summary.json)",
+                    "ncu_tensor_pipe_pct_of_peak": "63 % (sm__ops_path_tensor_op_utcimma_src_int8, c2 launch, profiles/r01_imma_gemm_ncu_summary.json)",
                     "traffic": traffic, "ops_per_launch": mac_rate * 128 * (mac_ms * 1e-3) / max(mac_n, 1),
                     "int8_macs_per_62bit_mac": 64}
     else:

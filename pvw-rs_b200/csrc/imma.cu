@@ -14,17 +14,22 @@
 // padding in the GEMM.  The epilogue thread that owns a TMEM lane (= a row) reads the 15 sums of each dealer,
 // recombines them into one 160-bit integer and reduces it: no cross-lane traffic.
 // (First version, kept in git history: V expanded into 15 diagonal rows, M rows used as they lie in memory -- 120 int8
-//  MACs per 62-bit one and 15x the V bytes; 8.4e12 MAC/s, bound by the L2 -> shared-memory traffic of the expanded operand.)
+//  MACs per 62-bit one and 15x the V bytes; 8.4e12 MAC/s.  This one: 2.05e13 MAC/s on the c2 product of the bench.)
 //
 // Kernel shape: persistent, one CTA per SM, warp specialised --
-//   warp 0: TMA producer (per K-chunk: the B chunk into one of two 32 KB slots, then the eight (plane s, chunk) tiles of M
-//           through a ring of ten 16 KB stages),
-//   warp 1: TMEM allocation + MMA issue (one lane), warps 2-9: epilogue (two warps per TMEM lane group, half the dealers each):
-//   phase 1 turns the 15 sums of each dealer into five 32-bit words and hands TMEM back, phase 2 (reduction, stores) runs
-//   under the next tile's MMAs.  Measured alternative (not kept): reading diagonal u as soon as plane u has completed and
-//   freeing its columns at once -- the interleaved tcgen05.ld slow the MMA stream down (2.49 ms against 2.29 ms per launch).
+//   warp 0: TMA producer.  RES (two whole B tiles fit, k <= 256): the B tile once per output tile into one of two slots, then
+//           the (plane s, K-chunk) tiles of M, plane-major, through a ring of 16 KB stages; otherwise one 128-byte K-chunk of
+//           B at a time (two chunk slots) and the loop runs chunk-major, so shared memory does not depend on k.
+//   warp 1: TMEM allocation + MMA issue by one lane (elect.sync).  This thread's scalar code paces the whole kernel: ring
+//           position / phase are counters and descriptors are base + offset -- with two integer divisions per stage and
+//           descriptors rebuilt from addresses every MMA cost ~195 cycles whatever its shape.
+//   warps 2-9: epilogue, two warps per TMEM lane group, half the dealers each: phase 1 turns the 15 sums of each dealer into
+//           five 32-bit words and hands TMEM back, phase 2 (reduction, stores) runs under the next tile's MMAs.  Measured
+//           alternative (not kept): reading diagonal u as soon as plane u has completed and freeing its columns at once --
+//           slower with both the old and the lean issue loop (2.16 ms against 1.98 ms per c2 launch).
 // A window that starts DT*s columns in touches DT columns no earlier MMA has written: on the first K step of plane s >= 1 the
 // MMA is issued in two parts, N = 7*DT accumulating and N = DT (the t = 7 rows of B) overwriting, so TMEM never needs clearing.
+// Outputs should be written slot-major (O_rs = 1): the lanes of a warp are consecutive rows, so that is the unit-stride form.
 #include <cuda.h>
 
 #include <algorithm>

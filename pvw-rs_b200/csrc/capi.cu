@@ -839,12 +839,21 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     c->z.ensure((size_t)Dstep * L * Pc_max * ell * 8);
     c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * Dstep) * 8);   // sized for the largest chunk up front: growing a
     c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * Dstep) * 8);   // buffer mid-call would synchronise the device
-    // host inputs: a short first chunk, so that little of the secret-key copy is exposed before the kernels start
+    // host inputs: a short first chunk, so that little of the secret-key copy is exposed before the kernels start, then chunks
+    // growing threefold: a party's share of the work takes about 3.5x as long as the copy of its key, so chunk i+1 (<= 3x chunk i)
+    // has arrived by the time chunk i is done
     const uint32_t first = host ? std::max<uint32_t>(1, std::min<uint32_t>(Pc_max, std::max<uint32_t>(Pc_max / 8, 64))) : Pc_max;
+    std::vector<uint32_t> chunks;
+    for (uint32_t p0 = 0, pc = first; p0 < P; ) {
+      const uint32_t Pc = std::min(pc, P - p0);
+      chunks.push_back(Pc);
+      p0 += Pc;
+      pc = (uint32_t)std::min<uint64_t>(Pc_max, 3ull * pc);
+    }
     if (host) {  // every chunk's secret keys are queued now, in order, each with its own event: chunk i+1 arrives while chunk i computes
       uint32_t i = 0;
       for (uint32_t p0 = 0; p0 < P; i++) {
-        const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
+        const uint32_t Pc = chunks[i];
         if (c->chunk_ev.size() <= i) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->chunk_ev.push_back(e); }
         CUDA_CHECK(cudaMemcpyAsync(c->in_small.as<long long>() + (size_t)p0 * k * ell, sk + (size_t)p0 * k * ell, (size_t)Pc * k * ell * 8,
                                    cudaMemcpyHostToDevice, c->copy_stream));
@@ -863,7 +872,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       }
       uint32_t chunk_no = 0;
       for (uint32_t p0 = 0; p0 < P; chunk_no++) {
-        const uint32_t Pc = std::min(p0 == 0 ? first : Pc_max, P - p0);
+        const uint32_t Pc = chunks[chunk_no];
         if (host && dc0 == 0) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->chunk_ev[chunk_no], 0));
         // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274), with
         // s_hat = SecretKey::get_polynomial (secret_key.rs:98-112) computed once per party, not per ciphertext

@@ -16,6 +16,16 @@
 #include "kernels.cuh"
 #include "ntt_regs.cuh"
 
+// Minimum resident CTAs per SM asked of ptxas for the lift and tail kernels.  Both are latency-bound at the occupancy their
+// natural register counts allow (ncu: 98 registers -> 24 % of the warp slots, 154 -> 18 %); capping them at 80 / 128
+// registers costs a few spilled words and buys 1.62 -> 1.46 ms and 0.93 -> 0.80 ms per bench step.  (8, 5) was measured slower.
+#ifndef PVW_LIFT_MINB
+#define PVW_LIFT_MINB 6
+#endif
+#ifndef PVW_TAIL_MINB
+#define PVW_TAIL_MINB 4
+#endif
+
 namespace pvw {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -200,7 +210,7 @@ PVW_DEV bool short_lift(const u64* __restrict__ y, size_t ystride, uint32_t L, c
 }
 
 template <int NWT>
-__global__ void __launch_bounds__(128) crt_lift_kernel(const u64* __restrict__ y, u64* __restrict__ X, uint64_t S, uint32_t L, uint32_t ellp1,
+__global__ void __launch_bounds__(128, PVW_LIFT_MINB) crt_lift_kernel(const u64* __restrict__ y, u64* __restrict__ X, uint64_t S, uint32_t L, uint32_t ellp1,
                                                        uint32_t NW, const u64* __restrict__ qhat, const u64* __restrict__ Qsh, uint32_t LB, const DevTables T) {
   constexpr int W = 2 * NWT;   // 32-bit words of one Q/q_j row
   constexpr int N = W + 3;     // accumulator words: the sum is < L*Q < 2^(32 W + 7)
@@ -591,7 +601,7 @@ PVW_DEV void divrem_fixed(u64 (&un)[NU + 1], const u64* v, u64 vinv, u64 (&q)[NU
 }
 
 template <int NW, int NM, int ND>
-__global__ void __launch_bounds__(128) decode_tail_fixed_kernel(const u64* __restrict__ X, uint64_t S, uint32_t Pc, uint32_t ell, u64* __restrict__ out,
+__global__ void __launch_bounds__(128, PVW_TAIL_MINB) decode_tail_fixed_kernel(const u64* __restrict__ X, uint64_t S, uint32_t Pc, uint32_t ell, u64* __restrict__ out,
                                                                 size_t out_ps, const DevTables T) {
   __shared__ u64 sc[5 * NW + NM + ND];
   const u64* cQ = sc; const u64* cHQ = sc + NW; const u64* cM = sc + 2 * NW; const u64* cHM = sc + 3 * NW; const u64* cD = sc + 4 * NW;

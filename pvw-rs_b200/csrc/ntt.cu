@@ -18,9 +18,11 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
                                                         const u64* __restrict__ tw_sh, const u64* __restrict__ gadget_hat,
-                                                        const u64* __restrict__ gadget_hat_sh, const u64* __restrict__ addend) {
+                                                        const u64* __restrict__ gadget_hat_sh, const u64* __restrict__ addend, const uint32_t L) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL], s_g[ELL], s_g_sh[ELL];
-  const uint32_t limb = blockIdx.y;
+  // 1-D grid, limb fastest: the L CTAs that transform the same 128 polynomials run together, so the small-integer input (and
+  // the message) is fetched from DRAM once, not once per limb
+  const uint32_t limb = blockIdx.x % L, blk = blockIdx.x / L;
   if (threadIdx.x < ELL) {
     s_tw[threadIdx.x] = tw[(size_t)limb * ELL + threadIdx.x];
     s_tw_sh[threadIdx.x] = tw_sh[(size_t)limb * ELL + threadIdx.x];
@@ -29,7 +31,7 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   }
   __syncthreads();
   const LimbConst lc = lcs[limb];
-  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t idx = (uint64_t)blk * blockDim.x + threadIdx.x;
   if (idx >= count) return;
   u64 a[ELL];
   const longlong2* src = reinterpret_cast<const longlong2*>(coef + idx * ELL);
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   uint64_t vec = idx / inner, j = idx % inner;
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + vec * vstride + (size_t)limb * lstride + j * ELL);
   if (MODE == 5) {
-    const u64* ad = addend + ((size_t)vec * gridDim.y + limb) * ELL * inner + j;
+    const u64* ad = addend + ((size_t)vec * L + limb) * ELL * inner + j;
 #pragma unroll
     for (int t = 0; t < ELL; t++) a[t] = addmod(a[t], ad[(size_t)t * inner], lc.q);
   }
@@ -83,21 +85,21 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
 void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
                       size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes, const u64* addend) {
   if (count == 0) return;
-  dim3 grid((unsigned)((count + 127) / 128), T.L);
+  const unsigned grid = (unsigned)(((count + 127) / 128) * T.L);
 #define PVW_NTT_CASE(E)                                                                                                       \
   case E:                                                                                                                     \
     if (addend)                                                                                                               \
-      ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+      ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
     else if (planes == 1)                                                                                                     \
-      ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+      ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
     else if (planes == 2)                                                                                                     \
-      ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+      ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
     else if (accumulate)                                                                                                           \
-      ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+      ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
     else if (pack_out)                                                                                                        \
-      ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+      ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
     else                                                                                                                      \
-      ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend);  \
+      ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
     break;
   switch (T.ell) {
     PVW_NTT_CASE(8)

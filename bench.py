@@ -377,11 +377,13 @@ def run_b200(args):
     ntt_rate = ntt_mulmods / (ntt_ms * 1e-3) if ntt_ms > 0 else 0.0
     # The batched product runs on the INT8 tensor cores (csrc/imma.cu): 64 u8 x u8 multiply-accumulates per 62-bit one, so the
     # kernel's roof is the tensor pipe.  Peak: kind::i8 issues K = 32 per instruction where bf16 issues K = 16 at the same
-    # cadence, i.e. twice the dense bf16 rate; MEASURED_PEAKS.json holds the measured cuBLAS bf16 figure (sustained one: the
-    # kernel is timed inside a long step), else the nominal 2 x 2250 TFLOP/s.
+    # cadence, i.e. twice the dense bf16 rate.  MEASURED_PEAKS.json holds the measured cuBLAS bf16 figures; the product runs in
+    # bursts of <= 2 ms between CUDA-core kernels (tensor duty 43 % of the step), so the burst figure is the denominator and the
+    # fractions against the sustained figure and the nominal 4.5 POP/s are reported next to it.
     imma_on = os.environ.get("PVW_OPTS", "").replace(" ", "").find("imma=0") < 0
-    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
+    bf16 = float(peaks.get("bf16_tflops", 2250.0))
     int8_peak = 2.0 * bf16
+    int8_peak_sustained = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
     int8_ops = mac_rate * 64 * 2 / 1e12
     hbm_view = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "what": "SURVEY 8d algorithmic bytes (one operand row read per (dealer, row) + one polynomial written) over the kernel "
@@ -389,8 +391,8 @@ def run_b200(args):
     if imma_on:
         roofline = {"bound": "tensor", "kernel": "mac_gemm (imma_gemm_kernel: tcgen05.mma kind::i8)", "achieved": int8_ops, "peak": int8_peak,
                     "unit": "TOP/s (u8 x u8 -> s32, dense)", "frac": int8_ops / int8_peak,
-                    "peak_source": ("2 x measured cuBLAS bf16 (MEASURED_PEAKS.json, sustained)" if peaks else "2 x nominal dense bf16 (fallback)"),
-                    "frac_of_nominal_4500_TOPs": int8_ops / 4500.0,
+                    "peak_source": ("2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "2 x nominal dense bf16 (fallback)"),
+                    "frac_of_2x_sustained_bf16": int8_ops / int8_peak_sustained, "frac_of_nominal_4500_TOPs": int8_ops / 4500.0,
                     "ncu_tensor_pipe_pct_of_peak": "63 % (sm__ops_path_tensor_op_utcimma_src_int8, c2 launch, profiles/r01_imma_gemm_ncu_summary.json)",
                     "traffic": traffic, "ops_per_launch": mac_rate * 128 * (mac_ms * 1e-3) / max(mac_n, 1),
                     "int8_macs_per_62bit_mac": 64}

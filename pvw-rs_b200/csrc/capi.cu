@@ -1264,6 +1264,6 @@ int pvw_ctx_profile(pvw_ctx* c, int kind, double* ms_total, uint64_t* launches, 
   });
 }
 uint64_t pvw_ctx_launch_count(const pvw_ctx* c) { return c ? c->launches : 0; }
-const char* pvw_version(void) { return "pvw_b200 0.1 (sm_100a)"; }
+const char* pvw_version(void) { return "pvw_b200 0.2 (sm_100a; tcgen05 int8 product)"; }
 
 }  // extern "C"

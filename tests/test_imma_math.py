@@ -1,0 +1,91 @@
+"""CPU: the arithmetic identity behind the tensor-core product (pvw-rs_b200/csrc/imma.cu), modelled with numpy / Python integers.
+
+The kernel never multiplies 62-bit numbers: it multiplies byte planes with u8 x u8 -> s32 MMAs on overlapping windows of one
+accumulator, and the epilogue recombines 15 diagonal sums.  This test restates exactly that data flow -- byte planes of both
+operands, window s starting DT*s columns in, B-tile row (t, d) landing in column DT*(s+t)+d, the word-grouped recombination of
+`combine160` and the two-step reduction -- and checks it against plain modular dot products.  It needs no GPU; the GPU parity
+tests (tests/test_gpu_imma.py) check the kernel itself."""
+import numpy as np
+import pytest
+
+import pvw_oracle as O
+
+DT = 32                      # dealers per tile
+DIAGS = 15
+
+
+def byte_planes(x):          # x: uint64 [..., k] -> uint8 [8, ..., k]   (plane s = byte s of every value)
+    return np.stack([((x >> np.uint64(8 * s)) & np.uint64(0xFF)).astype(np.int64) for s in range(8)])
+
+
+def windowed_accumulator(M, V):
+    """M: uint64 [rows][k], V: uint64 [DT][k]  ->  int64 [rows][15*DT] exactly as the MMAs leave TMEM"""
+    rows, k = M.shape
+    Mb = byte_planes(M)                                   # [8][rows][k]
+    Vb = byte_planes(V)                                   # [8][DT][k]
+    B = Vb.reshape(8 * DT, k)                             # B tile: row (t, d) = t*DT + d
+    acc = np.zeros((rows, 16 * DT), dtype=np.int64)       # 512 TMEM columns
+    for s in range(8):                                    # one chain of MMAs per byte plane of M, on the window DT*s .. DT*s + 8*DT
+        acc[:, DT * s:DT * s + 8 * DT] += Mb[s] @ B.T
+    assert acc.max() < 2 ** 31                            # the s32 accumulator never overflows
+    return acc[:, :DIAGS * DT]
+
+
+def combine160(s):
+    """the epilogue's recombination: diagonals u = r mod 4 are word aligned among themselves (imma.cu combine160)"""
+    w, acc = [], 0
+    get = lambda i: int(s[i]) if 0 <= i < DIAGS else 0
+    fsl = lambda hi, lo, n: ((hi << n) | (lo >> (32 - n))) & 0xFFFFFFFF      # __funnelshift_l(lo, hi, n): upper word of (hi:lo) << n
+    for i in range(5):
+        c0, c1, c2, c3 = (get(4 * i + r) if i < 4 else 0 for r in range(4))
+        p1, p2, p3 = (get(4 * i - 3), get(4 * i - 2), get(4 * i - 1)) if i > 0 else (0, 0, 0)
+        if i == 4:
+            p3 = 0                                                         # s[15] does not exist
+        acc += c0 + fsl(c1, p1, 8) + fsl(c2, p2, 16) + fsl(c3, p3, 24)
+        w.append(acc & 0xFFFFFFFF)
+        acc >>= 32
+    return w
+
+
+@pytest.mark.parametrize("k,q", [(256, O.largest_ntt_primes(1)[0]), (250, O.EX_MODULI[1]), (18, O.TEST_MODULI[0]), (1024, O.VD_MODULI[0])])
+def test_byte_plane_windows_reproduce_the_modular_product(k, q):
+    rng = np.random.default_rng(k)
+    rows = 5
+    M = rng.integers(0, q, size=(rows, k), dtype=np.uint64)
+    V = rng.integers(0, q, size=(DT, k), dtype=np.uint64)
+    M[0, :] = q - 1                                       # extreme operands
+    V[0, :] = q - 1
+    acc = windowed_accumulator(M, V)
+    for r in range(rows):
+        for d in (0, 1, DT - 1):
+            sums = [acc[r, DT * u + d] for u in range(DIAGS)]                # what the lane of row r reads for dealer d
+            words = combine160(sums)
+            value = sum(wd << (32 * i) for i, wd in enumerate(words))
+            exact = sum(int(a) * int(b) for a, b in zip(M[r], V[d]))
+            assert value == exact                                            # the 160-bit integer IS the unreduced dot product
+            assert value % q == sum(int(a) * int(b) % q for a, b in zip(M[r], V[d])) % q
+            assert words[4] < 2 ** 16                                        # the fifth word stays small: value < k * 2^124
+
+
+def test_first_k_step_split_needs_no_clearing():
+    """window s >= 1 touches DT columns no earlier MMA wrote: issuing its first K step as N = 7*DT accumulating plus N = DT
+    overwriting equals accumulating into a cleared accumulator (the kernel's alternative to zeroing TMEM)"""
+    rng = np.random.default_rng(7)
+    k, rows, q = 64, 3, O.largest_ntt_primes(1)[0]
+    M = rng.integers(0, q, size=(rows, k), dtype=np.uint64)
+    V = rng.integers(0, q, size=(DT, k), dtype=np.uint64)
+    want = windowed_accumulator(M, V)
+    Mb, B = byte_planes(M), byte_planes(V).reshape(8 * DT, k)
+    acc = rng.integers(-2 ** 31, 2 ** 31, size=(rows, 16 * DT)).astype(np.int64)   # garbage left by the previous tile
+    for s in range(8):
+        for k0 in range(0, k, 32):                                           # K = 32 bytes per MMA
+            prod = Mb[s][:, k0:k0 + 32] @ B[:, k0:k0 + 32].T
+            lo = DT * s
+            if k0:
+                acc[:, lo:lo + 8 * DT] += prod
+            elif s == 0:
+                acc[:, lo:lo + 8 * DT] = prod                                # the tile's very first MMA overwrites its whole window
+            else:
+                acc[:, lo:lo + 7 * DT] += prod[:, :7 * DT]                   # N = 7*DT, accumulate
+                acc[:, lo + 7 * DT:lo + 8 * DT] = prod[:, 7 * DT:]           # N = DT (the t = 7 rows of B), overwrite
+    assert (acc[:, :DIAGS * DT] == want).all()

@@ -205,7 +205,8 @@ int pvw_ctx_synchronize(pvw_ctx *ctx);
 /* the CUDA stream (cudaStream_t) all work of the context is ordered on, for CUDA-event timing by the caller */
 void *pvw_ctx_stream(pvw_ctx *ctx);
 /* tuning / introspection: "imma" (1 = batched products on the INT8 tensor cores, the default; 0 = CUDA-core kernel),
- * "imma_min_dealers" (smallest batch that takes the tensor-core path, default 8), "imma_chunk_dealers" (dealers per scratch
+ * "imma_min_dealers" / "imma_min_rows" (smallest batch of dealers / rows of the matrix operand that take the tensor-core path,
+ * defaults 8 / 16), "imma_chunk_dealers" (dealers per scratch
  * chunk, default 512), "imma_pair" (1 = the two-SM cta_group::2 form, a measured alternative), "gemm_impl" (CUDA-core kernel:
  * 0 = synchronous tiles, 1 = TMA bulk-copy pipeline, 2 = tensor-map boxes), "gemm_tile", "refill_lag", "tail_impl", "lift_fast",
  * "decrypt_chunk_shares", "upload_chunk_bytes", "profile" */

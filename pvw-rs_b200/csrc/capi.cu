@@ -99,7 +99,7 @@ struct pvw_ctx {
   // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
   int use_imma = 1, imma_pair = 0;
-  int64_t imma_min_dealers = 8, imma_chunk_dealers = 512;
+  int64_t imma_min_dealers = 8, imma_min_rows = 16, imma_chunk_dealers = 512;
   DevBuf As, Bs, Vx, shat_s, prod;
   bool As_valid = false, Bs_valid = false;
   int64_t decrypt_chunk_shares = 1 << 19;
@@ -341,7 +341,9 @@ void gemm(pvw_ctx* c, GemmArgs a) {
 
 // ---- tensor-core product (imma.cu) --------------------------------------------------------------------------------
 bool imma_wanted(const pvw_ctx* c, uint32_t rows, uint32_t D) {
-  return c->use_imma && D >= (uint32_t)c->imma_min_dealers && imma_shape_ok(rows, D, c->hp.k);
+  // a tile is 128 rows x 32 dealers: below ~16 rows (e.g. one party decrypting many ciphertexts) or 8 dealers the CUDA-core
+  // kernel, which streams the big operand once, is the faster one
+  return c->use_imma && D >= (uint32_t)c->imma_min_dealers && rows >= (uint32_t)c->imma_min_rows && imma_shape_ok(rows, D, c->hp.k);
 }
 // zero padding of the byte planes when k is not a multiple of 16 (imma_kp): only ever non-empty for toy parameter sets
 void planes_clear(pvw_ctx* c, DevBuf& buf, size_t bytes) {
@@ -1235,6 +1237,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
   if (c && name && std::string(name) == "imma") { c->use_imma = value != 0; return PVW_OK; }
   if (c && name && std::string(name) == "imma_pair") { c->imma_pair = value != 0; return PVW_OK; }
   if (c && name && std::string(name) == "imma_min_dealers") { c->imma_min_dealers = std::max<int64_t>(1, value); return PVW_OK; }
+  if (c && name && std::string(name) == "imma_min_rows") { c->imma_min_rows = std::max<int64_t>(1, value); return PVW_OK; }
   if (c && name && std::string(name) == "imma_chunk_dealers") { c->imma_chunk_dealers = std::max<int64_t>(16, value); return PVW_OK; }
   return guarded(c, [&] {
     require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");

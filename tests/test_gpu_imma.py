@@ -32,6 +32,7 @@ def forced(pkg, P, on=True, **over):
     eng = pkg.Engine(**engine_kwargs(P, **over))
     eng.set_option("imma", 1 if on else 0)
     eng.set_option("imma_min_dealers", 1)
+    eng.set_option("imma_min_rows", 1)
     eng.set_option("imma_chunk_dealers", 16)
     return eng
 
@@ -118,6 +119,24 @@ def test_two_sm_form_matches(pkg, name, D):
         g1, g2 = eng.ct_download(d)
         assert (g1 == c1[d]).all() and (g2 == c2[d]).all(), f"dealer {d}"
     assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=D) == S.co.decrypt(S.sk, c1, c2)).all()
+
+
+def test_few_rows_take_the_cuda_core_kernel_by_default(pkg):
+    """one party decrypting many ciphertexts (the reference's decrypt_party_shares): rows = 1 -> no tensor-core tile is worth it"""
+    P = SETS["P128s"]()
+    D = 40
+    S = System(P, D, "u63")
+    c1, c2 = S.encrypt()
+    eng = load(pkg.Engine(**engine_kwargs(P)), S, D)      # default options
+    eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)            # 24 rows x 40 dealers: tensor cores
+    eng.set_option("profile", 2)
+    one = eng.decrypt_batch(np.array([5], dtype=np.uint32), S.sk[5:6], D=D)
+    assert eng.profile()["expand"][1] == 0                # no byte-plane conversion: the CUDA-core kernel ran
+    many = eng.decrypt_batch(np.arange(P.n, dtype=np.uint32), S.sk, D=D)
+    assert eng.profile()["expand"][1] >= 1                # 24 parties: tensor cores
+    eng.set_option("profile", 0)
+    want = S.co.decrypt(S.sk, c1, c2)
+    assert (one == want[5:6]).all() and (many == want).all()
 
 
 def test_odd_k_falls_back_to_the_imad_kernel(pkg):

@@ -1238,7 +1238,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
   if (c && name && std::string(name) == "imma_pair") { c->imma_pair = value != 0; return PVW_OK; }
   if (c && name && std::string(name) == "imma_min_dealers") { c->imma_min_dealers = std::max<int64_t>(1, value); return PVW_OK; }
   if (c && name && std::string(name) == "imma_min_rows") { c->imma_min_rows = std::max<int64_t>(1, value); return PVW_OK; }
-  if (c && name && std::string(name) == "imma_chunk_dealers") { c->imma_chunk_dealers = std::max<int64_t>(16, value); return PVW_OK; }
+  if (c && name && std::string(name) == "imma_chunk_dealers") { c->imma_chunk_dealers = std::min<int64_t>(std::max<int64_t>(16, value), 32768); return PVW_OK; }   // grid.y of the byte-plane kernel
   return guarded(c, [&] {
     require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");
     std::string n(name);

@@ -27,9 +27,9 @@ int main(int argc, char** argv) {
                       .set_secret_variance(0.5f).set_error_bounds_u32(50, 50) /* suggest_error_bounds for this set */.build_arc();
     printf("PVW parameters: n=%u t=%u k=%u l=%u, %zu moduli, delta=%llu, correctness condition: %s\n", params->n, params->t, params->k, params->l,
            params->L(), (unsigned long long)params->delta[0], params->verify_correctness_condition() ? "ok" : "VIOLATED");
-    Rng rng(2026);
+    Rng crs_rng, rng;   // OS-seeded CSPRNGs (the reference: thread_rng()); one for the public CRS, one for secrets
     auto t0 = clk::now();
-    PvwCrs crs = PvwCrs::new_random(params, rng);
+    PvwCrs crs = PvwCrs::new_random(params, crs_rng);
     GlobalPublicKey global_pk(crs);
     std::vector<Party> parties;
     for (uint32_t i = 0; i < num_parties; i++) {

@@ -12,8 +12,9 @@
  *  - every function returns 0 on success or a negative pvw_status that maps 1:1 onto a PvwError variant
  *    (src/errors.rs:11-70); pvw_last_error() returns the message.  No exception or abort crosses the boundary.
  *  - a context is bound to ONE CUDA device and ONE shard of parties [row0, row0+nrows) (rows of the global public
- *    key B).  One process per GPU; collectives (NCCL) are issued by the host layer on the device pointers that
- *    pvw_ct_c1_device_ptr() exposes.  A context is not thread-safe; guard it with a mutex (the Rust shim does).
+ *    key B).  One process per GPU; the one exchange of the path (c1 slices) is pvw_shard_* below (copy engines over NVLink), or a
+ *    collective of the host layer's choice (NCCL) on the device pointer pvw_ct_c1_device_ptr() exposes.  A context is not
+ *    thread-safe; guard it with a mutex (the Rust shim does).
  *  - `PVW_IO_DEVICE` in `flags` means the data pointers of that call are CUDA device pointers on the context's
  *    device (inputs already resident in HBM); otherwise they are host pointers and the call performs the copies.
  *    Device-pointer calls are asynchronous: they are queued on pvw_ctx_stream() and return at once, so the caller must
@@ -48,10 +49,19 @@ typedef enum {
 enum { PVW_IO_HOST = 0u, PVW_IO_DEVICE = 1u,
        /* pvw_encrypt_batch only: compute just c1 (dealers c1_lo..c1_hi) or just c2, so that a multi-GPU host layer can start the
           all-gather of the c1 slices while the (much larger) c2 product runs; m / e2 may be NULL with C1_ONLY, e1 with C2_ONLY */
-       PVW_ENC_C1_ONLY = 2u, PVW_ENC_C2_ONLY = 4u };
+       PVW_ENC_C1_ONLY = 2u, PVW_ENC_C2_ONLY = 4u,
+       /* element type of the small signed inputs.  Default: int64_t, the reference's `i64` coefficient type (SecretKey.secret_coeffs,
+          secret_key.rs:14-18; Poly::from_coefficients(&[i64]), encryption.rs:148).  The values are tiny -- CBD(variance <= 16) secrets
+          and randomness lie in [-32, 32], errors within the bounds of parameters.rs:110-114 -- so a host that feeds many dealers per
+          call can pass them narrow and cut the host-to-device volume 8x / 2-4x:
+            PVW_IN_SECRET_I8: r (pvw_encrypt_batch), sk (pvw_decrypt_batch, pvw_keygen_batch) are int8_t
+            PVW_IN_ERROR_I32 / _I16: e1, e2 (pvw_encrypt_batch), e (pvw_keygen_batch) are int32_t / int16_t
+          The pointers are `const void *` for that reason; without a flag they point to int64_t as before. */
+       PVW_IN_SECRET_I8 = 0x100u, PVW_IN_ERROR_I32 = 0x200u, PVW_IN_ERROR_I16 = 0x400u };
 
 /* Replaces PvwParametersBuilder::build (src/params/parameters.rs:117-195) + fhe-math Context::new.
- * Same validation: n > 0, k > 0, ell a power of two >= 8, moduli prime, < 2^62, = 1 mod 2*ell, distinct,
+ * Same validation: n > 0, k > 0, ell a power of two >= 8 (8, 16, 32 run on register-resident kernels, 64 .. 256 on generic ones;
+ * above 256 is rejected: no reference test, example or parameter recommendation goes past 32), moduli prime, < 2^62, = 1 mod 2*ell, distinct,
  * error bounds > 0 (bounds >= 2^63 are not representable here; the reference type is BigInt but every
  * call site uses <= u32, parameters.rs:110-114). */
 typedef struct {
@@ -105,8 +115,8 @@ int pvw_pk_num_keys(const pvw_ctx *ctx, uint32_t *num_keys);
 /* Batched key generation: PublicKey::generate (public_key.rs:111-147) + PvwCrs::multiply_by_secret_key
  * (crs.rs:138-171) for `count` parties starting at global index `row`, with the error e supplied explicitly:
  *   b_p[c] = sum_j NTT(s_p[j]) (.) A[j][c] + NTT(e_p[c]).   Rows land in the device-resident B. */
-int pvw_keygen_batch(pvw_ctx *ctx, uint32_t row, uint32_t count, const int64_t *sk /* [count][k][ell] */,
-                     const int64_t *e /* [count][k][ell] */, uint32_t flags);
+int pvw_keygen_batch(pvw_ctx *ctx, uint32_t row, uint32_t count, const void *sk /* [count][k][ell] int64_t (or PVW_IN_SECRET_I8) */,
+                     const void *e /* [count][k][ell] int64_t (or PVW_IN_ERROR_*) */, uint32_t flags);
 
 /* PvwCrs::multiply_by_randomness (crs.rs:177-205): out[i] = sum_j A[i][j] (.) r[j] for D independent vectors.
  * r_hat and out are NTT-form polynomials in the host layout.  len != k is the caller's DimensionMismatch. */
@@ -126,8 +136,9 @@ int pvw_ct_reserve(pvw_ctx *ctx, uint32_t capacity);
  * the store, see pvw_ct_c1_device_ptr).  e1 may be NULL when c1_lo == c1_hi.
  * Fails like the reference when the key is not full (:117) or the correctness condition is false (:124). */
 int pvw_encrypt_batch(pvw_ctx *ctx, uint32_t slot0, uint32_t D, uint32_t c1_lo, uint32_t c1_hi,
-                      const uint64_t *m /* [D][nrows] */, const int64_t *r /* [D][k][ell] */,
-                      const int64_t *e1 /* [D][k][ell] */, const int64_t *e2 /* [D][nrows][ell] */, uint32_t flags);
+                      const uint64_t *m /* [D][nrows] */, const void *r /* [D][k][ell] int64_t (or PVW_IN_SECRET_I8) */,
+                      const void *e1 /* [D][k][ell] int64_t (or PVW_IN_ERROR_*) */, const void *e2 /* [D][nrows][ell] likewise */,
+                      uint32_t flags);
 
 /* PvwCiphertext download / upload in the reference layout (c1 [k][L][ell], c2 [nrows][L][ell]); NULL = skip. */
 int pvw_ct_download(pvw_ctx *ctx, uint32_t slot, uint64_t *c1, uint64_t *c2);
@@ -142,7 +153,7 @@ int pvw_ct_c1_device_ptr(pvw_ctx *ctx, uint32_t slot, void **ptr, uint64_t *slot
  * This is the subset form of examples/pvw_valid_dec.rs:198-210; the "exactly n ciphertexts" rule of
  * decrypt_party_shares (:295) is enforced by the host layer. */
 int pvw_decrypt_batch(pvw_ctx *ctx, uint32_t D, const uint32_t *dealer_slots /* [D] host, or NULL */, uint32_t P,
-                      const uint32_t *party_idx /* [P] host */, const int64_t *sk /* [P][k][ell] */,
+                      const uint32_t *party_idx /* [P] host */, const void *sk /* [P][k][ell] int64_t (or PVW_IN_SECRET_I8) */,
                       uint64_t *out /* [P][D] */, uint32_t flags);
 
 /* decode_scalar_pvw_rns (decryption.rs:10-58) on `count` noisy polynomials given in the host layout. */
@@ -199,6 +210,30 @@ int pvw_wire_crs_deserialize(pvw_ctx *ctx, const uint8_t *in, uint64_t len, uint
 /* `count` polynomials in the host layout <-> `count` records (e.g. GlobalPublicKey.error_polynomials); host pointers */
 int pvw_wire_polys_serialize(pvw_ctx *ctx, uint32_t count, const uint64_t *polys /* [count][L][ell] */, uint8_t *out);
 int pvw_wire_polys_deserialize(pvw_ctx *ctx, uint32_t count, const uint8_t *in, uint64_t *polys /* [count][L][ell] */);
+
+/* ---- multi-GPU: the c1 exchange of the row-sharded contexts of one box (one process per GPU) --------------------
+ * Rows of B shard across the GPUs; c1 = A r + e1 does not.  Every rank computes c1 for its slice of a step's dealers
+ * (pvw_encrypt_batch c1_lo..c1_hi) and needs all of it to decrypt (decryption.rs:257-263 reads the whole c1).  The reference has
+ * no counterpart (single address space).  The exchange below runs on the COPY ENGINES over NVLink, under the c2 product, instead of
+ * an all-gather kernel that competes with it for the SMs:
+ *   setup   every rank: pvw_ct_reserve, pvw_shard_export(world) -> one pvw_shard_handle (CUDA IPC handles of its c1 store and of a
+ *           small flag array); the host layer all-gathers the `world` handles by any means (MPI, torch.distributed, a file) and gives
+ *           every rank the whole table: pvw_shard_connect(world, rank, handles).
+ *   step    pvw_encrypt_batch(... c1_lo, c1_hi ...); pvw_shard_push_c1(slot0 + c1_lo, c1_hi - c1_lo) queues, on a dedicated stream and
+ *           after the c1 product, one peer copy of the slice into every peer's store and an 8-byte counter write per peer;
+ *           pvw_shard_wait_c1() makes the context's compute stream wait (cuStreamWaitValue64) until every peer's slice of this
+ *           exchange has landed; then pvw_decrypt_batch; pvw_shard_release_c1() tells the peers that this rank's store may be
+ *           overwritten by the next exchange (their next push waits for it).  Every rank issues the same sequence of push / wait /
+ *           release calls; nothing synchronises the host.  The c1 product must be queued BEFORE the push, the c2 product after it
+ *           (PVW_ENC_C1_ONLY, then PVW_ENC_C2_ONLY) if the transfer is to overlap the c2 product.
+ *   pvw_ct_reserve is refused while connected (peers hold mappings of the store): pvw_shard_disconnect on every rank first. */
+typedef struct { uint8_t bytes[192]; } pvw_shard_handle;
+int pvw_shard_export(pvw_ctx *ctx, uint32_t world, pvw_shard_handle *out);
+int pvw_shard_connect(pvw_ctx *ctx, uint32_t world, uint32_t rank, const pvw_shard_handle *all /* [world] */);
+int pvw_shard_push_c1(pvw_ctx *ctx, uint32_t slot0, uint32_t count);
+int pvw_shard_wait_c1(pvw_ctx *ctx);
+int pvw_shard_release_c1(pvw_ctx *ctx);
+int pvw_shard_disconnect(pvw_ctx *ctx);
 
 /* blocks until all work queued by this context has finished; returns a sticky CUDA error if one occurred */
 int pvw_ctx_synchronize(pvw_ctx *ctx);

@@ -6,8 +6,11 @@
 // NTT form); matrices / vectors of polynomials are std::vector<uint64_t>.  The Rust shim of INTEGRATION.md is the same
 // code with `Poly` at the edges.
 #pragma once
+#include <sys/random.h>
+
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <mutex>
 #include <random>
@@ -42,7 +45,65 @@ class PvwError : public std::runtime_error {
   int status_;
 };
 
-using Rng = std::mt19937_64;
+// The reference samples secret keys, encryption randomness and errors from `thread_rng()`: `RngCore + CryptoRng`, ChaCha12 keyed
+// from the operating system (secret_key.rs:45-63, encryption.rs:138,164,180).  CryptoRng is the equivalent here: ChaCha20 keyed with
+// 32 bytes of getrandom(2), usable wherever a C++ UniformRandomBitGenerator is.  A general-purpose PRNG (std::mt19937_64, ...)
+// must never produce key material -- its state is recoverable from outputs -- so the samplers below accept nothing else.  Use one
+// generator for public values (PvwCrs::new_random) and another for secrets.
+class CryptoRng {
+ public:
+  using result_type = uint64_t;
+  static constexpr result_type min() { return 0; }
+  static constexpr result_type max() { return ~0ull; }
+  CryptoRng() {
+    uint8_t key[32];
+    size_t got = 0;
+    while (got < sizeof(key)) {
+      const ssize_t r = getrandom(key + got, sizeof(key) - got, 0);
+      if (r < 0) throw std::runtime_error("getrandom failed: no entropy source for key material");
+      got += (size_t)r;
+    }
+    init(key);
+    std::memset(key, 0, sizeof(key));
+  }
+  // Deterministic stream for reproducible tests and fixtures ONLY (the reference offers no such constructor on its samplers).
+  static CryptoRng from_seed_for_tests(const uint8_t (&key)[32]) { CryptoRng g(0); g.init(key); return g; }
+  CryptoRng(const CryptoRng&) = delete;             // two copies would emit the same "random" secrets
+  CryptoRng& operator=(const CryptoRng&) = delete;
+  CryptoRng(CryptoRng&&) = default;
+  result_type operator()() {
+    if (pos_ == 8) refill();
+    return buf_[pos_++];
+  }
+ private:
+  explicit CryptoRng(int) {}
+  void init(const uint8_t (&key)[32]) {
+    static const uint32_t sigma[4] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};   // "expand 32-byte k"
+    for (int i = 0; i < 4; i++) st_[i] = sigma[i];
+    for (int i = 0; i < 8; i++) st_[4 + i] = (uint32_t)key[4 * i] | (uint32_t)key[4 * i + 1] << 8 | (uint32_t)key[4 * i + 2] << 16 | (uint32_t)key[4 * i + 3] << 24;
+    st_[12] = st_[13] = st_[14] = st_[15] = 0;       // 64-bit block counter, 64-bit nonce 0 (one stream per key)
+    pos_ = 8;
+  }
+  static uint32_t rotl(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+  static void qr(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    a += b; d ^= a; d = rotl(d, 16); c += d; b ^= c; b = rotl(b, 12); a += b; d ^= a; d = rotl(d, 8); c += d; b ^= c; b = rotl(b, 7);
+  }
+  void refill() {                                    // one ChaCha20 block = eight 64-bit outputs
+    uint32_t x[16];
+    for (int i = 0; i < 16; i++) x[i] = st_[i];
+    for (int r = 0; r < 10; r++) {
+      qr(x[0], x[4], x[8], x[12]); qr(x[1], x[5], x[9], x[13]); qr(x[2], x[6], x[10], x[14]); qr(x[3], x[7], x[11], x[15]);
+      qr(x[0], x[5], x[10], x[15]); qr(x[1], x[6], x[11], x[12]); qr(x[2], x[7], x[8], x[13]); qr(x[3], x[4], x[9], x[14]);
+    }
+    for (int i = 0; i < 8; i++) buf_[i] = (uint64_t)(x[2 * i] + st_[2 * i]) | (uint64_t)(x[2 * i + 1] + st_[2 * i + 1]) << 32;
+    if (++st_[12] == 0) ++st_[13];
+    pos_ = 0;
+  }
+  uint32_t st_[16];
+  uint64_t buf_[8];
+  int pos_ = 8;
+};
+using Rng = CryptoRng;
 
 // sample_vec_cbd (src/sampling/uniform.rs:27-70) and sample_uniform_coefficients (:5-22), host side
 inline std::vector<int64_t> sample_vec_cbd(size_t n, float variance, Rng& rng) {
@@ -193,13 +254,24 @@ class GlobalPublicKey {
     ctx_->check(pvw_keygen_batch(ctx_->get(), party.index, 1, party.sk.secret_coeffs.data(), e.data(), PVW_IO_HOST));
   }
   // generate_all_party_keys (public_key.rs:376-401): one batched device call
+  // every key lands in row party.index (add_public_key, public_key.rs:214-250) whatever the order of the list; one device call
+  // per run of consecutive indices (a single call for the usual 0..len-1 list)
   void generate_all_party_keys(const std::vector<Party>& parties, Rng& rng) {
+    if (parties.size() > params->n) throw PvwError(PVW_ERR_INVALID_PARAMETERS, "Too many parties: " + std::to_string(parties.size()) + " > " + std::to_string(params->n));
     const size_t w = (size_t)params->k * params->l;
     std::vector<int64_t> sk(parties.size() * w);
-    for (size_t i = 0; i < parties.size(); i++) std::copy(parties[i].sk.secret_coeffs.begin(), parties[i].sk.secret_coeffs.end(), sk.begin() + i * w);
+    for (size_t i = 0; i < parties.size(); i++) {
+      if (parties[i].index >= params->n) throw PvwError(PVW_ERR_INDEX_OUT_OF_BOUNDS, "Party index " + std::to_string(parties[i].index) + " exceeds maximum " + std::to_string(params->n - 1));
+      std::copy(parties[i].sk.secret_coeffs.begin(), parties[i].sk.secret_coeffs.end(), sk.begin() + i * w);
+    }
     auto e = sample_uniform_coefficients(params->error_bound_1, parties.size() * w, rng);
     std::lock_guard<std::mutex> g(ctx_->mu);
-    ctx_->check(pvw_keygen_batch(ctx_->get(), 0, (uint32_t)parties.size(), sk.data(), e.data(), PVW_IO_HOST));
+    for (size_t start = 0; start < parties.size();) {
+      size_t stop = start + 1;
+      while (stop < parties.size() && parties[stop].index == parties[stop - 1].index + 1) stop++;
+      ctx_->check(pvw_keygen_batch(ctx_->get(), parties[start].index, (uint32_t)(stop - start), sk.data() + start * w, e.data() + start * w, PVW_IO_HOST));
+      start = stop;
+    }
   }
   std::vector<uint64_t> get_public_key(uint32_t index) const {                         // k polynomials of row `index`
     std::vector<uint64_t> row((size_t)params->k * params->poly_words());

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libpvw_b200.so")
 PVW_OK = 0
 PVW_IO_HOST, PVW_IO_DEVICE = 0, 1
 PVW_ENC_C1_ONLY, PVW_ENC_C2_ONLY = 2, 4
+PVW_IN_SECRET_I8, PVW_IN_ERROR_I32, PVW_IN_ERROR_I16 = 0x100, 0x200, 0x400
 STATUS_NAMES = {
     0: "Ok", -1: "InvalidParameters", -2: "DimensionMismatch", -3: "IndexOutOfBounds", -4: "EncryptionError",
     -5: "DecryptionError", -6: "KeyGenerationError", -7: "InternalError", -8: "DeserializationError", -9: "InsufficientData",
@@ -30,6 +31,10 @@ class PvwParamsDesc(C.Structure):
 class PvwWireLayout(C.Structure):
     _fields_ = [(name, C.c_uint64) for name in ("poly_bytes", "record_bytes", "params_bytes", "pk_row_bytes", "ciphertext_bytes",
                                                 "crs_bytes", "ct_c1_offset", "ct_c2_offset", "ct_params_offset")]
+
+
+class PvwShardHandle(C.Structure):
+    _fields_ = [("bytes", C.c_uint8 * 192)]
 
 
 _vp, _u32, _u64, _i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64
@@ -72,6 +77,12 @@ SIGNATURES = {
     "pvw_wire_crs_deserialize": (C.c_int, [_vp, _vp, _u64, _u32]),
     "pvw_wire_polys_serialize": (C.c_int, [_vp, _u32, _vp, _vp]),
     "pvw_wire_polys_deserialize": (C.c_int, [_vp, _u32, _vp, _vp]),
+    "pvw_shard_export": (C.c_int, [_vp, _u32, C.POINTER(PvwShardHandle)]),
+    "pvw_shard_connect": (C.c_int, [_vp, _u32, _u32, C.POINTER(PvwShardHandle)]),
+    "pvw_shard_push_c1": (C.c_int, [_vp, _u32, _u32]),
+    "pvw_shard_wait_c1": (C.c_int, [_vp]),
+    "pvw_shard_release_c1": (C.c_int, [_vp]),
+    "pvw_shard_disconnect": (C.c_int, [_vp]),
     "pvw_ctx_synchronize": (C.c_int, [_vp]),
     "pvw_ctx_stream": (_vp, [_vp]),
     "pvw_ctx_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),

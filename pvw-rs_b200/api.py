@@ -25,8 +25,46 @@ _U64 = (1 << 64) - 1
 # --------------------------------------------------------------------------------------------------------------
 # sampling (host) -- src/sampling/uniform.rs
 # --------------------------------------------------------------------------------------------------------------
-def _rng(rng) -> np.random.Generator:
-    return rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+class _OsRng:
+    """Uniform integers drawn from the operating system's CSPRNG (os.urandom = getrandom(2)).  The reference samples keys,
+    randomness and errors from `thread_rng()`, a CryptoRng (ChaCha12 seeded from the OS); numpy's generators (PCG64,
+    MT19937, ...) are not cryptographic and must never produce secret material."""
+
+    def integers(self, low, high=None, size=None, dtype=np.int64):
+        import os
+        if high is None:
+            low, high = 0, low
+        low, high = int(low), int(high)
+        span = high - low
+        if span <= 0:
+            raise ValueError("empty range")
+        shape = () if size is None else ((size,) if np.isscalar(size) else tuple(size))
+        count = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        if span & (span - 1) == 0 and span <= 256:                  # power of two <= 256: one byte each, no rejection
+            x = np.frombuffer(os.urandom(count), dtype=np.uint8).astype(np.uint64) & np.uint64(span - 1)
+        else:
+            wdt, bits = (np.uint32, 32) if span <= (1 << 16) else (np.uint64, 64)
+            limit = ((1 << bits) // span) * span                      # rejection sampling: accept draws below the largest multiple of span
+            x = np.empty(count, dtype=np.uint64)
+            todo = np.arange(count)
+            while len(todo):
+                draw = np.frombuffer(os.urandom(len(todo) * (bits // 8)), dtype=wdt).astype(np.uint64)
+                ok = draw < np.uint64(limit) if limit < (1 << 64) else np.ones(len(draw), dtype=bool)
+                x[todo[ok]] = draw[ok] % np.uint64(span)
+                todo = todo[~ok]
+        if low >= 0 and high <= (1 << 64) and np.dtype(dtype) == np.uint64:
+            out = x + np.uint64(low)
+        else:
+            out = (x.astype(np.int64) + np.int64(low)).astype(dtype)
+        return out.reshape(shape) if shape else out[0]
+
+
+def _rng(rng):
+    """None -> the OS CSPRNG (production).  A numpy Generator or an integer seed gives a reproducible NON-cryptographic stream:
+    for tests and fixtures only (the reference has no such option; its samplers take `RngCore + CryptoRng`)."""
+    if rng is None:
+        return _OsRng()
+    return rng if isinstance(rng, (np.random.Generator, _OsRng)) else np.random.default_rng(rng)
 
 
 def sample_uniform_coefficients(bound: int, num_coeffs: int, rng=None) -> np.ndarray:
@@ -406,15 +444,28 @@ class GlobalPublicKey:
         return self.error_polynomials
 
     def generate_all_party_keys(self, parties: Sequence[Party], rng=None, errors=None):
-        """public_key.rs:376-401: parties' indices must be 0..len-1 in order; one batched device keygen"""
+        """public_key.rs:376-401: every key lands in row party.index() (add_public_key, :214-250), whatever the order of the list;
+        one batched device keygen per run of consecutive indices (a single call for the usual 0..len-1 list)"""
         P = self.params
         if len(parties) > P.n:
             raise PvwError("InvalidParameters", f"Too many parties: {len(parties)} > {P.n}")
+        for p in parties:
+            if not 0 <= p.index() < P.n:
+                raise PvwError("IndexOutOfBounds", f"Party index {p.index()} exceeds maximum {P.n - 1}")
         sk = np.stack([p.secret_key().secret_coeffs for p in parties]) if parties else np.zeros((0, P.k, P.l), np.int64)
         e = (sample_uniform_coefficients(P.error_bound_1, len(parties) * P.k * P.l, rng).reshape(len(parties), P.k, P.l)
              if errors is None else np.asarray(errors, np.int64))
+        if e.shape != sk.shape:
+            raise PvwError("DimensionMismatch", f"errors: expected {sk.shape}, got {e.shape}")
+        idx = [p.index() for p in parties]
         with self._lock:
-            self.engine.keygen_batch(0, sk, e)
+            start = 0
+            while start < len(idx):
+                stop = start + 1
+                while stop < len(idx) and idx[stop] == idx[stop - 1] + 1:
+                    stop += 1
+                self.engine.keygen_batch(idx[start], sk[start:stop], e[start:stop])
+                start = stop
 
     def generate_all_keys(self, secret_keys: Sequence[SecretKey], rng=None, errors=None):
         """public_key.rs:407-434"""
@@ -448,9 +499,12 @@ class _SlotPool:
         self.resident: "dict[int, weakref.ref]" = {}
         self.order: List[int] = []
 
-    def take(self, owner: "PvwCiphertext") -> int:
+    def take(self, owner: "PvwCiphertext", pinned=()) -> int:
+        """a slot for `owner`; slots in `pinned` (ciphertexts of the call in progress) are never spilled"""
         if not self.free:
             for s in list(self.order):
+                if s in pinned:
+                    continue
                 ct = self.resident[s]()
                 if ct is not None:
                     ct._spill()
@@ -458,6 +512,8 @@ class _SlotPool:
                     self._release(s)
                 if self.free:
                     break
+        if not self.free:
+            raise PvwError("InvalidParameters", "every ciphertext slot is pinned by the call in progress")
         s = self.free.pop()
         self.resident[s] = weakref.ref(owner)
         self.order.append(s)
@@ -505,9 +561,9 @@ class PvwCiphertext:
             self._pk._slots._release(self._slot)
             self._slot = None
 
-    def _resident_slot(self) -> int:
+    def _resident_slot(self, pinned=()) -> int:
         if self._slot is None:
-            self._slot = self._pk._slots.take(self)
+            self._slot = self._pk._slots.take(self, pinned)
             self._pk.engine.ct_upload(self._slot, self._c1, self._c2)
         return self._slot
 
@@ -585,10 +641,15 @@ def _encrypt_many(all_scalars: np.ndarray, global_pk: GlobalPublicKey, randomnes
 
 
 def _as_scalars(x, what: str) -> np.ndarray:
+    """&[u64] of the reference: anything outside [0, 2^64) is not representable there and is rejected, not wrapped"""
     try:
-        return np.array([int(v) & _U64 for v in x], dtype=np.uint64)
-    except TypeError:
+        vals = [int(v) for v in x]
+    except (TypeError, ValueError):
         raise PvwError("InvalidParameters", f"{what} must be a sequence of u64")
+    for v in vals:
+        if not 0 <= v <= _U64:
+            raise PvwError("InvalidParameters", f"{what}: {v} does not fit u64")
+    return np.array(vals, dtype=np.uint64)
 
 
 def encrypt(scalars: Sequence[int], global_pk: GlobalPublicKey, randomness=None) -> PvwCiphertext:
@@ -661,7 +722,14 @@ def decrypt_party_shares(all_ciphertexts: Sequence[PvwCiphertext], secret_key: S
     pk = all_ciphertexts[0]._pk
     with pk._lock:
         if len(all_ciphertexts) <= pk.engine.capacity:
-            slots = [ct._resident_slot() for ct in all_ciphertexts]
+            # making a spilled ciphertext resident may evict another one: never one of THIS list (its recorded slot would then hold
+            # a different ciphertext and a dealer would silently be decrypted from the wrong data)
+            slots, pinned = [], set()
+            for ct in all_ciphertexts:
+                s = ct._resident_slot(pinned)
+                pinned.add(s)
+                slots.append(s)
+            assert all(ct._slot == s for ct, s in zip(all_ciphertexts, slots))
             out = pk.engine.decrypt_batch([party_index], secret_key.secret_coeffs[None], dealer_slots=slots)
             return [int(v) for v in out[0]]
     return [decrypt_party_value(ct, secret_key, party_index) for ct in all_ciphertexts]

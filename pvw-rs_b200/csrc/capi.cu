@@ -8,6 +8,7 @@
 //   c1   u64[cap][L][k][ell]        ciphertext store, PvwCiphertext.c1             encryption.rs:15-24
 //   c2   u64[cap][L][nrows][ell]                      PvwCiphertext.c2 (local rows)
 // Host layout at the boundary is always the reference's: polynomial = u64[L][ell] row-major.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -85,6 +86,7 @@ struct pvw_ctx {
   const uint8_t *env_k = nullptr, *env_n = nullptr, *env_params = nullptr;
   int* wire_err = nullptr;
   uint64_t rq_bytes = 0;
+  std::vector<uint32_t> h_idxp;  // local party indices of the current decrypt call
   std::string err;
   uint64_t launches = 0;
   // optional per-kernel-kind CUDA-event timing (bench.py's roofline leg): events bracket each launch on `stream`
@@ -104,6 +106,19 @@ struct pvw_ctx {
   bool As_valid = false, Bs_valid = false;
   int64_t decrypt_chunk_shares = 1 << 19;
   int64_t upload_chunk_bytes = 256ll << 20;
+  // multi-GPU c1 exchange over the copy engines (pvw_shard_*): peers' ciphertext stores and flag arrays mapped through CUDA IPC
+  struct Shard {
+    uint32_t world = 0, rank = 0;
+    std::vector<u64*> peer_c1;          // [world] IPC mappings of the peers' c1 stores (own entry: the local store)
+    std::vector<u64*> peer_flags;       // [world] IPC mappings of the peers' flag arrays
+    u64* flags = nullptr;               // local: [0, world) data counters written by the peers' pushes, [world, 2 world) their acks,
+                                        //        [2 world], [2 world + 1] staging words for the values this rank sends
+    uint32_t flags_world = 0;           // the world size `flags` was allocated for
+    u64 push_seq = 0, wait_seq = 0;
+    cudaStream_t xstream = nullptr;     // the exchange stream (copy engines only)
+    cudaEvent_t ev_c1 = nullptr;
+    bool connected = false;
+  } sh;
 
   size_t poly() const { return (size_t)hp.L * hp.ell; }
   void use() { CUDA_CHECK(cudaSetDevice(device)); }
@@ -331,12 +346,30 @@ void download_polys(pvw_ctx* c, const u64* src, size_t src_limb_stride, uint64_t
 
 void require(bool cond, int code, const std::string& msg) { if (!cond) throw PvwException(code, msg); }
 
+// element size of the small signed inputs of a call (pvw_b200.h PVW_IN_*): secrets / randomness, and errors
+int secret_bytes(uint32_t flags) { return (flags & PVW_IN_SECRET_I8) ? 1 : 8; }
+int error_bytes(uint32_t flags) {
+  require(!((flags & PVW_IN_ERROR_I32) && (flags & PVW_IN_ERROR_I16)), PVW_ERR_INVALID_PARAMETERS, "PVW_IN_ERROR_I32 and PVW_IN_ERROR_I16 exclude each other");
+  return (flags & PVW_IN_ERROR_I32) ? 4 : (flags & PVW_IN_ERROR_I16) ? 2 : 8;
+}
+const void* at_bytes(const void* p, size_t bytes) { return reinterpret_cast<const uint8_t*>(p) + bytes; }
+
+// ntt.cu: small signed coefficients (element size cbytes) -> NTT form in one of the device layouts
+void ntt(pvw_ctx* c, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out, size_t vstride, size_t lstride,
+         bool accumulate = false, bool pack_out = false, int planes = 0, const u64* addend = nullptr) {
+  bool ok = true;
+  launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_ntt_small(c->T, coef, cbytes, m, count, inner, out, vstride, lstride, c->stream, accumulate, pack_out, planes, addend); });
+  require(ok, PVW_ERR_INTERNAL, "forward NTT: unsupported shape (ring degree above 256 or more than 2^31 thread blocks)");
+}
+
 void gemm(pvw_ctx* c, GemmArgs a) {
   a.tile = c->gemm_tile;
   a.refill_lag = a.D == 1 ? 1 : c->refill_lag;  // the HBM-bound matrix-vector form wants the deepest prefetch
   // algorithmic bytes: per (dealer, row) one k-polynomial operand row read + one polynomial written
   const double bytes = (double)a.D * a.rows * (a.k + 1.0) * a.L * a.ell * 8.0;
-  launch(c, PVW_KERNEL_MAC, bytes, [&] { launch_mac_gemm(a, c->gemm_impl, c->stream); });
+  bool ok = true;
+  launch(c, PVW_KERNEL_MAC, bytes, [&] { ok = launch_mac_gemm(a, c->gemm_impl, c->stream); });
+  require(ok, PVW_ERR_INTERNAL, "matrix product: unsupported shape");
 }
 
 // ---- tensor-core product (imma.cu) --------------------------------------------------------------------------------
@@ -354,7 +387,9 @@ const uint8_t* planes_A(pvw_ctx* c) {
   const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, kp = imma_kp(k);
   if (!c->As_valid) {
     planes_clear(c, c->As, (size_t)L * ell * k * 8 * kp);
-    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_planes_m(c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, k, k, L, ell, c->As.as<uint8_t>(), (size_t)k * 8 * kp, true, c->stream); });
+    bool ok = true;
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { ok = launch_imma_planes_m(c->A.as<u64>(), (size_t)k * k * ell, (size_t)k * ell, k, k, L, ell, c->As.as<uint8_t>(), (size_t)k * 8 * kp, true, c->stream); });
+    require(ok, PVW_ERR_INTERNAL, "byte-plane conversion of A: launch grid too large");
     c->As_valid = true;
   }
   return c->As.as<uint8_t>();
@@ -363,7 +398,9 @@ const uint8_t* planes_B(pvw_ctx* c) {
   const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows, kp = imma_kp(k);
   if (!c->Bs_valid) {
     planes_clear(c, c->Bs, (size_t)L * ell * nrows * 8 * kp);
-    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { launch_imma_planes_m(c->B.as<u64>(), (size_t)nrows * k * ell, (size_t)k * ell, nrows, k, L, ell, c->Bs.as<uint8_t>(), (size_t)nrows * 8 * kp, true, c->stream); });
+    bool ok = true;
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { ok = launch_imma_planes_m(c->B.as<u64>(), (size_t)nrows * k * ell, (size_t)k * ell, nrows, k, L, ell, c->Bs.as<uint8_t>(), (size_t)nrows * 8 * kp, true, c->stream); });
+    require(ok, PVW_ERR_INTERNAL, "byte-plane conversion of B: launch grid too large");
     c->Bs_valid = true;
   }
   return c->Bs.as<uint8_t>();
@@ -446,9 +483,15 @@ int pvw_ctx_create(pvw_ctx** out, const pvw_params_desc* d) {
   }
 }
 
+static void shard_disconnect(pvw_ctx* c);
+
 void pvw_ctx_destroy(pvw_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  shard_disconnect(c);
+  if (c->sh.flags) cudaFree(c->sh.flags);
+  if (c->sh.xstream) cudaStreamDestroy(c->sh.xstream);
+  if (c->sh.ev_c1) cudaEventDestroy(c->sh.ev_c1);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -577,7 +620,7 @@ int pvw_pk_num_keys(const pvw_ctx* c, uint32_t* num_keys) {
   return PVW_OK;
 }
 
-int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk, const int64_t* e, uint32_t flags) {
+int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const void* sk, const void* e, uint32_t flags) {
   return guarded(c, [&] {
     if (count == 0) return;
     require(sk && e, PVW_ERR_INVALID_PARAMETERS, "sk / e is null");
@@ -586,16 +629,16 @@ int pvw_keygen_batch(pvw_ctx* c, uint32_t row, uint32_t count, const int64_t* sk
     ensure_B(c);
     ensure_At(c);
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell;
-    const size_t small = (size_t)count * k * ell * 8;
-    const long long* d_sk = (const long long*)stage_in(c, c->in_small, sk, small, flags);
-    const long long* d_e = (const long long*)stage_in(c, c->in_small2, e, small, flags);
+    const int sb = secret_bytes(flags), eb = error_bytes(flags);
+    const size_t small = (size_t)count * k * ell;
+    const void* d_sk = stage_in(c, c->in_small, sk, small * sb, flags);
+    const void* d_e = stage_in(c, c->in_small2, e, small * eb, flags);
     // s_hat[p][limb][j][ell]
     c->rhat.ensure((size_t)count * L * k * ell * 8);
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, c->stream, false, true); });
+    ntt(c, d_sk, sb, nullptr, (uint64_t)count * k, k, c->rhat.as<u64>(), (size_t)L * k * ell, (size_t)k * ell, false, true);
     // B rows <- NTT(e): item idx = p*k + cidx lands at B[limb][row+p][cidx]
     u64* Brow = c->B.as<u64>() + (size_t)(row - c->row0) * k * ell;
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e, nullptr, (uint64_t)count * k, (uint32_t)std::min<uint64_t>((uint64_t)count * k, 0xFFFFFFFFu), Brow, 0,
-                     (size_t)c->nrows * k * ell, c->stream); });
+    ntt(c, d_e, eb, nullptr, (uint64_t)count * k, (uint32_t)std::min<uint64_t>((uint64_t)count * k, 0xFFFFFFFFu), Brow, 0, (size_t)c->nrows * k * ell);
     GemmArgs g{};
     g.M = c->At.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
     g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell;
@@ -637,6 +680,7 @@ int pvw_ct_reserve(pvw_ctx* c, uint32_t capacity) {
   return guarded(c, [&] {
     const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell, w2 = (size_t)c->hp.L * c->nrows * c->hp.ell;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    require(!c->sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_ct_reserve: peers hold IPC mappings of this store; call pvw_shard_disconnect on every rank first");
     c->c1s.release(); c->c2s.release();
     c->cap = 0;
     if (capacity == 0) return;
@@ -648,8 +692,8 @@ int pvw_ct_reserve(pvw_ctx* c, uint32_t capacity) {
   });
 }
 
-int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, uint32_t c1_hi, const uint64_t* m, const int64_t* r,
-                      const int64_t* e1, const int64_t* e2, uint32_t flags) {
+int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, uint32_t c1_hi, const uint64_t* m, const void* r,
+                      const void* e1, const void* e2, uint32_t flags) {
   return guarded(c, [&] {
     if (D == 0) return;
     const HostParams& hp = c->hp;
@@ -672,31 +716,32 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     const bool host = !(flags & PVW_IO_DEVICE);
     // copy order matters (one host-to-device DMA queue): the small inputs the first kernels need go first, then the big
     // ones (e2, m) on the copy stream, waited for only after the c2 product
-    const long long* d_r = (const long long*)stage_in(c, c->in_small, r, (size_t)D * k * ell * 8, flags);
-    const long long* d_e1 = nullptr;
+    const int sb = secret_bytes(flags), eb = error_bytes(flags);
+    const void* d_r = stage_in(c, c->in_small, r, (size_t)D * k * ell * sb, flags);
+    const void* d_e1 = nullptr;
     if (c1_hi > c1_lo)
-      d_e1 = (const long long*)stage_in(c, c->in_small2, e1 + (size_t)c1_lo * k * ell, (size_t)(c1_hi - c1_lo) * k * ell * 8, flags);
-    const long long* d_e2 = do_c2 ? (const long long*)stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * 8, flags, c->ev[0]) : nullptr;
+      d_e1 = stage_in(c, c->in_small2, at_bytes(e1, (size_t)c1_lo * k * ell * eb), (size_t)(c1_hi - c1_lo) * k * ell * eb, flags);
+    const void* d_e2 = do_c2 ? stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * eb, flags, c->ev[0]) : nullptr;
     const u64* d_m = do_c2 ? (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]) : nullptr;
     // r_hat (encryption.rs:147-154): operand form [d][limb][j][ell] for the IMAD kernel, byte planes for the tensor-core one
     const bool imma = imma_wanted(c, nrows, D);
     const uint32_t kp = imma_kp(k);
     if (imma) {
       planes_clear(c, c->Vx, (size_t)L * ell * D * 8 * kp);
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->Vx.as<u64>(), kp, (size_t)D * 8 * kp, c->stream, false, false, 2); });
+      ntt(c, d_r, sb, nullptr, (uint64_t)D * k, k, c->Vx.as<u64>(), kp, (size_t)D * 8 * kp, false, false, 2);
     } else {
       c->rhat.ensure((size_t)D * w1 * 8);
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_r, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, c->stream, false, true); });
+      ntt(c, d_r, sb, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, false, true);
     }
     u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
     // c1 <- NTT(e1)   (encryption.rs:161-167); c1 += A r_hat below   (crs.rs:187-199, encryption.rs:171-173)
     if (c1_hi > c1_lo)
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e1, nullptr, (uint64_t)(c1_hi - c1_lo) * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell, c->stream); });
+      ntt(c, d_e1, eb, nullptr, (uint64_t)(c1_hi - c1_lo) * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell);
     // device inputs: c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
     // host inputs:   c2 <- B r_hat first (it does not need e2 / m, whose copy is still in flight), then c2 += NTT(e2) + m g_hat
     auto preload = [&](bool accumulate) {
-      launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_e2, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, c->stream, accumulate); });
+      ntt(c, d_e2, eb, d_m, (uint64_t)D * nrows, nrows, c2, w2, (size_t)nrows * ell, accumulate);
     };
     if (!host && !imma && do_c2) preload(false);
     if (imma) {
@@ -724,10 +769,8 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
           g.d_first = dc0; g.D = Dc; g.O = c->prod.as<u64>();
           imma_launch(c, g);
           if (host && dc0 == 0) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));   // e2 / m arrive under the first product
-          launch(c, PVW_KERNEL_NTT, 0.0, [&] {
-            launch_ntt_small(c->T, d_e2 + (size_t)dc0 * nrows * ell, d_m + (size_t)dc0 * nrows, (uint64_t)Dc * nrows, nrows, c2 + (size_t)dc0 * w2, w2,
-                             (size_t)nrows * ell, c->stream, false, false, 0, c->prod.as<u64>());
-          });
+          ntt(c, at_bytes(d_e2, (size_t)dc0 * nrows * ell * eb), eb, d_m + (size_t)dc0 * nrows, (uint64_t)Dc * nrows, nrows, c2 + (size_t)dc0 * w2, w2,
+              (size_t)nrows * ell, false, false, 0, c->prod.as<u64>());
         }
       }
     } else {
@@ -788,12 +831,14 @@ static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds,
   const uint64_t S = (uint64_t)Pc * D;
   c->y.ensure(decode_scratch_words_y(c->T, S) * 8);
   c->X.ensure(decode_scratch_words_X(c->T, S) * 8);
-  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream, z_cs, sub); });
+  bool ok = true;
+  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { ok = launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream, z_cs, sub); });
+  require(ok, PVW_ERR_INTERNAL, "decode: unsupported shape");
   launch(c, PVW_KERNEL_CRT_LIFT, 0.0, [&] { launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream); });
   launch(c, PVW_KERNEL_DECODE_TAIL, 0.0, [&] { launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream); });
 }
 
-int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint32_t P, const uint32_t* party_idx, const int64_t* sk,
+int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint32_t P, const uint32_t* party_idx, const void* sk,
                       uint64_t* out, uint32_t flags) {
   return guarded(c, [&] {
     if (D == 0 || P == 0) return;
@@ -805,7 +850,8 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     } else {
       require(D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("%u ciphertexts requested, %u reserved", D, c->cap));
     }
-    std::vector<uint32_t> local(P);
+    std::vector<uint32_t>& local = c->h_idxp;   // owned by the context: nothing here goes out of scope under an async copy
+    local.resize(P);
     for (uint32_t p = 0; p < P; p++) {
       // decrypt_party_shares: party_index >= n, decryption.rs:303-309
       if (party_idx[p] >= c->hp.n) throw PvwException(PVW_ERR_INVALID_PARAMETERS, fmt("Party index %u exceeds maximum %u", party_idx[p], c->hp.n - 1));
@@ -821,13 +867,15 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       CUDA_CHECK(cudaMemcpyAsync(c->idxd.p, dealer_slots, (size_t)D * 4, cudaMemcpyHostToDevice, c->stream));
       d_slots = c->idxd.as<uint32_t>();
     }
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // `local` goes out of scope below only after use; keep it simple and safe
+    // (both copies read pageable host memory: cudaMemcpyAsync returns once the source has been staged, so neither the caller's
+    //  dealer_slots nor h_idxp needs to outlive this call and the stream is not synchronised)
     const bool host = !(flags & PVW_IO_DEVICE);
-    const long long* d_sk = reinterpret_cast<const long long*>(sk);
+    const int sb = secret_bytes(flags);
+    const void* d_sk = sk;
     u64* d_out = reinterpret_cast<u64*>(out);
     if (host) {
-      c->in_small.ensure((size_t)P * k * ell * 8);
-      d_sk = c->in_small.as<long long>();
+      c->in_small.ensure((size_t)P * k * ell * sb);
+      d_sk = c->in_small.p;
       c->outd.ensure((size_t)P * D * 8);
       d_out = c->outd.as<u64>();
     }
@@ -857,7 +905,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       for (uint32_t p0 = 0; p0 < P; i++) {
         const uint32_t Pc = chunks[i];
         if (c->chunk_ev.size() <= i) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->chunk_ev.push_back(e); }
-        CUDA_CHECK(cudaMemcpyAsync(c->in_small.as<long long>() + (size_t)p0 * k * ell, sk + (size_t)p0 * k * ell, (size_t)Pc * k * ell * 8,
+        CUDA_CHECK(cudaMemcpyAsync(c->in_small.as<uint8_t>() + (size_t)p0 * k * ell * sb, at_bytes(sk, (size_t)p0 * k * ell * sb), (size_t)Pc * k * ell * sb,
                                    cudaMemcpyHostToDevice, c->copy_stream));
         CUDA_CHECK(cudaEventRecord(c->chunk_ev[i], c->copy_stream));
         p0 += Pc;
@@ -867,10 +915,12 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       const uint32_t Dc = std::min(Dstep, D - dc0);
       if (imma) {  // byte planes of this chunk's c1 (the store holds the operand form)
         planes_clear(c, c->Vx, (size_t)L * ell * Dc * 8 * kp);
+        bool ok = true;
         launch(c, PVW_KERNEL_EXPAND, (double)Dc * L * k * ell * 16.0, [&] {
-          launch_imma_planes_v(d_slots ? c->c1s.as<u64>() : c->c1s.as<u64>() + (size_t)dc0 * L * k * ell, (size_t)L * k * ell, (size_t)k * ell, ell, Dc, k, L,
+          ok = launch_imma_planes_v(d_slots ? c->c1s.as<u64>() : c->c1s.as<u64>() + (size_t)dc0 * L * k * ell, (size_t)L * k * ell, (size_t)k * ell, ell, Dc, k, L,
                                c->Vx.as<uint8_t>(), (size_t)Dc * 8 * kp, true, d_slots ? d_slots + dc0 : nullptr, c->stream);
         });
+        require(ok, PVW_ERR_INTERNAL, "byte-plane conversion of c1: launch grid too large");
       }
       uint32_t chunk_no = 0;
       for (uint32_t p0 = 0; p0 < P; chunk_no++) {
@@ -879,7 +929,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
         // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274), with
         // s_hat = SecretKey::get_polynomial (secret_key.rs:98-112) computed once per party, not per ciphertext
         if (imma) {
-          launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, c->stream, false, false, 1); });
+          ntt(c, at_bytes(d_sk, (size_t)p0 * k * ell * sb), sb, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, false, false, 1);
           // the product is stored alone, slot-major (lanes of a warp = consecutive parties: full-sector stores); c2 is
           // subtracted by the decode kernel, which reads both with unit stride
           ImmaArgs g{};
@@ -889,7 +939,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
           g.k = k; g.L = L; g.ell = ell; g.mode = 2; g.lc = c->T.lc;
           imma_launch(c, g);
         } else {
-          launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, d_sk + (size_t)p0 * k * ell, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, c->stream, false, true); });
+          ntt(c, at_bytes(d_sk, (size_t)p0 * k * ell * sb), sb, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, false, true);
           GemmArgs g{};
           g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;
           g.V = c->c1s.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell; g.V_dmap = d_slots;
@@ -944,7 +994,7 @@ int pvw_ntt_forward_small(pvw_ctx* c, uint32_t count, const int64_t* coeffs, uin
     c->in_small.ensure((size_t)count * c->hp.ell * 8);
     c->stage.ensure((size_t)count * poly * 8);
     CUDA_CHECK(cudaMemcpyAsync(c->in_small.p, coeffs, (size_t)count * c->hp.ell * 8, cudaMemcpyHostToDevice, c->stream));
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, c->in_small.as<long long>(), nullptr, count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream); });
+    ntt(c, c->in_small.p, 8, nullptr, count, 1, c->stage.as<u64>(), poly, c->hp.ell);
     CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -960,7 +1010,7 @@ int pvw_encode_scalars(pvw_ctx* c, uint32_t count, const uint64_t* m, uint64_t* 
     c->stage.ensure((size_t)count * poly * 8);
     CUDA_CHECK(cudaMemsetAsync(c->in_small.p, 0, (size_t)count * c->hp.ell * 8, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(c->in_m.p, m, (size_t)count * 8, cudaMemcpyHostToDevice, c->stream));
-    launch(c, PVW_KERNEL_NTT, 0.0, [&] { launch_ntt_small(c->T, c->in_small.as<long long>(), c->in_m.as<u64>(), count, 1, c->stage.as<u64>(), poly, c->hp.ell, c->stream); });
+    ntt(c, c->in_small.p, 8, c->in_m.as<u64>(), count, 1, c->stage.as<u64>(), poly, c->hp.ell);
     CUDA_CHECK(cudaMemcpyAsync(out, c->stage.p, (size_t)count * poly * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
@@ -1076,29 +1126,38 @@ int pvw_wire_ct_deserialize(pvw_ctx* c, uint32_t slot0, uint32_t D, const uint8_
     const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
     const bool host = !(flags & PVW_IO_DEVICE);
     const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.ct) : D;
-    for (uint32_t d0 = 0; d0 < D; d0 += per) {
-      const uint32_t Dc = std::min(per, D - d0);
-      const uint8_t* dev = in + (size_t)d0 * stride;
-      size_t ds = stride;
-      if (host) {
-        c->wire_buf.ensure((size_t)Dc * z.ct);
-        CUDA_CHECK(cudaMemcpy2DAsync(c->wire_buf.p, z.ct, in + (size_t)d0 * stride, stride, z.ct, Dc, cudaMemcpyHostToDevice, c->stream));
-        dev = c->wire_buf.as<uint8_t>(); ds = z.ct;
+    // Host input larger than one staging chunk: validate EVERY chunk before the first store write, so that a malformed blob
+    // anywhere in the batch leaves the store untouched (the reference returns Err without side effects); a single chunk is
+    // validated and written in one residency.
+    const bool two_pass = D > per;
+    for (int pass = two_pass ? 0 : 1; pass < 2; pass++) {
+      for (uint32_t d0 = 0; d0 < D; d0 += per) {
+        const uint32_t Dc = std::min(per, D - d0);
+        const uint8_t* dev = in + (size_t)d0 * stride;
+        size_t ds = stride;
+        if (host) {
+          c->wire_buf.ensure((size_t)Dc * z.ct);
+          CUDA_CHECK(cudaMemcpy2DAsync(c->wire_buf.p, z.ct, in + (size_t)d0 * stride, stride, z.ct, Dc, cudaMemcpyHostToDevice, c->stream));
+          dev = c->wire_buf.as<uint8_t>(); ds = z.ct;
+        }
+        u64* c1 = c->c1s.as<u64>() + (size_t)(slot0 + d0) * w1;
+        u64* c2 = c->c2s.as<u64>() + (size_t)(slot0 + d0) * w2;
+        const uint8_t* r2 = dev + z.row + 8 + (size_t)c->row0 * z.rec;
+        if (pass == 0 || !two_pass) {
+          wire_err_reset(c);
+          wire_expect(c, dev, ds, Dc, c->env_k, 8);
+          wire_expect(c, dev + z.row, ds, Dc, c->env_n, 8);
+          wire_expect(c, dev + z.ct - z.params, ds, Dc, c->env_params, (uint32_t)z.params);
+          wire_unpack(c, dev + 8, ds, k, Dc, c1, (size_t)k * ell, w1, true, false);
+          wire_unpack(c, r2, ds, nrows, Dc, c2, (size_t)nrows * ell, w2, false, false);
+          wire_err_check(c, "PvwCiphertext");
+        }
+        if (pass == 1) {
+          wire_unpack(c, dev + 8, ds, k, Dc, c1, (size_t)k * ell, w1, true, true);
+          wire_unpack(c, r2, ds, nrows, Dc, c2, (size_t)nrows * ell, w2, false, true);
+        }
+        if (host) CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
       }
-      u64* c1 = c->c1s.as<u64>() + (size_t)(slot0 + d0) * w1;
-      u64* c2 = c->c2s.as<u64>() + (size_t)(slot0 + d0) * w2;
-      const uint8_t* r2 = dev + z.row + 8 + (size_t)c->row0 * z.rec;
-      wire_err_reset(c);
-      wire_expect(c, dev, ds, Dc, c->env_k, 8);
-      wire_expect(c, dev + z.row, ds, Dc, c->env_n, 8);
-      wire_expect(c, dev + z.ct - z.params, ds, Dc, c->env_params, (uint32_t)z.params);
-      // validate everything first: a rejected blob leaves the store untouched (the reference returns Err, no side effects)
-      wire_unpack(c, dev + 8, ds, k, Dc, c1, (size_t)k * ell, w1, true, false);
-      wire_unpack(c, r2, ds, nrows, Dc, c2, (size_t)nrows * ell, w2, false, false);
-      wire_err_check(c, "PvwCiphertext");
-      wire_unpack(c, dev + 8, ds, k, Dc, c1, (size_t)k * ell, w1, true, true);
-      wire_unpack(c, r2, ds, nrows, Dc, c2, (size_t)nrows * ell, w2, false, true);
-      if (host) CUDA_CHECK(cudaStreamSynchronize(c->stream));  // the staging buffer is reused by the next chunk
     }
   });
 }
@@ -1228,21 +1287,185 @@ int pvw_wire_polys_deserialize(pvw_ctx* c, uint32_t count, const uint8_t* in, ui
   });
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU: exchange of the c1 dealer slices between the row-sharded contexts of one box
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*stream_value_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+struct StreamMemOps { stream_value_fn wait = nullptr, write = nullptr; };
+const StreamMemOps& stream_mem_ops() {
+  static StreamMemOps ops;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      ops.wait = reinterpret_cast<stream_value_fn>(fn);
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      ops.write = reinterpret_cast<stream_value_fn>(fn);
+  }
+  return ops;
+}
+void stream_wait_geq(cudaStream_t st, const u64* addr, u64 value) {
+  const CUresult r = stream_mem_ops().wait((CUstream)st, (CUdeviceptr)(uintptr_t)addr, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) throw PvwException(PVW_ERR_INTERNAL, fmt("cuStreamWaitValue64 failed (CUresult %d)", (int)r));
+}
+void stream_write(cudaStream_t st, u64* addr, u64 value) {
+  const CUresult r = stream_mem_ops().write((CUstream)st, (CUdeviceptr)(uintptr_t)addr, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS) throw PvwException(PVW_ERR_INTERNAL, fmt("cuStreamWriteValue64 failed (CUresult %d)", (int)r));
+}
+
+struct ShardBlob {   // what pvw_shard_export hands to the peers (fits pvw_shard_handle)
+  cudaIpcMemHandle_t c1, flags;
+  uint64_t cap, w1, world;
+  uint64_t magic;
+};
+static_assert(sizeof(ShardBlob) <= sizeof(pvw_shard_handle), "pvw_shard_handle too small");
+constexpr uint64_t SHARD_MAGIC = 0x5056573153484452ull;
+
+}  // namespace
+
+static void shard_disconnect(pvw_ctx* c) {
+  pvw_ctx::Shard& sh = c->sh;
+  if (!sh.connected) return;
+  if (sh.xstream) cudaStreamSynchronize(sh.xstream);
+  cudaStreamSynchronize(c->stream);
+  for (uint32_t r = 0; r < sh.world; r++) {
+    if (r == sh.rank) continue;
+    if (sh.peer_c1[r]) cudaIpcCloseMemHandle(sh.peer_c1[r]);
+    if (sh.peer_flags[r]) cudaIpcCloseMemHandle(sh.peer_flags[r]);
+  }
+  sh.peer_c1.clear(); sh.peer_flags.clear();
+  sh.connected = false;
+}
+
+int pvw_shard_export(pvw_ctx* c, uint32_t world, pvw_shard_handle* out) {
+  return guarded(c, [&] {
+    require(out != nullptr && world >= 1, PVW_ERR_INVALID_PARAMETERS, "null argument / empty world");
+    require(c->cap > 0, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_export: reserve the ciphertext store first (pvw_ct_reserve)");
+    require(!c->sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_export: already connected; disconnect first");
+    require(stream_mem_ops().wait && stream_mem_ops().write, PVW_ERR_INTERNAL, "this driver does not export cuStreamWaitValue64 / cuStreamWriteValue64");
+    pvw_ctx::Shard& sh = c->sh;
+    if (!sh.xstream) CUDA_CHECK(cudaStreamCreateWithFlags(&sh.xstream, cudaStreamNonBlocking));
+    if (!sh.ev_c1) CUDA_CHECK(cudaEventCreateWithFlags(&sh.ev_c1, cudaEventDisableTiming));
+    if (sh.flags && sh.flags_world != world) { CUDA_CHECK(cudaFree(sh.flags)); sh.flags = nullptr; }
+    if (!sh.flags) { CUDA_CHECK(cudaMalloc(&sh.flags, (2 * (size_t)world + 2) * 8)); sh.flags_world = world; }
+    CUDA_CHECK(cudaMemset(sh.flags, 0, (2 * (size_t)world + 2) * 8));   // counters restart with every (re)connection
+    sh.push_seq = sh.wait_seq = 0;
+    ShardBlob b;
+    memset(&b, 0, sizeof(b));
+    CUDA_CHECK(cudaIpcGetMemHandle(&b.c1, c->c1s.p));
+    CUDA_CHECK(cudaIpcGetMemHandle(&b.flags, sh.flags));
+    b.cap = c->cap; b.w1 = (uint64_t)c->hp.L * c->hp.k * c->hp.ell; b.world = world; b.magic = SHARD_MAGIC;
+    memset(out, 0, sizeof(*out));
+    memcpy(out, &b, sizeof(b));
+  });
+}
+
+int pvw_shard_connect(pvw_ctx* c, uint32_t world, uint32_t rank, const pvw_shard_handle* all) {
+  return guarded(c, [&] {
+    require(all != nullptr && world >= 1 && rank < world, PVW_ERR_INVALID_PARAMETERS, "bad world / rank");
+    pvw_ctx::Shard& sh = c->sh;
+    require(!sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_connect: already connected");
+    require(sh.flags && sh.flags_world == world, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_connect: call pvw_shard_export(world) first");
+    const uint64_t w1 = (uint64_t)c->hp.L * c->hp.k * c->hp.ell;
+    sh.peer_c1.assign(world, nullptr); sh.peer_flags.assign(world, nullptr);
+    sh.world = world; sh.rank = rank;
+    sh.connected = true;                       // from here on a failure is cleaned up by shard_disconnect
+    try {
+      for (uint32_t r = 0; r < world; r++) {
+        ShardBlob b;
+        memcpy(&b, &all[r], sizeof(b));
+        require(b.magic == SHARD_MAGIC && b.world == world, PVW_ERR_INVALID_PARAMETERS, fmt("handle of rank %u is not a pvw_shard_handle of this world", r));
+        require(b.cap == c->cap && b.w1 == w1, PVW_ERR_DIMENSION_MISMATCH,
+                fmt("rank %u reserved %llu ciphertext slots of %llu words, this rank %u of %llu", r, (unsigned long long)b.cap, (unsigned long long)b.w1, c->cap, (unsigned long long)w1));
+        if (r == rank) { sh.peer_c1[r] = c->c1s.as<u64>(); sh.peer_flags[r] = sh.flags; continue; }
+        void* p = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&p, b.c1, cudaIpcMemLazyEnablePeerAccess));
+        sh.peer_c1[r] = reinterpret_cast<u64*>(p);
+        CUDA_CHECK(cudaIpcOpenMemHandle(&p, b.flags, cudaIpcMemLazyEnablePeerAccess));
+        sh.peer_flags[r] = reinterpret_cast<u64*>(p);
+      }
+    } catch (...) {
+      shard_disconnect(c);
+      throw;
+    }
+  });
+}
+
+int pvw_shard_disconnect(pvw_ctx* c) {
+  return guarded(c, [&] { shard_disconnect(c); });
+}
+
+int pvw_shard_push_c1(pvw_ctx* c, uint32_t slot0, uint32_t count) {
+  return guarded(c, [&] {
+    pvw_ctx::Shard& sh = c->sh;
+    require(sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_push_c1: not connected");
+    require((uint64_t)slot0 + count <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + count, c->cap));
+    const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell;
+    const u64 seq = ++sh.push_seq;
+    u64* stage = sh.flags + 2 * (size_t)sh.world;
+    // the slice is final once everything queued on the compute stream so far (its c1 product) has run
+    CUDA_CHECK(cudaEventRecord(sh.ev_c1, c->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(sh.xstream, sh.ev_c1, 0));
+    for (uint32_t i = 1; i < sh.world; i++) {
+      const uint32_t r = (sh.rank + i) % sh.world;                       // staggered: at any moment every peer receives from one rank
+      stream_wait_geq(sh.xstream, sh.flags + sh.world + r, seq - 1);     // peer r has released the c1 of the previous exchange
+      if (count)
+        CUDA_CHECK(cudaMemcpyAsync(sh.peer_c1[r] + (size_t)slot0 * w1, c->c1s.as<u64>() + (size_t)slot0 * w1, (size_t)count * w1 * 8, cudaMemcpyDeviceToDevice, sh.xstream));
+    }
+    stream_write(sh.xstream, stage, seq);
+    for (uint32_t i = 1; i < sh.world; i++) {
+      const uint32_t r = (sh.rank + i) % sh.world;
+      CUDA_CHECK(cudaMemcpyAsync(sh.peer_flags[r] + sh.rank, stage, 8, cudaMemcpyDeviceToDevice, sh.xstream));   // "my slice of exchange seq has landed"
+    }
+  });
+}
+
+int pvw_shard_wait_c1(pvw_ctx* c) {
+  return guarded(c, [&] {
+    pvw_ctx::Shard& sh = c->sh;
+    require(sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_wait_c1: not connected");
+    const u64 seq = ++sh.wait_seq;
+    require(seq <= sh.push_seq, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_wait_c1 without a matching pvw_shard_push_c1 on this rank");
+    for (uint32_t r = 0; r < sh.world; r++)
+      if (r != sh.rank) stream_wait_geq(c->stream, sh.flags + r, seq);
+  });
+}
+
+int pvw_shard_release_c1(pvw_ctx* c) {
+  return guarded(c, [&] {
+    pvw_ctx::Shard& sh = c->sh;
+    require(sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_release_c1: not connected");
+    u64* stage = sh.flags + 2 * (size_t)sh.world + 1;
+    stream_write(c->stream, stage, sh.wait_seq);
+    for (uint32_t i = 1; i < sh.world; i++) {
+      const uint32_t r = (sh.rank + i) % sh.world;
+      CUDA_CHECK(cudaMemcpyAsync(sh.peer_flags[r] + sh.world + sh.rank, stage, 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  });
+}
+
 int pvw_ctx_synchronize(pvw_ctx* c) {
-  return guarded(c, [&] { CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+  return guarded(c, [&] {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->sh.xstream) CUDA_CHECK(cudaStreamSynchronize(c->sh.xstream));
+  });
 }
 void* pvw_ctx_stream(pvw_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
-  if (c && name && std::string(name) == "imma") { c->use_imma = value != 0; return PVW_OK; }
-  if (c && name && std::string(name) == "imma_pair") { c->imma_pair = value != 0; return PVW_OK; }
-  if (c && name && std::string(name) == "imma_min_dealers") { c->imma_min_dealers = std::max<int64_t>(1, value); return PVW_OK; }
-  if (c && name && std::string(name) == "imma_min_rows") { c->imma_min_rows = std::max<int64_t>(1, value); return PVW_OK; }
-  if (c && name && std::string(name) == "imma_chunk_dealers") { c->imma_chunk_dealers = std::min<int64_t>(std::max<int64_t>(16, value), 32768); return PVW_OK; }   // grid.y of the byte-plane kernel
   return guarded(c, [&] {
     require(name != nullptr, PVW_ERR_INVALID_PARAMETERS, "null option name");
     std::string n(name);
-    if (n == "gemm_impl") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0, 1 or 2"); c->gemm_impl = (int)value; }
+    if (n == "imma") c->use_imma = value != 0;
+    else if (n == "imma_pair") c->imma_pair = value != 0;
+    else if (n == "imma_min_dealers") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_dealers must be >= 1"); c->imma_min_dealers = value; }
+    else if (n == "imma_min_rows") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_rows must be >= 1"); c->imma_min_rows = value; }
+    else if (n == "imma_chunk_dealers") { require(value >= 16 && value <= (1 << 20), PVW_ERR_INVALID_PARAMETERS, "imma_chunk_dealers must be in [16, 2^20]"); c->imma_chunk_dealers = value; }
+    else if (n == "gemm_impl") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "gemm_impl must be 0, 1 or 2"); c->gemm_impl = (int)value; }
     else if (n == "gemm_tile") { require(value >= 0 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..3"); c->gemm_tile = (int)value; }
     else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
     else if (n == "lift_fast") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "lift_fast must be 0 or 1"); c->T.lift_fast = (value && c->hp.shortL > 0) ? 1 : 0; }

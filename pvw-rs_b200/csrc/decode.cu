@@ -90,17 +90,68 @@ __global__ void __launch_bounds__(128) decode_rns_kernel(const u64* __restrict__
   yo[(size_t)(ELL - 1) * S] = mulmod_shoup(last, lc.qhinv, lc.qhinv_sh, q);
 }
 
-void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st, size_t z_cs,
+// the same step for any power-of-two ring degree up to 256 (run-time loops, coefficients in local memory): correct, not tuned
+constexpr int GEN_MAX_ELL = 256;
+__global__ void __launch_bounds__(64) decode_rns_generic_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, uint32_t Pc, uint64_t S,
+                                                                u64* __restrict__ y, const LimbConst* __restrict__ lcs, const u64* __restrict__ twi,
+                                                                const u64* __restrict__ twi_sh, size_t z_cs, const DecodeSub sub,
+                                                                const u64* __restrict__ dec_c, const uint32_t ell) {
+  const uint32_t limb = blockIdx.y;
+  const LimbConst lc = lcs[limb];
+  const u64 q = lc.q;
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const uint64_t d = s / Pc, p = s % Pc;
+  u64 a[GEN_MAX_ELL];
+  for (uint32_t t = 0; t < ell; t++)
+    a[t] = z_cs ? z[d * z_ds + (size_t)limb * z_ls + (size_t)t * z_cs + p] : z[d * z_ds + (size_t)limb * z_ls + p * ell + t];
+  if (sub.S) {
+    const uint32_t sd = sub.dmap ? sub.dmap[d] : (uint32_t)d, srow = sub.rowmap ? sub.rowmap[p] : (uint32_t)p;
+    const u64* sp = sub.S + (size_t)sd * sub.S_ds + (size_t)limb * sub.S_ls + (size_t)srow * ell;
+    for (uint32_t t = 0; t < ell; t++) a[t] = submod(a[t], sp[t], q);
+  }
+  const u64* w = twi + (size_t)limb * ell;
+  const u64* w_sh = twi_sh + (size_t)limb * ell;
+  for (uint32_t m = ell, t = 1; m > 1; m >>= 1, t <<= 1) {   // Gentleman-Sande passes, unscaled (ntt_regs.cuh)
+    const uint32_t h = m >> 1;
+    for (uint32_t i = 0, j1 = 0; i < h; i++, j1 += 2 * t) {
+      const u64 sw = w[h + i], sw_sh = w_sh[h + i];
+      for (uint32_t j = j1; j < j1 + t; j++) {
+        const u64 u = a[j], v = a[j + t];
+        a[j] = addmod(u, v, q);
+        a[j + t] = mulmod_shoup(submod(u, v, q), sw, sw_sh, q);
+      }
+    }
+  }
+  const u64 c1 = dec_c[4 * limb], c1_sh = dec_c[4 * limb + 1], c2 = dec_c[4 * limb + 2], c2_sh = dec_c[4 * limb + 3];
+  u64* yo = y + ((size_t)limb * (ell + 1)) * S + s;
+  u64 last = 0, p2 = mulmod_shoup(a[0], c2, c2_sh, q);
+  yo[(size_t)ell * S] = negmod(p2, q);
+  for (uint32_t i = 0; i + 1 < ell; i++) {
+    p2 = mulmod_shoup(a[i + 1], c2, c2_sh, q);
+    const u64 tmp = submod(mulmod_shoup(a[i], c1, c1_sh, q), p2, q);
+    last = (i == 0) ? tmp : addmod(mulmod_shoup(last, lc.delta, lc.delta_sh, q), tmp, q);
+    yo[(size_t)i * S] = tmp;
+  }
+  yo[(size_t)(ell - 1) * S] = mulmod_shoup(last, lc.qhinv, lc.qhinv_sh, q);
+}
+
+bool launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st, size_t z_cs,
                        const DecodeSub* sub) {
   const uint64_t S = (uint64_t)Pc * D;
-  if (S == 0) return;
+  if (S == 0) return true;
+  if ((S + 63) / 64 >= (1ull << 31) || T.L > 65535u) return false;
   dim3 grid((unsigned)((S + 127) / 128), T.L);
   const DecodeSub sb = sub ? *sub : DecodeSub{nullptr, 0, 0, nullptr, nullptr};
   switch (T.ell) {
     case 8: decode_rns_kernel<8><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c); break;
     case 16: decode_rns_kernel<16><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c); break;
     case 32: decode_rns_kernel<32><<<grid, 128, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c); break;
+    default:
+      if (T.ell > (uint32_t)GEN_MAX_ELL) return false;
+      decode_rns_generic_kernel<<<dim3((unsigned)((S + 63) / 64), T.L), 64, 0, st>>>(z, z_ls, z_ds, Pc, S, y, T.lc, T.twi, T.twi_sh, z_cs, sb, T.dec_c, T.ell);
   }
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

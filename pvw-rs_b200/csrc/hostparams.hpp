@@ -244,7 +244,7 @@ struct HostParams {
     if (k_ == 0) throw PvwException(IP, "k must be > 0");                                   // :134
     if (ell_ < 8 || (ell_ & (ell_ - 1)) != 0)                                               // :140
       throw PvwException(IP, "l must be power of 2 and >= 8 (fhe.rs Context requirement)");
-    if (ell_ > 32) throw PvwException(IP, "l > 32 is not supported by the B200 kernels (reference sets use 8, 16, 32)");
+    if (ell_ > 256) throw PvwException(IP, "l > 256 is not supported by the B200 kernels (8, 16, 32: register-resident; 64..256: generic)");
     if (L_ == 0 || mods == nullptr) throw PvwException(IP, "moduli not set");
     if (L_ > 64) throw PvwException(IP, "more than 64 moduli are not supported");
     n = n_; k = k_; ell = ell_; L = L_; secret_variance = var; b1 = b1_; b2 = b2_;

@@ -33,7 +33,6 @@
 #include <cuda.h>
 
 #include <algorithm>
-#include <cstdlib>
 
 #include "imma.cuh"
 
@@ -515,32 +514,52 @@ imma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-// one CTA per (row, limb): thread = (c, j) with j fastest -> the byte stores of a warp fill one sector of one plane
-__global__ void __launch_bounds__(256) imma_planes_m_kernel(const u64* __restrict__ M, size_t M_ls, size_t M_rs, uint32_t k, uint32_t ell,
-                                                            uint8_t* __restrict__ Mb, size_t Mb_plane, int packed) {
-  const uint32_t row = blockIdx.x, limb = blockIdx.y, kp = imma_kp(k);
-  const u64* src = M + (size_t)limb * M_ls + (size_t)row * M_rs;
-  for (uint32_t t = threadIdx.x; t < k * ell; t += blockDim.x) {
-    const uint32_t c = t / k, j = t - c * k;
-    u64 v = src[(size_t)j * ell + c];
-    if (packed) v = unpack_halves(v);
-    uint8_t* out = Mb + (size_t)(limb * ell + c) * Mb_plane + (size_t)row * 8 * kp + j;
+// Byte planes of a limb-major operand.  One CTA per (operand row, limb, chunk of JC polynomials): the chunk is read with
+// unit stride into shared memory (rows padded by one word: the transposed reads below are conflict free), then each thread
+// takes one slot c of FOUR consecutive polynomials j and writes the eight byte planes as 4-byte words -- a warp stores 128
+// contiguous bytes per instruction (the first version stored single bytes: 8x the store instructions, 32-byte bursts).
+//   src  = M + rowmap(row) * M_rs + limb * M_ls + j * ell + c            (canonical residues, or packed halves)
+//   dst  = Mb + (limb * ell + c) * Mb_plane + row * dst_rs + s * dst_bs + j          s = byte index
+// matrix side (A, B, s_hat): dst_rs = 8 * kp, dst_bs = kp;  dealer side (r_hat, c1): dst_rs = kp, dst_bs = rows * kp
+IMMA_DEV void transpose_4x8(const u64 (&v)[4], uint32_t (&w)[8]) {
 #pragma unroll
-    for (uint32_t s = 0; s < 8; s++) out[(size_t)s * kp] = (uint8_t)(v >> (8 * s));
+  for (int h = 0; h < 2; h++) {
+    const uint32_t a0 = (uint32_t)(v[0] >> (32 * h)), a1 = (uint32_t)(v[1] >> (32 * h)), a2 = (uint32_t)(v[2] >> (32 * h)), a3 = (uint32_t)(v[3] >> (32 * h));
+    const uint32_t t01 = __byte_perm(a0, a1, 0x5140), t23 = __byte_perm(a2, a3, 0x5140);   // bytes 0, 1 of the pair, interleaved
+    const uint32_t u01 = __byte_perm(a0, a1, 0x7362), u23 = __byte_perm(a2, a3, 0x7362);   // bytes 2, 3
+    w[4 * h + 0] = __byte_perm(t01, t23, 0x5410);
+    w[4 * h + 1] = __byte_perm(t01, t23, 0x7632);
+    w[4 * h + 2] = __byte_perm(u01, u23, 0x5410);
+    w[4 * h + 3] = __byte_perm(u01, u23, 0x7632);
   }
 }
-// grid (., D, L): thread = (c, j) of one dealer and limb, j fastest
-__global__ void __launch_bounds__(256) imma_planes_v_kernel(const u64* __restrict__ V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t k,
-                                                            uint8_t* __restrict__ Vb, size_t Vb_plane, int packed, const uint32_t* __restrict__ dmap) {
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y, limb = blockIdx.z, D = gridDim.y, kp = imma_kp(k);
-  if (e >= k * ell) return;
-  const uint32_t c = e / k, j = e - c * k;
-  const uint32_t sd = dmap ? dmap[d] : d;
-  u64 v = V[(size_t)sd * V_ds + (size_t)limb * V_ls + (size_t)j * ell + c];
-  if (packed) v = unpack_halves(v);
-  uint8_t* out = Vb + (size_t)(limb * ell + c) * Vb_plane + (size_t)d * kp + j;
+
+__global__ void __launch_bounds__(256) imma_planes_kernel(const u64* __restrict__ M, size_t M_ls, size_t M_rs, uint32_t k, uint32_t ell, uint32_t jc,
+                                                          uint8_t* __restrict__ Mb, size_t Mb_plane, size_t dst_rs, size_t dst_bs, int packed,
+                                                          const uint32_t* __restrict__ rowmap, uint32_t nchunks) {
+  extern __shared__ u64 s_v[];                                            // [jc][ell + 1]
+  const uint32_t row = blockIdx.x, limb = blockIdx.y / nchunks, j0 = (blockIdx.y - limb * nchunks) * jc;
+  const uint32_t jn = min(jc, k - j0), pitch = ell + 1;
+  const u64* src = M + (size_t)(rowmap ? rowmap[row] : row) * M_rs + (size_t)limb * M_ls + (size_t)j0 * ell;
+  for (uint32_t t = threadIdx.x; t < jn * ell; t += blockDim.x) {
+    u64 v = src[t];
+    if (packed) v = unpack_halves(v);
+    const uint32_t j = t / ell, c = t - j * ell;
+    s_v[j * pitch + c] = v;
+  }
+  __syncthreads();
+  const uint32_t groups = (jn + 3) / 4;
+  for (uint32_t t = threadIdx.x; t < groups * ell; t += blockDim.x) {
+    const uint32_t c = t / groups, jg = t - c * groups;
+    u64 v[4];
 #pragma unroll
-  for (uint32_t t = 0; t < 8; t++) out[(size_t)t * D * kp] = (uint8_t)(v >> (8 * t));
+    for (uint32_t i = 0; i < 4; i++) v[i] = (4 * jg + i < jn) ? s_v[(4 * jg + i) * pitch + c] : 0ull;   // the padding of a plane row is zero
+    uint32_t w[8];
+    transpose_4x8(v, w);
+    uint8_t* out = Mb + (size_t)(limb * ell + c) * Mb_plane + (size_t)row * dst_rs + j0 + 4 * jg;
+#pragma unroll
+    for (uint32_t b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(out + (size_t)b * dst_bs) = w[b];
+  }
 }
 
 typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -563,9 +582,8 @@ bool make_map(CUtensorMap* tm, const void* base, const cuuint64_t (&dims)[4], co
   if (!encode || ((uintptr_t)base & 15)) return false;
   for (cuuint64_t s : strides) if (s & 15) return false;
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  static const int promo = getenv("PVW_IMMA_L2PROMO") ? atoi(getenv("PVW_IMMA_L2PROMO")) : 3;   // experiment knob: 0 none, 1 64B, 2 128B, 3 256B
   return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <uint32_t DT>
@@ -581,14 +599,12 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   const uint32_t b_tile = nkc * 8 * DT * KC;
   const uint32_t resident = (2 * b_tile + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 1u : 0u;
   const uint32_t b_bytes = resident ? 2 * b_tile : 2 * 8 * DT * KC;
-  static const uint32_t stage_cap = getenv("PVW_IMMA_STAGES") ? (uint32_t)atoi(getenv("PVW_IMMA_STAGES")) : MAX_STAGES;   // experiment knob
-  const uint32_t nstages = std::max(2u, std::min<uint32_t>(std::min(stage_cap, MAX_STAGES), (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
+  const uint32_t nstages = std::max(2u, std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
   auto kern = resident ? imma_gemm_kernel<DT, true> : imma_gemm_kernel<DT, false>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);  // per device
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return false;  // per device
   int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   const uint64_t tiles = (uint64_t)((a.rows + RT - 1) / RT) * ((a.D + DT - 1) / DT) * planes;
   if (tiles >= (1ull << 32)) return false;
   kern<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, smem, st>>>(tmA, tmB, a, nstages);
@@ -606,10 +622,9 @@ bool launch_pair(const ImmaArgs& a, cudaStream_t st) {
   const uint32_t b_bytes = 2 * 4 * 32 * KC;
   const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE);
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
-  cudaFuncSetAttribute(imma_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (cudaFuncSetAttribute(imma_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return false;
   int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   const uint64_t tiles = (uint64_t)((a.rows + 2 * RT - 1) / (2 * RT)) * ((a.D + 31) / 32) * planes;
   if (tiles >= (1ull << 32)) return false;
   const unsigned pairs = (unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms / 2, 1));
@@ -626,22 +641,30 @@ bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
 
 bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
   if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
-  static const int dt = getenv("PVW_IMMA_DT") ? atoi(getenv("PVW_IMMA_DT")) : 32;   // experiment knobs
-  static const int pair = getenv("PVW_IMMA_PAIR") ? atoi(getenv("PVW_IMMA_PAIR")) : 0;
-  if (pair || a.pair) return launch_pair(a, st);
-  return dt == 16 ? launch_dt<16>(a, st) : launch_dt<32>(a, st);
+  if (a.pair) return launch_pair(a, st);
+  return launch_dt<32>(a, st);
 }
 
-void launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb,
+static bool launch_planes(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb, size_t Mb_plane,
+                          size_t dst_rs, size_t dst_bs, bool packed, const uint32_t* rowmap, cudaStream_t st) {
+  if (rows == 0) return true;
+  const uint32_t jc = std::max(4u, 2048u / ell), nchunks = (k + jc - 1) / jc;
+  if ((uint64_t)L * nchunks > 65535u) return false;                      // grid.y; L * ceil(k * ell / 2048) is a few hundred at most
+  const size_t smem = (size_t)jc * (ell + 1) * 8;
+  imma_planes_kernel<<<dim3(rows, L * nchunks), 256, smem, st>>>(M, M_ls, M_rs, k, ell, jc, Mb, Mb_plane, dst_rs, dst_bs, packed ? 1 : 0, rowmap, nchunks);
+  return true;
+}
+
+bool launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb,
                           size_t Mb_plane, bool packed, cudaStream_t st) {
-  if (rows == 0) return;
-  imma_planes_m_kernel<<<dim3(rows, L), 256, 0, st>>>(M, M_ls, M_rs, k, ell, Mb, Mb_plane, packed ? 1 : 0);
+  const uint32_t kp = imma_kp(k);
+  return launch_planes(M, M_ls, M_rs, rows, k, L, ell, Mb, Mb_plane, (size_t)8 * kp, kp, packed, nullptr, st);
 }
 
-void launch_imma_planes_v(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vb, size_t Vb_plane,
+bool launch_imma_planes_v(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vb, size_t Vb_plane,
                           bool packed, const uint32_t* dmap, cudaStream_t st) {
-  if (D == 0 || D > 65535) return;   // grid.y carries the dealer count (callers chunk dealers far below the limit)
-  imma_planes_v_kernel<<<dim3((k * ell + 255) / 256, D, L), 256, 0, st>>>(V, V_ds, V_ls, ell, k, Vb, Vb_plane, packed ? 1 : 0, dmap);
+  const uint32_t kp = imma_kp(k);
+  return launch_planes(V, V_ls, V_ds, D, k, L, ell, Vb, Vb_plane, kp, (size_t)D * kp, packed, dmap, st);
 }
 
 }  // namespace pvw

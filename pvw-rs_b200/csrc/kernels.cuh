@@ -46,7 +46,9 @@ struct DevTables {
 //   item idx in [0,count): vec = idx / inner, j = idx % inner;  out[vec*vstride + limb*lstride + j*ell + c]
 //   value = NTT(rns(coef[idx]))[c] (+ (m[idx] as i64 mod q) * gadget_hat[limb][c] when m != nullptr)
 // pack_out: write the 31-bit-halves operand form (modarith.cuh pack_halves) that the multiply-accumulate kernel reads
-void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
+// coef: signed integers of `cbytes` bytes each (8 = the reference's i64; 1 / 2 / 4 = the narrow input forms of pvw_b200.h)
+// returns false when the shape cannot be launched (ring degree above 256, more than 2^31 blocks) -- nothing was queued then
+bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out,
                       size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false, bool pack_out = false, int planes = 0,
                       const u64* addend = nullptr);
 // addend: out = value + addend[(vec*L + limb)*ell*inner + c*inner + j], the slot-major product of the tensor-core kernel
@@ -78,7 +80,8 @@ struct GemmArgs {
   int refill_lag;  // chunks between a stage's last use and its refill (1 .. NS-1)
 };
 // impl: 0 = synchronous shared-memory tiles, 1 = cp.async.bulk (TMA) + mbarrier pipeline with a producer warp
-void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st);
+// false: the shape cannot be launched (generic kernel: more than 65535 dealers per call)
+bool launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st);
 size_t mac_gemm_launches(const GemmArgs& a);
 
 // ---- decode.cu ----------------------------------------------------------------------------------------------
@@ -87,7 +90,7 @@ size_t mac_gemm_launches(const GemmArgs& a);
 // sub (optional): the polynomial to subtract first -- z holds <s, c1> only and sub describes c2 (decryption.rs:270-274):
 //   S[sd*S_ds + limb*S_ls + srow*ell + c], sd = dmap ? dmap[d] : d, srow = rowmap ? rowmap[p] : p
 struct DecodeSub { const u64* S; size_t S_ls, S_ds; const uint32_t* rowmap; const uint32_t* dmap; };
-void launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st,
+bool launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st,
                        size_t z_cs = 0, const DecodeSub* sub = nullptr);
 // X[(i*NW + w)*S + s'] = CRT lift of y[.][i][s']
 void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st);

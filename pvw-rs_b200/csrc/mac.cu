@@ -12,7 +12,7 @@
 // slot, so each M row tile fetched from HBM/L2 is reused for DT dealers and each V tile for RT rows.  The bound then
 // is the integer pipe, not HBM: a 62x62-bit product is 3 IMAD.WIDE.U32 (Karatsuba on 31-bit halves); the three partial
 // sums are accumulated unreduced in 96 bits each (modarith.cuh, AccK) and reduced once per k terms.  Measured on
-// B200 (tools/int_peaks.cu): an IMAD.WIDE with a 64-bit addend issues every 4 cycles per SM sub-partition, so the
+// B200 (tools/csrc/int_peaks.cu): an IMAD.WIDE with a 64-bit addend issues every 4 cycles per SM sub-partition, so the
 // ceiling is 12 cycles per warp-wide multiply-accumulate = 2.8e12 MAC/s.  No tensor cores: exact modular arithmetic.
 //   * thread = one NTT slot c of a TR x TD (row, dealer) sub-tile -> TR*TD independent carry chains (ILP);
 //     a warp's lanes sweep the ell slots of (32/ell) sub-tiles, so shared-memory reads are conflict-free 8-byte
@@ -262,8 +262,43 @@ static void launch_cfg(const GemmArgs& a, int impl, cudaStream_t st) {
   }
 }
 
-void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
-  if (a.rows == 0 || a.D == 0) return;
+// Any ring degree (run-time ell; used above 32, where the tiled kernels have no instantiation): one thread per output slot,
+// operands read from global memory (packed halves), the same lazy accumulator and epilogue.  Correct, not tuned.
+__global__ void __launch_bounds__(256) mac_gemm_generic_kernel(const GemmArgs g) {
+  const uint32_t limb = blockIdx.z, d = blockIdx.y;
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (uint64_t)g.rows * g.ell) return;
+  const uint32_t row = (uint32_t)(e / g.ell), c = (uint32_t)(e % g.ell);
+  const LimbConst lc = g.lc[limb];
+  const uint32_t ds = g.V_dmap ? g.V_dmap[d] : d;
+  const u64* mrow = g.M + (size_t)limb * g.M_ls + (size_t)row * g.M_rs + c;
+  const u64* vrow = g.V + (size_t)ds * g.V_ds + (size_t)limb * g.V_ls + c;
+  AccK acc;
+  acck_zero(acc);
+  for (uint32_t j = 0; j < g.k; j++) {
+    const u64 a = mrow[(size_t)j * g.ell], b = vrow[(size_t)j * g.ell];
+    SplitOp sa, sb;
+    sa.x0 = (u32)a; sa.x1 = (u32)(a >> 32); sa.xs = sa.x0 + sa.x1;
+    sb.x0 = (u32)b; sb.x1 = (u32)(b >> 32); sb.xs = sb.x0 + sb.x1;
+    acck_mac(acc, sa, sb);
+  }
+  u64 v = acck_reduce(acc, lc);
+  u64* o = g.O + (size_t)d * g.O_ds + (size_t)limb * g.O_ls + (size_t)row * g.ell + c;
+  if (g.mode == 0) v = addmod(v, *o, lc.q);
+  else if (g.mode == 1) {
+    const uint32_t srow = g.S_rowmap ? g.S_rowmap[row] : row;
+    v = submod(v, g.S[(size_t)ds * g.S_ds + (size_t)limb * g.S_ls + (size_t)srow * g.ell + c], lc.q);
+  }
+  *o = g.O_packed ? pack_halves(v) : v;
+}
+
+bool launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
+  if (a.rows == 0 || a.D == 0) return true;
+  if (a.ell != 8 && a.ell != 16 && a.ell != 32) {
+    if (a.D > 65535u || a.L > 65535u) return false;
+    mac_gemm_generic_kernel<<<dim3((unsigned)(((uint64_t)a.rows * a.ell + 255) / 256), a.D, a.L), 256, 0, st>>>(a);
+    return true;
+  }
   const bool matvec = a.D == 1;
   // tile 1 (default): 4x2 register tile, two CTAs per SM (<= 128 registers: one CTA's prologue / epilogue overlaps the
   //   other's main loop); CTA tile 16 rows x 16 dealers (fewest staged rows per output), 16 polynomials per stage, three
@@ -294,6 +329,7 @@ void launch_mac_gemm(const GemmArgs& a, int impl, cudaStream_t st) {
       else launch_cfg<32, 4, 2, 2, 8, 2, 2>(a, impl, st);
       break;
   }
+  return true;
 }
 size_t mac_gemm_launches(const GemmArgs& a) { return (a.rows == 0 || a.D == 0) ? 0 : 1; }
 

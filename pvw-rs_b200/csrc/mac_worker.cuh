@@ -1,5 +1,5 @@
 // mac_worker.cuh -- the register-tile inner loop of the matrix multiply-accumulate kernel (mac.cu), shared with the
-// integer-pipe microbenchmark (tools/int_peaks.cu) so that tile shapes can be timed without the copy pipeline.
+// integer-pipe microbenchmark (tools/csrc/int_peaks.cu) so that tile shapes can be timed without the copy pipeline.
 #pragma once
 #include "kernels.cuh"
 

@@ -64,7 +64,7 @@ PVW_DEV u64 reduce_i64(long long x, const LimbConst& c) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// [measured alternative, used only by tools/int_peaks.cu: 2.1e12 MAC/s in registers]
+// [measured alternative, used only by tools/csrc/int_peaks.cu: 2.1e12 MAC/s in registers]
 // Lazy 160-bit accumulator for sum_j a_j * b_j with a_j, b_j < 2^62: products are added unreduced and one Barrett
 // reduction runs after the whole k-term sum (k < 2^32).  The four 32x32 partial products go to an "even" column
 // set (a0*b0 at bit 0, a1*b1 at bit 64; words e0..e4) and an "odd" one (a0*b1 + a1*b0 at bit 32; words o0..o2) so
@@ -206,7 +206,7 @@ PVW_DEV u64 acck_reduce(const AccK& c, const LimbConst& lc) {
 // ---------------------------------------------------------------------------------------------------------------
 // Packed operand form (production): x = x1*2^31 + x0 is stored as (x1 << 32) | x0, see kernels.cuh.
 //
-// [measured alternative, used only by tools/int_peaks.cu: 1.6e12 MAC/s -- ptxas re-associates the plain mad.wide chains
+// [measured alternative, used only by tools/csrc/int_peaks.cu: 1.6e12 MAC/s -- ptxas re-associates the plain mad.wide chains
 //  into IMAD.WIDE(RZ) + IADD3 + IMAD.X, so dropping the carries does not pay]
 // Carry-free lazy accumulator: every partial product of 31-bit halves is < 2^62, so four consecutive terms are summed in
 // plain 64-bit accumulators (no carry possible) before being folded into 96-bit sums:
@@ -258,7 +258,7 @@ PVW_DEV u64 accw_reduce(const AccW& c, const LimbConst& lc) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// [measured alternative, used only by tools/int_peaks.cu: 2.0e12 MAC/s]
+// [measured alternative, used only by tools/csrc/int_peaks.cu: 2.0e12 MAC/s]
 // Hybrid: Karatsuba with the two small products (L = a0*b0, H = a1*b1 < 2^62) summed carry-free four at a time and
 // the cross term K = (a0+a1)*(b0+b1) < 2^64 accumulated with carry.  Packed operand word: (x1 << 32) | x0.
 // ---------------------------------------------------------------------------------------------------------------

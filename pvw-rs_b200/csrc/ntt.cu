@@ -10,11 +10,59 @@
 
 namespace pvw {
 
+// Small signed inputs (secrets, randomness, errors) arrive as int64 (the reference's i64 / BigInt-as-i64) or, to cut the
+// host-to-device volume of the host-pointer calls, as int8 / int16 / int32 (pvw_b200.h PVW_IN_*): `cbytes` is the element size.
+template <int N>
+PVW_DEV void load_small(const void* __restrict__ coef, int cbytes, uint64_t idx, long long (&x)[N]) {
+  if (cbytes == 8) {
+    const longlong2* src = reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(coef) + idx * N);
+#pragma unroll
+    for (int t = 0; t < N / 2; t++) { const longlong2 v = src[t]; x[2 * t] = v.x; x[2 * t + 1] = v.y; }
+  } else if (cbytes == 4) {
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const int*>(coef) + idx * N);
+#pragma unroll
+    for (int t = 0; t < N / 4; t++) { const int4 v = src[t]; x[4 * t] = v.x; x[4 * t + 1] = v.y; x[4 * t + 2] = v.z; x[4 * t + 3] = v.w; }
+  } else if (cbytes == 2) {
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const short*>(coef) + idx * N);
+#pragma unroll
+    for (int t = 0; t < N / 8; t++) {
+      const uint4 v = src[t];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) { x[8 * t + 2 * i] = (short)(w[i] & 0xffffu); x[8 * t + 2 * i + 1] = (short)(w[i] >> 16); }
+    }
+  } else {
+    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const signed char*>(coef) + idx * N);
+#pragma unroll
+    for (int t = 0; t < N / 8; t++) {
+      const uint2 v = src[t];
+      const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+      for (int i = 0; i < 8; i++) x[8 * t + i] = (signed char)((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    }
+  }
+}
+
+// bytes s of four residues -> eight words (word s = byte s of v[0..3]): the unit the byte-plane writers store
+PVW_DEV void bytes_4x8(const u64 (&v)[4], uint32_t (&w)[8]) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint32_t a0 = (uint32_t)(v[0] >> (32 * h)), a1 = (uint32_t)(v[1] >> (32 * h)), a2 = (uint32_t)(v[2] >> (32 * h)), a3 = (uint32_t)(v[3] >> (32 * h));
+    const uint32_t t01 = __byte_perm(a0, a1, 0x5140), t23 = __byte_perm(a2, a3, 0x5140);
+    const uint32_t u01 = __byte_perm(a0, a1, 0x7362), u23 = __byte_perm(a2, a3, 0x7362);
+    w[4 * h + 0] = __byte_perm(t01, t23, 0x5410);
+    w[4 * h + 1] = __byte_perm(t01, t23, 0x7632);
+    w[4 * h + 2] = __byte_perm(u01, u23, 0x5410);
+    w[4 * h + 3] = __byte_perm(u01, u23, 0x7632);
+  }
+}
+
 template <int ELL, int MODE>  // MODE 0: store canonical, 1: accumulate into canonical, 2: store packed halves (operand form),
-                               // 3 / 4: store the byte planes the tensor-core path reads (imma.cuh), M side / dealer side,
+                               // 3 / 4: store the byte planes the tensor-core path reads (imma.cuh), M side / dealer side, one
+                               //        polynomial per thread and single-byte stores (shapes the 4-polynomial kernel below cannot take),
                                // 5: store canonical value + addend, the addend in the slot-major form the tensor-core product writes:
                                //    addend[(vec*L + limb)*ELL*inner + c*inner + j]   (unit stride across the threads of a warp)
-__global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restrict__ coef, const u64* __restrict__ m, uint64_t count,
+__global__ void __launch_bounds__(128) ntt_small_kernel(const void* __restrict__ coef, int cbytes, const u64* __restrict__ m, uint64_t count,
                                                         uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
                                                         const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
                                                         const u64* __restrict__ tw_sh, const u64* __restrict__ gadget_hat,
@@ -34,12 +82,11 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   uint64_t idx = (uint64_t)blk * blockDim.x + threadIdx.x;
   if (idx >= count) return;
   u64 a[ELL];
-  const longlong2* src = reinterpret_cast<const longlong2*>(coef + idx * ELL);
+  {
+    long long x[ELL];
+    load_small<ELL>(coef, cbytes, idx, x);
 #pragma unroll
-  for (int t = 0; t < ELL / 2; t++) {
-    longlong2 v = src[t];
-    a[2 * t] = reduce_i64(v.x, lc);
-    a[2 * t + 1] = reduce_i64(v.y, lc);
+    for (int t = 0; t < ELL; t++) a[t] = reduce_i64(x[t], lc);
   }
   ntt_forward_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
   if (m != nullptr) {
@@ -49,7 +96,6 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   }
   if (MODE == 3 || MODE == 4) {
     // idx = r*inner + j (inner = k): r is a matrix row (MODE 3) or a dealer (MODE 4); vstride = kp, lstride = plane stride in bytes.
-    // Consecutive threads hold consecutive j: every byte store of a warp fills one sector of one plane.
     const uint64_t r = idx / inner, j = idx % inner, kp = vstride;
     uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (size_t)limb * ELL * lstride;
     const size_t first = MODE == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;        // byte plane 0
@@ -82,31 +128,141 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const long long* __restr
   }
 }
 
-void launch_ntt_small(const DevTables& T, const long long* coef, const u64* m, uint64_t count, uint32_t inner, u64* out,
+// Byte planes of NTT(small polynomial), FOUR consecutive polynomials j per thread (k % 4 == 0): every (slot, byte index) of the
+// four goes out as one 4-byte word and a warp stores 128 contiguous bytes per instruction.  (The first version stored single
+// bytes: 64 store instructions of 32 bytes per polynomial and limb.)  SIDE 3: matrix-row side, SIDE 4: dealer side (imma.cuh).
+template <int ELL, int SIDE>
+__global__ void __launch_bounds__(128) ntt_planes4_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t inner, uint8_t* __restrict__ out,
+                                                          size_t kp, size_t pstride, const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
+                                                          const u64* __restrict__ tw_sh, const uint32_t L) {
+  __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
+  const uint32_t limb = blockIdx.x % L, blk = blockIdx.x / L;
+  if (threadIdx.x < ELL) {
+    s_tw[threadIdx.x] = tw[(size_t)limb * ELL + threadIdx.x];
+    s_tw_sh[threadIdx.x] = tw_sh[(size_t)limb * ELL + threadIdx.x];
+  }
+  __syncthreads();
+  const LimbConst lc = lcs[limb];
+  const uint64_t idx = 4 * ((uint64_t)blk * blockDim.x + threadIdx.x);   // first of this thread's four polynomials (same row: inner % 4 == 0)
+  if (idx >= count) return;
+  u64 a[4][ELL];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    long long x[ELL];
+    load_small<ELL>(coef, cbytes, idx + p, x);
+#pragma unroll
+    for (int t = 0; t < ELL; t++) a[p][t] = reduce_i64(x[t], lc);
+    ntt_forward_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
+  }
+  const uint64_t r = idx / inner, j = idx % inner;
+  const size_t first = SIDE == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;
+  const size_t step = SIDE == 3 ? kp : (size_t)(count / inner) * kp;
+  uint8_t* o8 = out + (size_t)limb * ELL * pstride + first;
+#pragma unroll
+  for (int t = 0; t < ELL; t++) {
+    const u64 v[4] = {a[0][t], a[1][t], a[2][t], a[3][t]};
+    uint32_t w[8];
+    bytes_4x8(v, w);
+#pragma unroll
+    for (int b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(o8 + (size_t)t * pstride + (size_t)b * step) = w[b];
+  }
+}
+
+// Any power-of-two ring degree up to GEN_MAX_ELL (the reference accepts every power of two >= 8, parameters.rs:140-144; its
+// tests and examples use 8, 16, 32): the same transform with the coefficients in a per-thread local-memory array and run-time
+// loops.  Correct for every mode, not tuned -- the register-resident kernels above serve the parameter sets in use.
+constexpr int GEN_MAX_ELL = 256;
+__global__ void __launch_bounds__(64) ntt_small_generic_kernel(const int mode, const void* __restrict__ coef, int cbytes, const u64* __restrict__ m,
+                                                               uint64_t count, uint32_t inner, u64* __restrict__ out, size_t vstride, size_t lstride,
+                                                               const LimbConst* __restrict__ lcs, const u64* __restrict__ tw, const u64* __restrict__ tw_sh,
+                                                               const u64* __restrict__ gadget_hat, const u64* __restrict__ gadget_hat_sh,
+                                                               const u64* __restrict__ addend, const uint32_t L, const uint32_t ell) {
+  const uint32_t limb = blockIdx.x % L, blk = blockIdx.x / L;
+  const LimbConst lc = lcs[limb];
+  const uint64_t idx = (uint64_t)blk * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  u64 a[GEN_MAX_ELL];
+  for (uint32_t t = 0; t < ell; t++) {
+    long long x;
+    const uint64_t e = idx * ell + t;
+    if (cbytes == 8) x = reinterpret_cast<const long long*>(coef)[e];
+    else if (cbytes == 4) x = reinterpret_cast<const int*>(coef)[e];
+    else if (cbytes == 2) x = reinterpret_cast<const short*>(coef)[e];
+    else x = reinterpret_cast<const signed char*>(coef)[e];
+    a[t] = reduce_i64(x, lc);
+  }
+  const u64* w = tw + (size_t)limb * ell;
+  const u64* w_sh = tw_sh + (size_t)limb * ell;
+  for (uint32_t mm = 1, t = ell >> 1; mm < ell; mm <<= 1, t >>= 1)
+    for (uint32_t i = 0; i < mm; i++) {
+      const u64 s = w[mm + i], s_sh = w_sh[mm + i];
+      for (uint32_t j = 2 * i * t; j < 2 * i * t + t; j++) {
+        const u64 u = a[j], v = mulmod_shoup(a[j + t], s, s_sh, lc.q);
+        a[j] = addmod(u, v, lc.q);
+        a[j + t] = submod(u, v, lc.q);
+      }
+    }
+  if (m != nullptr) {
+    const u64 mr = reduce_i64((long long)m[idx], lc);
+    for (uint32_t t = 0; t < ell; t++)
+      a[t] = addmod(a[t], mulmod_shoup(mr, gadget_hat[(size_t)limb * ell + t], gadget_hat_sh[(size_t)limb * ell + t], lc.q), lc.q);
+  }
+  if (mode == 3 || mode == 4) {
+    const uint64_t r = idx / inner, j = idx % inner, kp = vstride;
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (size_t)limb * ell * lstride;
+    const size_t first = mode == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;
+    const size_t step = mode == 3 ? kp : (size_t)(count / inner) * kp;
+    for (uint32_t t = 0; t < ell; t++)
+      for (int b = 0; b < 8; b++) o8[(size_t)t * lstride + first + (size_t)b * step] = (uint8_t)(a[t] >> (8 * b));
+    return;
+  }
+  const uint64_t vec = idx / inner, j = idx % inner;
+  u64* dst = out + vec * vstride + (size_t)limb * lstride + j * ell;
+  for (uint32_t t = 0; t < ell; t++) {
+    u64 v = a[t];
+    if (mode == 5) v = addmod(v, addend[((size_t)vec * L + limb) * ell * inner + (size_t)t * inner + j], lc.q);
+    if (mode == 1) v = addmod(v, dst[t], lc.q);
+    dst[t] = mode == 2 ? pack_halves(v) : v;
+  }
+}
+
+bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out,
                       size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes, const u64* addend) {
-  if (count == 0) return;
-  const unsigned grid = (unsigned)(((count + 127) / 128) * T.L);
-#define PVW_NTT_CASE(E)                                                                                                       \
-  case E:                                                                                                                     \
-    if (addend)                                                                                                               \
-      ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
-    else if (planes == 1)                                                                                                     \
-      ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
-    else if (planes == 2)                                                                                                     \
-      ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
-    else if (accumulate)                                                                                                           \
-      ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
-    else if (pack_out)                                                                                                        \
-      ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
-    else                                                                                                                      \
-      ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(coef, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L);  \
+  if (count == 0) return true;
+  if (cbytes != 1 && cbytes != 2 && cbytes != 4 && cbytes != 8) return false;
+  const int mode = addend ? 5 : planes == 1 ? 3 : planes == 2 ? 4 : accumulate ? 1 : pack_out ? 2 : 0;
+  const uint64_t blocks = ((count + 127) / 128) * T.L;
+  if (blocks >= (1ull << 31)) return false;
+  const unsigned grid = (unsigned)blocks;
+  // byte planes, four polynomials per thread: needs whole groups of four inside a row and registers for 4 * ell residues
+  const bool four = (mode == 3 || mode == 4) && inner % 4 == 0 && T.ell <= 16 && m == nullptr;
+  const unsigned grid4 = (unsigned)(((count / 4 + 127) / 128) * T.L);
+#define PVW_NTT_ARGS coef, cbytes, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L
+#define PVW_NTT_CASE(E)                                                                                                          \
+  case E:                                                                                                                        \
+    if (four && mode == 3) ntt_planes4_kernel<(E <= 16 ? E : 8), 3><<<grid4, 128, 0, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L); \
+    else if (four) ntt_planes4_kernel<(E <= 16 ? E : 8), 4><<<grid4, 128, 0, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L);        \
+    else if (mode == 5) ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
+    else if (mode == 3) ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
+    else if (mode == 4) ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
+    else if (mode == 1) ntt_small_kernel<E, 1><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
+    else if (mode == 2) ntt_small_kernel<E, 2><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
+    else ntt_small_kernel<E, 0><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                                             \
     break;
   switch (T.ell) {
     PVW_NTT_CASE(8)
     PVW_NTT_CASE(16)
     PVW_NTT_CASE(32)
+    default: {
+      if (T.ell > (uint32_t)GEN_MAX_ELL) return false;
+      const uint64_t gb = ((count + 63) / 64) * T.L;
+      if (gb >= (1ull << 31)) return false;
+      ntt_small_generic_kernel<<<(unsigned)gb, 64, 0, st>>>(mode, PVW_NTT_ARGS, T.ell);
+    }
   }
 #undef PVW_NTT_CASE
+#undef PVW_NTT_ARGS
+  return true;
 }
 
 // out[b*obs + x*oxs + y*oys + c] = in[b*ibs + x*ixs + y*iys + c]; one thread per 16 bytes (blk is a multiple of 2)

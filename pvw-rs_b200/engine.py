@@ -38,6 +38,40 @@ class _Arg:
             raise PvwError("DimensionMismatch", f"{name}: expected shape {tuple(shape)}, got {tuple(got)}")
 
 
+class _SmallArg:
+    """Small signed integers (secrets, randomness, errors): int64 -- the reference's i64 -- or the narrow forms the C ABI accepts
+    (PVW_IN_SECRET_I8 for r / sk, PVW_IN_ERROR_I32 / _I16 for e, e1, e2).  The element type of the array picks the flag."""
+
+    def __init__(self, x, shape, name: str, kind: str):
+        allowed = {"secret": (1, 8), "error": (2, 4, 8)}[kind]
+        self.device = _is_device_tensor(x)
+        if self.device:
+            import torch
+            sizes = {torch.int8: 1, torch.int16: 2, torch.int32: 4, torch.int64: 8}
+            if x.dtype not in sizes or not x.is_contiguous():
+                raise PvwError("InvalidParameters", f"{name}: need a contiguous signed-integer CUDA tensor")
+            self.bytes = sizes[x.dtype]
+            self.keep, self.ptr, got = x, x.data_ptr(), tuple(x.shape)
+        else:
+            a = np.asarray(x)
+            if a.dtype not in (np.int8, np.int16, np.int32, np.int64) or a.dtype.itemsize not in allowed:
+                a = a.astype(np.int64)
+            a = np.ascontiguousarray(a)
+            self.bytes = a.dtype.itemsize
+            self.keep, self.ptr, got = a, a.ctypes.data, a.shape
+        if self.bytes not in allowed:
+            raise PvwError("InvalidParameters", f"{name}: element size {self.bytes} is not accepted for {kind} inputs (allowed: {allowed} bytes)")
+        if tuple(got) != tuple(shape):
+            raise PvwError("DimensionMismatch", f"{name}: expected shape {tuple(shape)}, got {tuple(got)}")
+        self.flag = {("secret", 1): _ffi.PVW_IN_SECRET_I8, ("error", 4): _ffi.PVW_IN_ERROR_I32, ("error", 2): _ffi.PVW_IN_ERROR_I16}.get((kind, self.bytes), 0)
+
+
+def _same_error_type(*args):
+    sizes = {a.bytes for a in args if a is not None}
+    if len(sizes) > 1:
+        raise PvwError("InvalidParameters", "error inputs of one call must share one element type")
+
+
 class Engine:
     """Owns a pvw_ctx.  `row0`/`nrows` select the shard of parties (rows of B) this context holds."""
 
@@ -215,13 +249,13 @@ class Engine:
 
     def keygen_batch(self, row: int, sk, e):
         count = int(sk.shape[0])
-        a = _Arg(sk, np.int64, (count, self.k, self.l), "sk")
-        b = _Arg(e, np.int64, (count, self.k, self.l), "e")
+        a = _SmallArg(sk, (count, self.k, self.l), "sk", "secret")
+        b = _SmallArg(e, (count, self.k, self.l), "e", "error")
         if a.device != b.device:
             raise PvwError("InvalidParameters", "sk and e must both be host or both be device arrays")
         if a.device:
             self._before_device_call()
-        self._check(self.lib.pvw_keygen_batch(self.h, row, count, a.ptr, b.ptr, _ffi.PVW_IO_DEVICE if a.device else 0))
+        self._check(self.lib.pvw_keygen_batch(self.h, row, count, a.ptr, b.ptr, (_ffi.PVW_IO_DEVICE if a.device else 0) | a.flag | b.flag))
         if a.device:
             self._after_device_call()
 
@@ -247,9 +281,10 @@ class Engine:
         lo, hi = (0, D) if c1_range is None else c1_range
         pflag = {"both": 0, "c1": _ffi.PVW_ENC_C1_ONLY, "c2": _ffi.PVW_ENC_C2_ONLY}[part]
         am = _Arg(m, np.uint64, (D, self.nrows), "m") if m is not None else None
-        ar = _Arg(r, np.int64, (D, self.k, self.l), "r")
-        ae2 = _Arg(e2, np.int64, (D, self.nrows, self.l), "e2") if e2 is not None else None
-        ae1 = _Arg(e1, np.int64, (D, self.k, self.l), "e1") if e1 is not None else None
+        ar = _SmallArg(r, (D, self.k, self.l), "r", "secret")
+        ae2 = _SmallArg(e2, (D, self.nrows, self.l), "e2", "error") if e2 is not None else None
+        ae1 = _SmallArg(e1, (D, self.k, self.l), "e1", "error") if e1 is not None else None
+        _same_error_type(ae1, ae2)
         if part != "c1" and (am is None or ae2 is None):
             raise PvwError("InvalidParameters", "m and e2 are required")
         devs = {a.device for a in (am, ar, ae2, ae1) if a is not None}
@@ -259,7 +294,8 @@ class Engine:
         if on_device:
             self._before_device_call()
         self._check(self.lib.pvw_encrypt_batch(self.h, slot0, D, lo, hi, am.ptr if am else None, ar.ptr, ae1.ptr if ae1 else None,
-                                               ae2.ptr if ae2 else None, (_ffi.PVW_IO_DEVICE if on_device else 0) | pflag))
+                                               ae2.ptr if ae2 else None,
+                                               (_ffi.PVW_IO_DEVICE if on_device else 0) | pflag | ar.flag | (ae1.flag if ae1 else ae2.flag if ae2 else 0)))
         if on_device:
             self._after_device_call()
 
@@ -291,6 +327,32 @@ class Engine:
         h = _Holder()
         h.__cuda_array_interface__ = {"shape": (count, stride), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
         return torch.as_tensor(h, device=f"cuda:{self.device}")
+
+    # -- multi-GPU c1 exchange over the copy engines (pvw_shard_*; host logic in sharding.CopyEngineExchange) ----
+    def shard_export(self, world: int) -> bytes:
+        h = _ffi.PvwShardHandle()
+        self._check(self.lib.pvw_shard_export(self.h, int(world), C.byref(h)))
+        return bytes(h.bytes)
+
+    def shard_connect(self, world: int, rank: int, handles: Sequence[bytes]):
+        if len(handles) != world or any(len(b) != 192 for b in handles):
+            raise PvwError("InvalidParameters", f"need {world} handles of 192 bytes")
+        arr = (_ffi.PvwShardHandle * world)()
+        for i, b in enumerate(handles):
+            C.memmove(C.byref(arr[i]), bytes(b), 192)
+        self._check(self.lib.pvw_shard_connect(self.h, int(world), int(rank), arr))
+
+    def shard_push_c1(self, slot0: int, count: int):
+        self._check(self.lib.pvw_shard_push_c1(self.h, int(slot0), int(count)))
+
+    def shard_wait_c1(self):
+        self._check(self.lib.pvw_shard_wait_c1(self.h))
+
+    def shard_release_c1(self):
+        self._check(self.lib.pvw_shard_release_c1(self.h))
+
+    def shard_disconnect(self):
+        self._check(self.lib.pvw_shard_disconnect(self.h))
 
     # -- wire format: bincode of the crate's serde impls, produced / parsed on the device ---------
     @property
@@ -403,7 +465,7 @@ class Engine:
         else:
             ds = None
             D = self.capacity if D is None else D
-        a = _Arg(sk, np.int64, (P, self.k, self.l), "sk")
+        a = _SmallArg(sk, (P, self.k, self.l), "sk", "secret")
         if a.device:
             if out is None:
                 import torch
@@ -411,7 +473,7 @@ class Engine:
             o = _Arg(out, np.uint64, (P, D), "out")
             self._before_device_call()
             self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr, o.ptr,
-                                                   _ffi.PVW_IO_DEVICE))
+                                                   _ffi.PVW_IO_DEVICE | a.flag))
             self._after_device_call()
             return out
         if out is not None:      # caller-provided host buffer (e.g. pinned memory): no allocation / page faults per call
@@ -421,7 +483,7 @@ class Engine:
         else:
             res = np.empty((P, D), dtype=np.uint64)
         self._check(self.lib.pvw_decrypt_batch(self.h, D, ds.ctypes.data if ds is not None else None, P, pidx.ctypes.data, a.ptr,
-                                               res.ctypes.data, 0))
+                                               res.ctypes.data, a.flag))
         return res
 
     def decode_batch(self, zhat) -> np.ndarray:

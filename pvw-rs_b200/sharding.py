@@ -59,3 +59,50 @@ def all_gather_c1(c1_store, plan: ShardPlan, group=None):
         return
     lo, hi = plan.dealer_slice(c1_store.shape[0])
     dist.all_gather_into_tensor(c1_store, c1_store[lo:hi], group=group)
+
+
+class CopyEngineExchange:
+    """The c1 exchange of a step without an all-gather kernel (include/pvw_b200.h, pvw_shard_*): every rank pushes its dealer
+    slice into the peers' ciphertext stores with copy-engine peer copies over NVLink, ordered by stream counters -- no SM, no
+    host synchronisation, so it runs under the c2 product.  This class is the host protocol only: it all-gathers the IPC
+    handles once (any torch.distributed backend; bytes travel as a uint8 tensor) and forwards the per-step calls.
+    `engine` needs shard_export / shard_connect / shard_push_c1 / shard_wait_c1 / shard_release_c1 / shard_disconnect."""
+
+    HANDLE_BYTES = 192
+
+    def __init__(self, engine, plan: ShardPlan, group=None, device=None):
+        self.engine, self.plan, self.connected = engine, plan, False
+        if plan.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        mine = torch.frombuffer(bytearray(engine.shard_export(plan.world)), dtype=torch.uint8)
+        if len(mine) != self.HANDLE_BYTES:
+            raise ValueError("unexpected handle size")
+        if device is not None:
+            mine = mine.to(device)
+        table = torch.empty(plan.world * self.HANDLE_BYTES, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(table, mine, group=group)
+        table = table.cpu().numpy().reshape(plan.world, self.HANDLE_BYTES)
+        engine.shard_connect(plan.world, plan.rank, [row.tobytes() for row in table])
+        self.connected = True
+
+    def push(self, slot0: int, D: int):
+        """after the c1 product of this rank's slice of the D dealers stored from slot0 has been queued"""
+        if self.plan.world == 1:
+            return
+        lo, hi = self.plan.dealer_slice(D)
+        self.engine.shard_push_c1(slot0 + lo, hi - lo)
+
+    def wait(self):
+        if self.plan.world > 1:
+            self.engine.shard_wait_c1()
+
+    def release(self):
+        if self.plan.world > 1:
+            self.engine.shard_release_c1()
+
+    def close(self):
+        if self.connected:
+            self.engine.shard_disconnect()
+            self.connected = False

@@ -3,7 +3,7 @@
 // warps): with equal sub-tiles the FP64 warps are the critical path, and an uneven split would add at most ~15 % to the
 // matrix kernel for a second operand / accumulator format -- not adopted.
 #pragma once
-#include "../mac_worker.cuh"
+#include "../../pvw-rs_b200/csrc/mac_worker.cuh"
 
 namespace pvw {
 

@@ -12,7 +12,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "../imma.cuh"
+#include "../../pvw-rs_b200/csrc/imma.cuh"
 
 using namespace pvw;
 

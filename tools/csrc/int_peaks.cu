@@ -9,8 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "../modarith.cuh"
-#include "../mac_worker.cuh"
+#include "../../pvw-rs_b200/csrc/modarith.cuh"
+#include "../../pvw-rs_b200/csrc/mac_worker.cuh"
 #include "fp64_worker.cuh"
 
 using namespace pvw;

@@ -1,7 +1,7 @@
 """Wall-clock breakdown of the host-buffer path vs the device-resident path (where does e2e lose time?)."""
 import os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import pvw_oracle as O
 import pvw_rs_b200 as pvw

@@ -1,6 +1,6 @@
 """Single-call encrypt / decrypt (D = 1: the reference's own call granularity, HBM-bound matrix-vector products):
 achieved GB/s of the MAC kernel on algorithmic bytes against the measured HBM copy bandwidth.
-usage: python pvw-rs_b200/tools/matvec_bw.py [n] [reps]"""
+usage: python tools/matvec_bw.py [n] [reps]"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import pvw_oracle as O  # noqa: E402
 import pvw_rs_b200 as pvw  # noqa: E402

@@ -1,6 +1,6 @@
 """Do the CUDA-core kernels (NTT, decode chain) overlap with the persistent tensor-core kernel when they run on another stream?
 Two contexts on one GPU (each has its own stream): context A encrypts (c2 product on the tensor cores), context B decrypts.
-usage: python pvw-rs_b200/tools/overlap_probe.py"""
+usage: python tools/overlap_probe.py"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import pvw_oracle as O  # noqa: E402
 import pvw_rs_b200 as pvw  # noqa: E402

@@ -7,7 +7,7 @@ one JSON line per configuration (kept under profiles/).  GPU box only.
   C5  pvw_valid_dec-style (k=1024, l=8, 4 x 56-bit, variance 10, bounds (1, 1172385)): every party decrypts only a random
       "valid" subset of the dealers (dealer index lists) -- subset == the matching entries of the full decryption
 
-usage: python pvw-rs_b200/tools/run_configs.py [C1 C2 C4 C5]
+usage: python tools/run_configs.py [C1 C2 C4 C5]
 """
 import json
 import os
@@ -17,7 +17,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import c_oracle as CO  # noqa: E402
 import pvw_oracle as O  # noqa: E402

@@ -1,12 +1,12 @@
 """Stress: repeat encrypt + decrypt on a mid-size P128 system and count iterations whose plaintexts differ from the
-messages (race hunting).  Usage: python pvw-rs_b200/tools/stress.py [iters] [opts like gemm_tile=1,refill_lag=2]"""
+messages (race hunting).  Usage: python tools/stress.py [iters] [opts like gemm_tile=1,refill_lag=2]"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import pvw_rs_b200 as pvw  # noqa: E402
 import pvw_oracle as O  # noqa: E402

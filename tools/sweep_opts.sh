@@ -1,5 +1,5 @@
 #!/bin/bash
-# Times bench.py under different tuning knobs (PVW_OPTS).  Usage (on a GPU box): bash pvw-rs_b200/tools/sweep_opts.sh "opt=a,opt2=b" ...
+# Times bench.py under different tuning knobs (PVW_OPTS).  Usage (on a GPU box): bash tools/sweep_opts.sh "opt=a,opt2=b" ...
 mkdir -p gpurun_out
 for opts in "$@"; do
   PVW_OPTS=$opts timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/sw.json 2> gpurun_out/sw.err || tail -3 gpurun_out/sw.err

@@ -1,7 +1,7 @@
 """Wire-format kernels (csrc/wire.cu) at the headline configuration: serialise / parse D ciphertexts of C3 (n=4096, k=256,
 l=8, 17 x 62-bit) between the device store and a device byte buffer; achieved GB/s on algorithmic bytes (residues read or
 written + wire bytes written or read) against the measured HBM copy bandwidth, and the host-buffer variant (PCIe inside).
-usage: python pvw-rs_b200/tools/wire_bw.py [D] [reps]"""
+usage: python tools/wire_bw.py [D] [reps]"""
 import json
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import pvw_oracle as O  # noqa: E402
 import pvw_rs_b200 as pvw  # noqa: E402

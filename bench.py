@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- party-shares encrypted + decrypted per second on the 128-bit parameter set (BASELINE.json).
+"""bench.py -- party-shares encrypted + decrypted per second (BASELINE.json), B200 arm and CPU reference arm.
 
 A "step" is one pass of the hot path over one batch of synthetic dealers:
     encrypt (c1 = A r + e1, c2 = B r + e2 + m g) for the step's dealers x all local parties, then
-    decrypt (<s, c1> - c2, l-redundant decode) of every local party x every dealer of the step.
-Workload C3 of SURVEY.md 8(d): k=256, l=8, 17 x 62-bit moduli (Q 1054 bit), n=4096 parties.
-Multi-GPU (one process per GPU, torchrun): rows of B / parties are sharded across ranks, A is broadcast once over
-NCCL, every rank computes c1 for its slice of the step's dealers and the slices are all-gathered over NCCL; the
-number of dealers per step grows with the rank count so that the per-GPU work is fixed ("weak").
+    decrypt (<s, c1> - c2, l-redundant decode) of every local party x the step's dealers (C5: x a random "valid" subset).
+Workloads (BASELINE.json `configs`), selected with --config; C3 is the one the metric is quoted on:
+    C1  examples/pvw.rs defaults             n=7,    k=32,   l=8,  2 moduli
+    C2  128-bit set                          n=1024, k=256,  l=8,  17 x 62-bit
+    C3  128-bit set (headline, default)      n=4096            (--parties 8192: the north_star target size)
+    C4  256-bit set                          n=8192, k=512,  l=16, 34 x 62-bit, rows of B sharded over the GPUs
+    C5  examples/pvw_valid_dec.rs:40-52      k=1024, l=8, 4 x 56-bit, variance 10, bounds (1, 1 172 385); n=4096 by default,
+        --parties 1024 / 16384 for the sweep; every party decrypts only a random valid subset of the dealers (:161-210)
+Multi-GPU (one process per GPU, torchrun): rows of B / parties are sharded across ranks, A is broadcast once over NCCL,
+every rank computes c1 for its slice of the step's dealers and the slices are exchanged -- by default with copy-engine peer
+copies ordered by stream counters (pvw_shard_*, under the c2 product), optionally with an NCCL all-gather or by replicating
+the c1 product.  Dealers per step grow with the rank count so that the per-GPU work is fixed ("weak").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--dealers D_per_gpu] [--impl reference]
+  python bench.py [--config C3] [--gpus N] [--steps K] [--warmup W] [--dealers D_per_gpu] [--parties n] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same through the host-buffer C-ABI
-calls (H2D of r/e1/e2/m/sk and D2H of the plaintexts inside the timed region), `roofline` = the MAC kernel against
-the measured HBM peak on algorithmic bytes, `cpu_baseline` = the oracle port on the host cores (bounded sample).
+calls (H2D of m / r / e1 / e2 / sk and D2H of the plaintexts inside the timed region), `roofline` = the dominant kernel
+against the tensor-pipe / HBM peak, `cpu_baseline` = the oracle port on the host cores (bounded sample).
 """
 from __future__ import annotations
 
@@ -24,6 +31,8 @@ import subprocess
 import sys
 import threading
 import time
+from dataclasses import dataclass
+from typing import List
 
 import numpy as np
 
@@ -34,25 +43,53 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 METRIC = "party-shares encrypted+decrypted/sec"
 UNIT = "shares/s"
-N_PARTIES, K_DIM, ELL, N_LIMBS = 4096, 256, 8, 17
 SEED = 0x5056572D42323030
 
 
-def p128_moduli():
-    import pvw_oracle as O          # parameter-set definition only (prime search), not on any timed path
-    return O.largest_ntt_primes(N_LIMBS)
+@dataclass
+class Workload:
+    key: str
+    title: str
+    n: int
+    k: int
+    l: int
+    moduli: List[int]
+    variance: float
+    b1: int
+    b2: int
+    dealers: int          # per GPU per step
+    msg: str              # "u62": uniform 62-bit messages; "share": d*1000 + p + 1 (examples/pvw.rs:98-100)
+    subset: bool          # decrypt a random valid subset of the dealers (examples/pvw_valid_dec.rs:161-210)
+    cpu_dealers: int      # dealers of the cpu_baseline sample
+    cpu_rows: int         # parties of the cpu_baseline sample (extrapolated linearly to n when smaller)
+
+    @property
+    def L(self):
+        return len(self.moduli)
+
+    def name(self, n):
+        qbits = sum(q.bit_length() for q in self.moduli)
+        what = "encrypt + subset decrypt (valid dealers only)" if self.subset else "encrypt + all-party decrypt"
+        return f"{self.title}: n={n} parties, k={self.k}, l={self.l}, L={self.L} moduli (Q ~{qbits} bit); {what}"
+
+    def bytes_per_share(self, n):
+        """algorithmic bytes per encrypted + decrypted share."""
+        poly = 8 * self.L * self.l
+        enc = ((self.k * self.k + n * self.k) * poly + (self.k + n) * poly + 8 * (2 * self.k * self.l + n * self.l + n)) / n
+        dec = self.k * poly + poly + 8
+        return enc + dec
 
 
-def workload_name(n=N_PARTIES):
-    return f"C3 P128: n={n} parties, k={K_DIM}, l={ELL}, L={N_LIMBS}x62-bit (Q 1054 bit); encrypt + all-party decrypt"
-
-
-def bytes_per_share(n=N_PARTIES):
-    """algorithmic bytes per encrypted + decrypted share."""
-    poly = 8 * N_LIMBS * ELL
-    enc = ((K_DIM * K_DIM + n * K_DIM) * poly + (K_DIM + n) * poly + 8 * (2 * K_DIM * ELL + n * ELL + n)) / n
-    dec = K_DIM * poly + poly + 8
-    return enc + dec
+def workloads():
+    import pvw_oracle as O          # parameter-set definitions only (prime search), not on any timed path
+    p128 = O.largest_ntt_primes(17)
+    return {
+        "C1": Workload("C1", "C1 examples/pvw.rs defaults", 7, 32, 8, list(O.EX_MODULI), 0.5, 50, 50, 7, "share", False, 7, 7),
+        "C2": Workload("C2", "C2 P128", 1024, 256, 8, p128, 0.5, 100, 200, 256, "u62", False, 128, 1024),
+        "C3": Workload("C3", "C3 P128", 4096, 256, 8, p128, 0.5, 100, 200, 256, "u62", False, 64, 4096),
+        "C4": Workload("C4", "C4 P256", 8192, 512, 16, O.largest_ntt_primes(34), 0.5, 100, 200, 32, "u62", False, 8, 4096),
+        "C5": Workload("C5", "C5 pvw_valid_dec-style", 4096, 1024, 8, list(O.VD_MODULI), 10.0, 1, 1172385, 256, "share", True, 64, 4096),
+    }
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -104,72 +141,116 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle port (the reference itself is Rust + un-vendored fhe-math: not buildable here)
+# CPU legs: the oracle port (the reference itself is Rust + un-vendored fhe-math: not buildable here).  One sample =
+# c1 for Dc dealers, c2 + decrypt for Dc dealers x n_s parties; a step of the real workload costs
+#     t_c1 + (n / n_s) * (t_c2 + frac_dec * t_dec)        (every term is linear in the parties; frac_dec = valid / all dealers)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_inputs(P, D, B=None):
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(co, A, B, sk, m, r, e1, e2, n_total, frac_dec=1.0):
+    """times the three legs on B [n_s][k][L][l], sk [n_s][k][l], m [Dc][n_s], e2 [Dc][n_s][l]; returns (shares/s, seconds, c1, c2, dec)"""
+    Dc, n_s = m.shape
+    t0 = time.perf_counter()
+    c1, _ = co.encrypt(A, B[:1], m[:, :1], r, e1, e2[:, :1], want_c2=False)
+    t1 = time.perf_counter()
+    _, c2 = co.encrypt(A, B, m, r, e1, e2, want_c1=False)
+    t2 = time.perf_counter()
+    dec = co.decrypt(sk, c1, c2)
+    t3 = time.perf_counter()
+    step_s = (t1 - t0) + (n_total / n_s) * ((t2 - t1) + frac_dec * (t3 - t2))
+    return Dc * n_total / step_s, t3 - t0, c1, c2, dec
+
+
+def cpu_uniform_inputs(P, W, Dc, n_s):
     import c_oracle as CO
     import pvw_oracle as O
     A = CO.synth_crs_np(P)
-    if B is None:   # uniform rows: identical arithmetic and memory traffic, plaintexts are not recovered
-        u = CO.stream_np(SEED, O.TAG_B, 0, P.n * P.k * P.L * P.l).reshape(P.n, P.k, P.L, P.l)
-        B = CO._mulhi_np(u, np.broadcast_to(np.array(P.moduli, dtype=np.uint64).reshape(1, 1, P.L, 1), u.shape))
-    sk = CO.synth_small_np(P, O.TAG_SK, P.n, P.k, "cbd")
-    m = CO.synth_messages_np(P, D, "u63")
-    r = CO.synth_small_np(P, O.TAG_R, D, P.k, "cbd")
-    e1 = CO.synth_small_np(P, O.TAG_E1, D, P.k, "uniform", P.error_bound_1)
-    e2 = CO.synth_small_np(P, O.TAG_E2, D, P.n, "uniform", P.error_bound_2)
-    return A, B, sk, m, r, e1, e2
+    # uniform rows: identical arithmetic and memory traffic, plaintexts are not recovered (SURVEY 8d)
+    u = CO.stream_np(SEED, O.TAG_B, 0, n_s * P.k * P.L * P.l).reshape(n_s, P.k, P.L, P.l)
+    B = CO._mulhi_np(u, np.broadcast_to(np.array(P.moduli, dtype=np.uint64).reshape(1, 1, P.L, 1), u.shape))
+    kind = "cbd"
+    sk = CO.synth_small_np(P, O.TAG_SK, n_s, P.k, kind)
+    m = CO.synth_messages_np(P, Dc, "u63")[:, :n_s]
+    r = CO.synth_small_np(P, O.TAG_R, Dc, P.k, kind)
+    e1 = CO.synth_small_np(P, O.TAG_E1, Dc, P.k, "uniform", W.b1)
+    e2 = CO.synth_small_np(P, O.TAG_E2, Dc, n_s, "uniform", W.b2)
+    return A, B, sk, np.ascontiguousarray(m), r, e1, e2
 
 
-def cpu_step(co, A, B, sk, m, r, e1, e2):
-    c1, c2 = co.encrypt(A, B, m, r, e1, e2)
-    return co.decrypt(sk, c1, c2)
-
-
-def run_reference(args):
+def run_reference(args, W: Workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import c_oracle as CO
     import pvw_oracle as O
-    n = args.parties
-    P = O.Params(n, K_DIM, ELL, p128_moduli())
+    n = args.parties or W.n
+    n_s = min(n, W.cpu_rows)
+    P = O.Params(n_s, W.k, W.l, W.moduli, secret_variance=W.variance, error_bound_1=W.b1, error_bound_2=W.b2)
     co = CO.COracle(P)
-    D = args.cpu_dealers
-    A, B, sk, m, r, e1, e2 = cpu_inputs(P, D)
+    cores = host_cores()
+    co.set_threads(cores)          # torch.distributed.run exports OMP_NUM_THREADS=1: the reference's rayon pool uses every core
+    D = args.cpu_dealers or max(1, W.cpu_dealers // 4)
+    frac = subset_fraction(W, W.dealers) if W.subset else 1.0
+    A, B, sk, m, r, e1, e2 = cpu_uniform_inputs(P, W, D, n_s)
     for _ in range(args.warmup):
-        cpu_step(co, A, B, sk, m[:1], r[:1], e1[:1], e2[:1])
+        cpu_sample(co, A, B[:8], sk[:8], m[:1, :8], r[:1], e1[:1], e2[:1, :8], n, frac)
     t0 = time.perf_counter()
+    vals = []
     for _ in range(args.steps):
-        cpu_step(co, A, B, sk, m, r, e1, e2)
+        vals.append(cpu_sample(co, A, B, sk, m, r, e1, e2, n, frac)[0])
     dt = time.perf_counter() - t0
-    val = args.steps * D * n / dt
-    sample = f"{D} dealers x {n} parties per step (encrypt + all-party decrypt), uniform synthetic B, {co.threads} OpenMP threads"
+    val = len(vals) / sum(1.0 / v for v in vals)                    # shares / total extrapolated step time
+    sample = (f"per step: c1 for {D} dealers + (c2, decrypt) for {D} dealers x {n_s} of the {n} parties, scaled linearly to n "
+              f"({'valid-subset fraction %.3f of the decryptions; ' % frac if W.subset else ''}uniform synthetic B); {co.threads} OpenMP threads; "
+              f"{dt:.1f} s for {args.steps} steps")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * D * n / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "dealers_per_step": D, "note": "CPU port of the reference path (oracle/pvw_oracle.c); "
-                       "the Rust crate and its fhe-math dependency cannot be built in this image"},
+            "config": {"workload": W.name(n), "dealers_per_step": D, "dealers_per_step_note": "the metric is per share: the B200 arm batches "
+                       f"{W.dealers} dealers per GPU and step of the same workload, this arm a bounded sample of it",
+                       "note": "CPU port of the reference path (oracle/pvw_oracle.c, OpenMP over dealers x parties like the crate's rayon loops); "
+                               "the Rust crate and its fhe-math dependency cannot be built in this image"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": co.threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+def subset_fraction(W: Workload, D: int) -> float:
+    return len(valid_subset(D)) / D
+
+
+def valid_subset(D: int) -> np.ndarray:
+    """threshold-style subset of a step's dealers (pvw_valid_dec.rs:161-195): t + U[0, D - t] of them, t = ceil(2 D / 5), random order"""
+    rng = np.random.default_rng(5)
+    t = -(-2 * D // 5)
+    return rng.permutation(D)[: t + rng.integers(0, D - t + 1)].astype(np.uint32)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------------------------------
-def synth_device(torch, dev, gen, shape, kind, bound=None):
-    if kind == "cbd":        # CBD(0.5): {-1, 0, 1}
-        b = torch.randint(0, 4, shape, device=dev, generator=gen, dtype=torch.int64)
-        return (b & 1) - ((b >> 1) & 1)
+def synth_device(torch, dev, gen, shape, kind, bound=None, variance=0.5):
+    if kind == "cbd":
+        if abs(variance - 0.5) < 1e-6:   # CBD(0.5): {-1, 0, 1}
+            b = torch.randint(0, 4, shape, device=dev, generator=gen, dtype=torch.int64)
+            return (b & 1) - ((b >> 1) & 1)
+        v = int(variance)                 # CBD(v): popcount(2v bits) - popcount(2v bits)  (uniform.rs:38-67)
+        a = torch.randint(0, 2, tuple(shape) + (2 * v,), device=dev, generator=gen, dtype=torch.int8).sum(-1, dtype=torch.int64)
+        b = torch.randint(0, 2, tuple(shape) + (2 * v,), device=dev, generator=gen, dtype=torch.int8).sum(-1, dtype=torch.int64)
+        return a - b
     if kind == "uniform":
         return torch.randint(-bound, bound + 1, shape, device=dev, generator=gen, dtype=torch.int64)
-    if kind == "u63":
+    if kind == "u62":
         return torch.randint(0, 2 ** 62, shape, device=dev, generator=gen, dtype=torch.int64)
     raise ValueError(kind)
 
 
-def run_b200(args):
+def run_b200(args, W: Workload):
     import torch
     import torch.distributed as dist
     import pvw_rs_b200 as pvw
@@ -181,17 +262,18 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    n, k, l, L = args.parties, K_DIM, ELL, N_LIMBS
+    n, k, l, L = args.parties or W.n, W.k, W.l, W.L
+    moduli = W.moduli
     plan = pvw.sharding.ShardPlan(n, world, rank)
     nrows, row0 = plan.nrows, plan.row0
-    Dg = args.dealers                 # dealers per GPU per step (this rank's c1 slice)
+    Dg = args.dealers or W.dealers    # dealers per GPU per step (this rank's c1 slice)
     D = Dg * world                    # dealers per step
     c1_lo, c1_hi = plan.dealer_slice(D)
-    moduli = p128_moduli()
+    exchange = args.c1_exchange if world > 1 else "none"
 
-    eng = pvw.Engine(n, k, l, moduli, row0=row0, nrows=nrows, device=local)
+    eng = pvw.Engine(n, k, l, moduli, secret_variance=W.variance, error_bound_1=W.b1, error_bound_2=W.b2, row0=row0, nrows=nrows, device=local)
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
-    for kv in filter(None, os.environ.get("PVW_OPTS", "").split(",")):     # tuning knobs, e.g. PVW_OPTS=gemm_tile=0,refill_lag=1
+    for kv in filter(None, os.environ.get("PVW_OPTS", "").split(",")):     # tuning knobs, e.g. PVW_OPTS=imma=0
         name, val = kv.split("=")
         eng.set_option(name.strip(), int(val))
 
@@ -206,54 +288,75 @@ def run_b200(args):
         dist.broadcast(A, 0)
     torch.cuda.synchronize()
     eng.crs_upload(A)
-    gen.manual_seed((SEED >> 8) & 0x7FFFFFFF)       # identical key material on every rank; each keeps its slice
-    sk_all = synth_device(torch, dev, gen, (n, k, l), "cbd")
-    sk = sk_all[row0:row0 + nrows].contiguous()
-    del sk_all
+    del A
     gen.manual_seed(1000 + rank)
-    for p0 in range(0, nrows, 512):
-        cnt = min(512, nrows - p0)
-        ke = synth_device(torch, dev, gen, (cnt, k, l), "uniform", 100)
+    sk = synth_device(torch, dev, gen, (nrows, k, l), "cbd", variance=W.variance)
+    kchunk = max(1, min(512, (256 << 20) // (k * L * l * 8)))
+    for p0 in range(0, nrows, kchunk):
+        cnt = min(kchunk, nrows - p0)
+        ke = synth_device(torch, dev, gen, (cnt, k, l), "uniform", W.b1)
         eng.keygen_batch(row0 + p0, sk[p0:p0 + cnt].contiguous(), ke)
     eng.synchronize()
     eng.ct_reserve(D)
+    xch = pvw.sharding.CopyEngineExchange(eng, plan, device=dev) if exchange == "ce" else None
 
     # ---- the step's synthetic inputs: same dealers on every rank (r, e1), local columns of m / e2 ---------------
     gen.manual_seed(77)
-    r = synth_device(torch, dev, gen, (D, k, l), "cbd")
-    e1 = synth_device(torch, dev, gen, (D, k, l), "uniform", 100)
+    r = synth_device(torch, dev, gen, (D, k, l), "cbd", variance=W.variance)
+    e1 = synth_device(torch, dev, gen, (D, k, l), "uniform", W.b1)
     gen.manual_seed(78 + rank)
-    m = synth_device(torch, dev, gen, (D, nrows), "u63")
-    e2 = synth_device(torch, dev, gen, (D, nrows, l), "uniform", 200)
-    out = torch.empty((nrows, D), dtype=torch.int64, device=dev)
+    if W.msg == "share":
+        m = (torch.arange(D, device=dev, dtype=torch.int64).reshape(D, 1) * 1000 + torch.arange(row0, row0 + nrows, device=dev, dtype=torch.int64).reshape(1, nrows) + 1).contiguous()
+    else:
+        m = synth_device(torch, dev, gen, (D, nrows), "u62")
+    e2 = synth_device(torch, dev, gen, (D, nrows, l), "uniform", W.b2)
+    valid = valid_subset(D) if W.subset else None
+    Dv = len(valid) if W.subset else D
+    out = torch.empty((nrows, Dv), dtype=torch.int64, device=dev)
     parties = np.arange(row0, row0 + nrows, dtype=np.uint32)
-    c1_view = eng.c1_store_tensor(0, D) if world > 1 else None
+    c1_view = eng.c1_store_tensor(0, D) if exchange == "nccl" else None
+    vt = torch.from_numpy(valid.astype(np.int64)).to(dev) if W.subset else None
 
-    def encrypt_and_gather(m_, r_, e1_, e2_):
-        """c1 slice + c2 in one call, then the in-place all-gather of the c1 slices ordered on the library's stream.  (Issuing
-        c1 first, its all-gather on a side stream and the c2 product meanwhile -- PVW_ENC_C1_ONLY / C2_ONLY -- was measured
-        slower: 692.7 M against 738.6 M shares/s on 8 GPUs; the NCCL kernel does not co-reside with the persistent product.)"""
-        eng.encrypt_batch(0, m_, r_, e1_, e2_, c1_range=(c1_lo, c1_hi))
-        if world > 1:
+    def step(m_, r_, e1_, e2_, sk_, out_):
+        """encrypt + c1 exchange + decrypt; the arguments are all device tensors or all host arrays"""
+        if exchange == "ce":        # c1 slice first, its peer copies run on the copy engines under the c2 product
+            eng.encrypt_batch(0, None, r_, e1_, None, c1_range=(c1_lo, c1_hi), part="c1")
+            xch.push(0, D)
+            eng.encrypt_batch(0, m_, r_, None, e2_, part="c2")
+            xch.wait()
+        elif exchange == "nccl":    # one call, then the in-place all-gather ordered on the library's stream
+            eng.encrypt_batch(0, m_, r_, e1_, e2_, c1_range=(c1_lo, c1_hi))
             with torch.cuda.stream(ext):
                 pvw.sharding.all_gather_c1(c1_view, plan)
+        elif exchange == "replicate":   # every rank computes the whole of c1: no exchange, world x the c1 product
+            eng.encrypt_batch(0, m_, r_, e1_, e2_)
+        else:
+            eng.encrypt_batch(0, m_, r_, e1_, e2_, c1_range=(c1_lo, c1_hi))
+        res = eng.decrypt_batch(parties, sk_, D=None if W.subset else D, dealer_slots=valid, out=out_)
+        if exchange == "ce":
+            xch.release()
+        return res
 
     def step_device():
-        encrypt_and_gather(m, r, e1, e2)
-        eng.decrypt_batch(parties, sk, D=D, out=out)
+        return step(m, r, e1, e2, sk, out)
 
-    # host-buffer path (e2e): pinned host inputs, H2D inside the library calls, plaintexts read back to the host
+    # host-buffer path (e2e): pinned host inputs, H2D inside the library calls, plaintexts read back to the host.
+    # Narrow element types (PVW_IN_SECRET_I8 / PVW_IN_ERROR_*): the values are tiny, the reference's i64 is 8x / 2-4x the bytes.
+    etype = torch.int16 if max(W.b1, W.b2) < (1 << 15) else torch.int32
     pin = lambda t: t.cpu().pin_memory()
-    h_m, h_r, h_e1, h_e2, h_sk = pin(m), pin(r), pin(e1), pin(e2), pin(sk)
-    n_m, n_r, n_e1, n_e2, n_sk = (t.numpy() for t in (h_m, h_r, h_e1, h_e2, h_sk))
-    n_m = n_m.view(np.uint64)
-
-    h_out = torch.empty((nrows, D), dtype=torch.int64).pin_memory()
+    h64 = {"m": pin(m), "r": pin(r), "e1": pin(e1), "e2": pin(e2), "sk": pin(sk)}
+    hn = {"m": h64["m"], "r": pin(r.to(torch.int8)), "e1": pin(e1.to(etype)), "e2": pin(e2.to(etype)), "sk": pin(sk.to(torch.int8))}
+    n64 = {kk: v.numpy() for kk, v in h64.items()}
+    nn = {kk: v.numpy() for kk, v in hn.items()}
+    n_m = n64["m"].view(np.uint64)
+    h_out = torch.empty((nrows, Dv), dtype=torch.int64).pin_memory()
     n_out = h_out.numpy().view(np.uint64)
 
     def step_host():
-        encrypt_and_gather(n_m, n_r, n_e1, n_e2)
-        return eng.decrypt_batch(parties, n_sk, D=D, out=n_out)
+        return step(n_m, nn["r"], nn["e1"], nn["e2"], nn["sk"], n_out)
+
+    def step_host_i64():
+        return step(n_m, n64["r"], n64["e1"], n64["e2"], n64["sk"], n_out)
 
     def barrier():
         if world > 1:
@@ -274,11 +377,12 @@ def run_b200(args):
         return float(ms.item())
 
     # ---- correctness guard: the plaintexts of the step are the messages (genuine keys) -------------------------
+    want = m if not W.subset else m[vt]
     step_device()
     eng.synchronize()
-    bad_dev = (out.t() != m)
-    res_host = step_host()
-    bad_host = torch.from_numpy(res_host.view(np.int64).T != n_m.view(np.int64))
+    bad_dev = (out.t() != want)
+    res_host = step_host().copy()
+    bad_host = torch.from_numpy(res_host.view(np.int64).T != want.cpu().numpy())
     for name, bad in (("device-resident", bad_dev), ("host-buffer", bad_host)):
         if bool(bad.any().item()):
             idx = bad.nonzero()
@@ -287,7 +391,8 @@ def run_b200(args):
                              f"{idx[:, 1].unique().numel()}) -- refusing to report a number")
 
     # ---- value: inputs resident in HBM ------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3) - 1):
+    warm = max(args.warmup, 3)
+    for _ in range(warm - 1):
         step_device()
     eng.set_option("profile", 2)
     l0 = eng.launch_count
@@ -307,17 +412,44 @@ def run_b200(args):
         step_host()
     ms_e2e = timed(step_host, args.steps)
     e2e_value = shares_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(a.nbytes for a in (n_m, n_r, n_e2, n_sk)) + n_e1[c1_lo:c1_hi].nbytes + parties.nbytes
-    d2h = nrows * D * 8
+    small = lambda d: d["r"].nbytes + d["sk"].nbytes + d["e2"].nbytes + d["e1"][c1_lo:c1_hi].nbytes
+    h2d = n_m.nbytes + small(nn) + parties.nbytes + (valid.nbytes if W.subset else 0)
+    d2h = nrows * Dv * 8
+    # the same with the reference's i64 element type for every small input
+    e2e_steps = max(2, args.steps // 2)
+    step_host_i64()
+    ms_e2e64 = timed(step_host_i64, e2e_steps)
+    # ... and with every ciphertext of the step returned to the host in the crate's wire format (a caller of the reference API
+    # owns PvwCiphertext values; `e2e` keeps them in the device store, where the decryption of the same box reads them)
+    wire = None
+    try:
+        wl = eng.wire_layout
+        blob = torch.empty((D, int(wl.ciphertext_bytes)), dtype=torch.uint8).pin_memory()
+        nblob = blob.numpy()
+
+        def step_wire():
+            r_ = step_host()
+            eng.wire_ct_serialize(0, D, out=nblob)
+            return r_
+        step_wire()
+        ws = max(2, args.steps // 3)
+        ms_wire = timed(step_wire, ws)
+        wire = {"value": shares_per_step * ws / (ms_wire * 1e-3), "unit": UNIT, "ms_per_step": ms_wire / ws,
+                "d2h_ciphertext_bytes_per_step": int(D * wl.ciphertext_bytes),
+                "what": "e2e + bincode(PvwCiphertext) of every dealer of the step written to pinned host memory (pvw_wire_ct_serialize)"}
+        del blob, nblob
+    except Exception as ex:           # the wire leg is informative; never lose the headline to it
+        wire = {"error": str(ex)[:200]}
 
     # ---- the reference's own call granularity: ONE encrypt / ONE decrypt_party_shares-per-party pass (D = 1).  The MAC kernel
     # is then a matrix-vector product that must stream B (or the secret keys) from HBM once: the HBM-bound case of the path.
     single = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
         single = {}
+        out1 = torch.empty((nrows, 1), dtype=torch.int64, device=dev)
         for name, fn in (("encrypt", lambda: eng.encrypt_batch(0, m[:1], r[:1], e1[:1], e2[:1], c1_range=(0, 1))),
-                         ("decrypt_all_parties", lambda: eng.decrypt_batch(parties, sk, D=1, out=out[:, :1].contiguous()))):
+                         ("decrypt_all_parties", lambda: eng.decrypt_batch(parties, sk, D=1, out=out1))):
             fn()
             eng.set_option("profile", 2)
             reps = 10
@@ -333,6 +465,10 @@ def run_b200(args):
         del flush
 
     if rank != 0:
+        if xch is not None:
+            eng.synchronize()
+            barrier()
+            xch.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -347,42 +483,40 @@ def run_b200(args):
     mac_ms, mac_n, mac_bytes = prof["mac_gemm"]
     achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     kernel_ms = {kname: round(v[0] / args.steps, 4) for kname, v in prof.items()}
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "mac_gemm_traffic.json")
-    if os.path.exists(tpath):
+
+    def json_lines(path, key):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            for ln in open(os.path.join(ROOT, "profiles", path)):
+                if key in ln:
+                    return float(json.loads(ln)[key])
         except Exception:
-            traffic = None
-    int_peak = None
-    try:
-        for ln in open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")):
-            if "mac_karatsuba_per_s" in ln:
-                int_peak = float(json.loads(ln)["mac_karatsuba_per_s"])
-    except Exception:
-        pass
+            pass
+        return None
+
+    def traffic_of(path):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", path))).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    traffic = traffic_of("r02_imma_gemm_traffic.json") or traffic_of("r01_imma_gemm_traffic.json") if W.key == "C3" else None
+    int_peak = json_lines("r01_int_peaks.json", "mac_karatsuba_per_s")
+    shoup_peak = json_lines("r01_int_peaks.json", "mulmod_shoup_per_s")
     mac_rate = (mac_bytes / ((k + 1.0) * 8)) * k / (mac_ms * 1e-3) if mac_ms > 0 else 0.0
-    # NTT kernel against the measured Shoup modular-multiply rate: forward butterflies + gadget multiplies per step
-    shoup_peak = None
-    try:
-        for ln in open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")):
-            if "mulmod_shoup_per_s" in ln:
-                shoup_peak = float(json.loads(ln)["mulmod_shoup_per_s"])
-    except Exception:
-        pass
+    # NTT kernels against the measured Shoup modular-multiply rate: forward butterflies + gadget multiplies per step
     ntt_ms, ntt_n, _ = prof["ntt_small"]
-    polys = args.steps * (D * k + (c1_hi - c1_lo) * k + D * nrows + nrows * k)          # r, e1 slice, e2 (+m), sk
+    c1_dealers = D if exchange == "replicate" else (c1_hi - c1_lo)
+    polys = args.steps * (D * k + c1_dealers * k + D * nrows + nrows * k)          # r, e1 slice, e2 (+m), sk
     log2l = l.bit_length() - 1
     ntt_mulmods = polys * L * ((l // 2) * log2l) + args.steps * D * nrows * L * l        # butterflies + m * g_hat
     ntt_rate = ntt_mulmods / (ntt_ms * 1e-3) if ntt_ms > 0 else 0.0
     # The batched product runs on the INT8 tensor cores (csrc/imma.cu): 64 u8 x u8 multiply-accumulates per 62-bit one, so the
-    # kernel's roof is the tensor pipe.  Peak: kind::i8 issues K = 32 per instruction where bf16 issues K = 16 at the same
-    # cadence, i.e. twice the dense bf16 rate.  MEASURED_PEAKS.json holds the measured cuBLAS bf16 figures; the product runs in
-    # bursts of <= 2 ms between CUDA-core kernels (tensor duty 43 % of the step), so the burst figure is the denominator and the
-    # fractions against the sustained figure and the nominal 4.5 POP/s are reported next to it.
+    # kernel's roof is the tensor pipe.  Peak: the rate measured on this part with the kernel's own MMA stream and nothing else
+    # (tools/csrc/imma_probe.cu mode 4: operands resident in shared memory, no epilogue -> profiles/r02_int8_peak.json) when that
+    # file exists, else twice the measured cuBLAS bf16 burst (kind::i8 issues K = 32 per instruction where bf16 issues 16).
     imma_on = os.environ.get("PVW_OPTS", "").replace(" ", "").find("imma=0") < 0
     bf16 = float(peaks.get("bf16_tflops", 2250.0))
-    int8_peak = 2.0 * bf16
+    int8_meas = json_lines("r02_int8_peak.json", "int8_tops_mma_only")
+    int8_peak = int8_meas if int8_meas else 2.0 * bf16
     int8_peak_sustained = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0)))
     int8_ops = mac_rate * 64 * 2 / 1e12
     hbm_view = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -391,9 +525,10 @@ def run_b200(args):
     if imma_on:
         roofline = {"bound": "tensor", "kernel": "mac_gemm (imma_gemm_kernel: tcgen05.mma kind::i8)", "achieved": int8_ops, "peak": int8_peak,
                     "unit": "TOP/s (u8 x u8 -> s32, dense)", "frac": int8_ops / int8_peak,
-                    "peak_source": ("2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "2 x nominal dense bf16 (fallback)"),
-                    "frac_of_2x_sustained_bf16": int8_ops / int8_peak_sustained, "frac_of_nominal_4500_TOPs": int8_ops / 4500.0,
-                    "ncu_tensor_pipe_pct_of_peak": "63 % (sm__ops_path_tensor_op_utcimma_src_int8, c2 launch, profiles/r01_imma_gemm_ncu_summary.json)",
+                    "peak_source": ("measured on B200: the kernel's MMA stream alone, operands resident, no epilogue (profiles/r02_int8_peak.json)" if int8_meas
+                                    else "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "2 x nominal dense bf16 (fallback)"),
+                    "frac_of_2x_burst_bf16": int8_ops / (2.0 * bf16), "frac_of_2x_sustained_bf16": int8_ops / int8_peak_sustained,
+                    "frac_of_nominal_4500_TOPs": int8_ops / 4500.0,
                     "traffic": traffic, "ops_per_launch": mac_rate * 128 * (mac_ms * 1e-3) / max(mac_n, 1),
                     "int8_macs_per_62bit_mac": 64}
     else:
@@ -405,7 +540,7 @@ def run_b200(args):
                 "kernel_ms_per_step": kernel_ms, "kernel_share_of_step": round(mac_ms / ms_total, 4),
                 "ntt": {"kernel": "ntt_small", "achieved": ntt_rate, "peak": shoup_peak, "unit": "Shoup modular multiplies/s",
                         "frac": (ntt_rate / shoup_peak) if shoup_peak else None,
-                        "what": "forward butterflies + gadget multiplies of r, e1, e2, sk per step over the kernel's event time; peak = "
+                        "what": "forward butterflies + gadget multiplies of r, e1, e2, sk per step over the kernels' event time; peak = "
                                 "register-resident mulmod_shoup loop (profiles/r01_int_peaks.json)"},
                 "single_call": {"what": "D = 1 (one reference-style encrypt call / one all-party decrypt pass): HBM-bound matrix-vector "
                                         "form on the CUDA cores (mac.cu), L2 flushed between calls, rows = %d" % nrows,
@@ -413,49 +548,66 @@ def run_b200(args):
                 "modmuladds_per_s": mac_rate,
                 "integer_pipe": {"achieved": mac_rate, "peak": int_peak, "unit": "62-bit modular multiply-accumulates/s",
                                  "frac": (mac_rate / int_peak) if int_peak else None,
-                                 "peak_source": "ceiling of the CUDA-core form (3 IMAD.WIDE + carries per MAC, csrc/tools/int_peaks.cu, "
+                                 "peak_source": "ceiling of the CUDA-core form (3 IMAD.WIDE + carries per MAC, tools/csrc/int_peaks.cu, "
                                                 "profiles/r01_int_peaks.json): the tensor-core kernel is measured against it for scale"},
                 "note": "batched encrypt / decrypt multiply on the INT8 tensor cores: operands are byte planes, the 64 byte products of a "
                         "62-bit multiply accumulate on overlapping windows of the TMEM accumulator into 15 diagonal sums, recombined and "
                         "reduced exactly in the epilogue (DESIGN.md 4); PVW_OPTS=imma=0 runs the CUDA-core kernel instead"})
 
-    # ---- CPU baseline: oracle port on the host cores, bounded sample -------------------------------------------------
+    # ---- CPU baseline: oracle port on the host cores, bounded sample, checked bit for bit against the GPU ---------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import c_oracle as CO
         import pvw_oracle as O
-        P = O.Params(n, k, l, moduli, psi=eng.psi)
+        n_s = min(n, W.cpu_rows)
+        Dc = min(args.cpu_baseline_dealers or W.cpu_dealers, Dg)
+        P = O.Params(n_s, k, l, moduli, psi=eng.psi, secret_variance=W.variance, error_bound_1=W.b1, error_bound_2=W.b2)
         co = CO.COracle(P)
-        Dc = min(args.cpu_baseline_dealers, Dg)
+        co.set_threads(host_cores())
         A_h = eng.crs_download()
-        B_h = eng.pk_download_rows(0, n)
-        r_h, e1_h, e2_h, m_h, sk_h = n_r[:Dc], n_e1[:Dc], n_e2[:Dc], n_m[:Dc], n_sk
-        t0 = time.perf_counter()
-        c1_h, c2_h = co.encrypt(A_h, B_h, m_h, r_h, e1_h, e2_h)
-        dec_h = co.decrypt(sk_h, c1_h, c2_h)
-        dt = time.perf_counter() - t0
-        # the CPU port and the GPU agree on this sample (same keys, same randomness): plaintexts and ciphertext of dealer 0
+        B_h = eng.pk_download_rows(0, n_s)
+        frac = Dv / D
+        val_c, secs, c1_h, c2_h, dec_h = cpu_sample(co, A_h, B_h, n64["sk"][:n_s], np.ascontiguousarray(n_m[:Dc, :n_s]), n64["r"][:Dc], n64["e1"][:Dc],
+                                                    np.ascontiguousarray(n64["e2"][:Dc, :n_s]), n, frac)
+        # the CPU port and the GPU agree on this sample (same keys, same randomness): ciphertext of dealer 0, plaintexts of the sample
         g1, g2 = eng.ct_download(0)
-        same = bool((dec_h == res_host[:, :Dc]).all() and (g1 == c1_h[0]).all() and (g2 == c2_h[0]).all())
-        cpu = {"value": Dc * n / dt, "unit": UNIT, "cores": co.threads, "kind": "port",
-               "sample": f"{Dc} dealers x {n} parties (encrypt + all-party decrypt) of the same workload, {dt:.1f} s; "
-                         f"bit-identical to the GPU result: {same}"}
+        if W.subset:
+            cols = [i for i, d in enumerate(valid) if d < Dc]
+            same_pt = bool((dec_h[:, [int(valid[i]) for i in cols]] == res_host[:n_s, cols]).all())
+        else:
+            same_pt = bool((dec_h == res_host[:n_s, :Dc]).all())
+        same = bool(same_pt and (g1 == c1_h[0]).all() and (g2[:n_s] == c2_h[0]).all())
+        cpu = {"value": val_c, "unit": UNIT, "cores": co.threads, "kind": "port",
+               "sample": f"c1 for {Dc} dealers + (c2, decrypt) for {Dc} dealers x {n_s} of the {n} parties of the same workload"
+                         f"{', scaled linearly to n' if n_s < n else ''}, {secs:.1f} s; bit-identical to the GPU result: {same}"}
         if not same:
             raise SystemExit("bench: CPU port and GPU disagree on the sample")
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    par = {"none": "single GPU",
+           "ce": f"B rows / parties sharded x{world}; c1 dealer slices exchanged by copy-engine peer copies + stream counters (pvw_shard_*) under the c2 product",
+           "nccl": f"B rows / parties sharded x{world}; c1 dealer slices all-gathered (NCCL)",
+           "replicate": f"B rows / parties sharded x{world}; c1 computed by every rank (no exchange)"}[exchange]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "dealers_per_step": D, "dealers_per_gpu_per_step": Dg, "shares_per_step": shares_per_step,
-                       "parallelism": f"B rows / parties sharded x{world}; c1 dealer slices all-gathered (NCCL)" if world > 1 else "single GPU",
+            "config": {"workload": W.name(n), "config_key": W.key, "dealers_per_step": D, "dealers_per_gpu_per_step": Dg, "shares_per_step": shares_per_step,
+                       "decrypted_shares_per_step": Dv * n, "parallelism": par,
                        "l2": "inputs larger than L2 (B shard %.0f MB, ciphertext store %.0f MB per step vs 126 MB L2)" % (
                            nrows * k * L * l * 8 / 1e6, D * (nrows + k) * L * l * 8 / 1e6),
                        "keys": "genuine (device keygen); every decrypted share checked == message before timing"},
             "clocks": clk, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "input_types": f"m u64; r, sk int8; e1, e2 {str(etype).replace('torch.', '')} (PVW_IN_SECRET_I8 / PVW_IN_ERROR_*); ciphertexts stay in the device store",
+                    "int64_inputs": {"value": shares_per_step * e2e_steps / (ms_e2e64 * 1e-3), "ms_per_step": ms_e2e64 / e2e_steps,
+                                     "h2d_bytes_per_step": int(n_m.nbytes + small(n64) + parties.nbytes)},
+                    "ciphertexts_to_host": wire},
             "roofline": roofline, "cpu_baseline": cpu,
-            "hbm_roof_shares_per_s": peak * 1e9 / bytes_per_share(n) * world}
+            "hbm_roof_shares_per_s": peak * 1e9 / W.bytes_per_share(n) * world}
     emit(line)
+    if xch is not None:
+        eng.synchronize()
+        barrier()
+        xch.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -488,12 +640,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dealers", type=int, default=256, help="dealers per GPU per step")
-    ap.add_argument("--parties", type=int, default=N_PARTIES)
-    ap.add_argument("--cpu-dealers", type=int, default=16, help="dealers per step of the --impl reference arm")
-    ap.add_argument("--cpu-baseline-dealers", type=int, default=64, help="dealers in the cpu_baseline sample (about 11 s on 16 cores)")
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"], help="BASELINE.json configuration (C3 = the headline)")
+    ap.add_argument("--dealers", type=int, default=0, help="dealers per GPU per step (default: the configuration's)")
+    ap.add_argument("--parties", type=int, default=0, help="override n (C3: 8192 = north_star target; C5 sweep: 1024 / 4096 / 16384)")
+    ap.add_argument("--c1-exchange", default="ce", choices=["ce", "nccl", "replicate"],
+                    help="multi-GPU: copy-engine peer copies (default), NCCL all-gather, or replicated c1")
+    ap.add_argument("--cpu-dealers", type=int, default=0, help="dealers per step of the --impl reference arm (default: a quarter of the cpu_baseline sample)")
+    ap.add_argument("--cpu-baseline-dealers", type=int, default=0, help="dealers in the cpu_baseline sample (default: the configuration's, 10-20 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    W = workloads()[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "b200" and world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -504,9 +660,9 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     _quiet_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, W)
     else:
-        run_b200(args)
+        run_b200(args, W)
 
 
 if __name__ == "__main__":

@@ -52,6 +52,8 @@ class COracle:
         self.lib = C.CDLL(build())
         self.P = P
         L, l = P.L, P.l
+        if L > 64 or l > 256:                     # PVWO_MAX_L / PVWO_MAX_ELL of pvw_oracle.c (fixed-size tables)
+            raise ValueError(f"the C oracle is built for at most 64 moduli and ring degree 256 (got L={L}, l={l})")
         self.nw = nw = (P.Q.bit_length() + 63) // 64 + 1
         self._keep = dict(
             moduli=_u64(P.moduli), psi=_u64(P.psi), Q=_words(P.Q, nw), delta=_words(P.delta, nw),
@@ -67,6 +69,11 @@ class COracle:
     @property
     def threads(self) -> int:
         return int(self.lib.pvwo_num_threads())
+
+    def set_threads(self, n: int):
+        """OpenMP threads of the following calls (the reference: rayon's global pool = all host cores)"""
+        self.lib.pvwo_set_num_threads.argtypes = [C.c_int]
+        self.lib.pvwo_set_num_threads(int(n))
 
     def ntt_small(self, coef) -> np.ndarray:
         coef = _i64(coef)

@@ -28,7 +28,7 @@
 typedef unsigned __int128 u128;
 
 #define PVWO_MAX_L 64
-#define PVWO_MAX_ELL 64
+#define PVWO_MAX_ELL 256
 #define BW 160 /* capacity of a big integer in 64-bit words */
 
 typedef struct {
@@ -278,7 +278,8 @@ static void mag_divrem(big *q, big *r, const big *a, const big *b) {
 static void big_tdivrem(big *q, big *r, const big *a, const big *b) {
   big qq, rr; mag_divrem(&qq, &rr, a, b);
   qq.neg = qq.n ? (a->neg ^ b->neg) : 0; rr.neg = rr.n ? a->neg : 0;
-  if (q) *q = qq; if (r) *r = rr;
+  if (q) *q = qq;
+  if (r) *r = rr;
 }
 /* x mod Q into [0, Q) for signed x */
 static void big_mod_floor(big *r, const big *x, const big *Q) {
@@ -382,6 +383,14 @@ int pvwo_num_threads(void) {
   return omp_get_max_threads();
 #else
   return 1;
+#endif
+}
+/* launchers such as torch.distributed.run export OMP_NUM_THREADS=1: the timed CPU baseline sets its thread count explicitly */
+void pvwo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
 #endif
 }
 

@@ -726,9 +726,13 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     // r_hat (encryption.rs:147-154): operand form [d][limb][j][ell] for the IMAD kernel, byte planes for the tensor-core one
     const bool imma = imma_wanted(c, nrows, D);
     const uint32_t kp = imma_kp(k);
+    // c1 alone (PVW_ENC_C1_ONLY, the first half of a multi-GPU step): only the slice's dealers need r_hat
+    const bool slice_only = imma && !do_c2;
+    const uint32_t v_first = slice_only ? c1_lo : 0, v_count = slice_only ? c1_hi - c1_lo : D;
     if (imma) {
-      planes_clear(c, c->Vx, (size_t)L * ell * D * 8 * kp);
-      ntt(c, d_r, sb, nullptr, (uint64_t)D * k, k, c->Vx.as<u64>(), kp, (size_t)D * 8 * kp, false, false, 2);
+      planes_clear(c, c->Vx, (size_t)L * ell * v_count * 8 * kp);
+      if (v_count)
+        ntt(c, at_bytes(d_r, (size_t)v_first * k * ell * sb), sb, nullptr, (uint64_t)v_count * k, k, c->Vx.as<u64>(), kp, (size_t)v_count * 8 * kp, false, false, 2);
     } else {
       c->rhat.ensure((size_t)D * w1 * 8);
       ntt(c, d_r, sb, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, false, true);
@@ -747,11 +751,11 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     if (imma) {
       // tensor-core product (imma.cu) on the byte planes of A / B (built once) and of r_hat (written by the NTT kernel)
       ImmaArgs g{};
-      g.Vb = c->Vx.as<uint8_t>(); g.Vb_plane = (size_t)D * 8 * kp; g.Vb_D = D;
+      g.Vb = c->Vx.as<uint8_t>(); g.Vb_plane = (size_t)v_count * 8 * kp; g.Vb_D = v_count;
       g.k = k; g.L = L; g.ell = ell; g.lc = c->T.lc;
       if (c1_hi > c1_lo) {
         g.Mb = planes_A(c); g.Mb_plane = (size_t)k * 8 * kp; g.rows = k;
-        g.d_first = c1_lo; g.D = c1_hi - c1_lo;
+        g.d_first = c1_lo - v_first; g.D = c1_hi - c1_lo;
         g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
         imma_launch(c, g);
       }

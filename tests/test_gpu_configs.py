@@ -134,9 +134,9 @@ def test_p128_at_8192_parties_sampled(pkg):
         assert (co.decrypt(h(sk)[rows], c1_o, c2_o)[:, 0] == h(out)[rows, d].view(np.uint64)).all()
 
 
-@pytest.mark.parametrize("ell,imma", [(64, 1), (64, 0), (128, 0)])
+@pytest.mark.parametrize("ell,imma", [(64, 1), (64, 0), (128, 0), (256, 1)])
 def test_ring_degree_above_32(pkg, ell, imma):
-    P = O.Params(9, 6, ell, O.largest_ntt_primes(3, 62, 2 * ell), error_bound_1=50, error_bound_2=50)
+    P = O.Params(9, 6, ell, O.largest_ntt_primes(3 if ell < 256 else 5, 62, 2 * ell), error_bound_1=50, error_bound_2=50)
     D = 10
     S = System(P, D, "u63")
     c1, c2 = S.encrypt()

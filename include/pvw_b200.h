@@ -243,14 +243,15 @@ void *pvw_ctx_stream(pvw_ctx *ctx);
  * "imma_min_dealers" / "imma_min_rows" (smallest batch of dealers / rows of the matrix operand that take the tensor-core path,
  * defaults 8 / 16), "imma_chunk_dealers" (dealers per scratch
  * chunk, default 512), "imma_pair" (1 = the two-SM cta_group::2 form, a measured alternative), "gemm_impl" (CUDA-core kernel:
- * 0 = synchronous tiles, 1 = TMA bulk-copy pipeline, 2 = tensor-map boxes), "gemm_tile", "refill_lag", "tail_impl", "lift_fast",
+ * 0 = synchronous tiles, 1 = TMA bulk-copy pipeline, 2 = tensor-map boxes), "gemm_tile", "refill_lag", "tail_impl", "lift_fast", "decode_fused" (1 = one-kernel decode of clean shares
+ * with the general chain as the per-share fallback, the default; 0 = the general chain for every share),
  * "decrypt_chunk_shares", "upload_chunk_bytes", "profile" */
 int pvw_ctx_set_option(pvw_ctx *ctx, const char *name, int64_t value);
 /* per-kernel-kind device timing, measured with CUDA events on the context's stream around every launch while the
  * option "profile" is 1 (2 = enable and reset, 0 = disable and reset): total milliseconds, launches and algorithmic
  * bytes accumulated since the last reset.  Synchronises the stream. */
 enum { PVW_KERNEL_NTT = 0, PVW_KERNEL_MAC = 1, PVW_KERNEL_DECODE_RNS = 2, PVW_KERNEL_CRT_LIFT = 3, PVW_KERNEL_DECODE_TAIL = 4,
-       PVW_KERNEL_PERMUTE = 5, PVW_KERNEL_WIRE = 6, PVW_KERNEL_EXPAND = 7, PVW_KERNEL_KINDS = 8 };
+       PVW_KERNEL_PERMUTE = 5, PVW_KERNEL_WIRE = 6, PVW_KERNEL_EXPAND = 7, PVW_KERNEL_DECODE_FUSED = 8, PVW_KERNEL_KINDS = 9 };
 int pvw_ctx_profile(pvw_ctx *ctx, int kind, double *ms_total, uint64_t *launches, double *algorithmic_bytes);
 /* number of kernels launched by this context so far */
 uint64_t pvw_ctx_launch_count(const pvw_ctx *ctx);

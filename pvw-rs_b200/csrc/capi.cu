@@ -71,6 +71,9 @@ struct pvw_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_ev;
   DevTables T{};
+  FusedConst F{};                // decode fast path constants (decode.cu (0))
+  int decode_fused = 1;          // option "decode_fused": 0 = always the three-kernel chain
+  DevBuf fb;                     // [count (16 bytes)][list u32[S]] of the shares the fast path hands to the chain
   DevBuf tables;                 // one allocation holding every constant table
   DevBuf A, At, B;
   bool A_set = false, At_valid = false;
@@ -147,6 +150,7 @@ void upload_tables(pvw_ctx* c) {
   size_t o_twi = put(hp.twi.data(), (size_t)L * ell), o_twis = put(hp.twi_sh.data(), (size_t)L * ell);
   size_t o_g = put(hp.gadget_hat.data(), (size_t)L * ell), o_gs = put(hp.gadget_hat_sh.data(), (size_t)L * ell);
   size_t o_dc = put(hp.dec_c.data(), (size_t)L * 4);
+  size_t o_lg = put(hp.lgad.data(), (size_t)L * ell), o_lgs = put(hp.lgad_sh.data(), (size_t)L * ell);
   std::vector<uint64_t> qhat_t((size_t)L * NWT, 0), qsh_t((size_t)LB * (NWT + 1), 0);
   for (uint32_t j = 0; j < L; j++) memcpy(&qhat_t[(size_t)j * NWT], &hp.qhat[(size_t)j * NW], (size_t)NW * 8);
   for (uint32_t b = 0; b < LB; b++) memcpy(&qsh_t[(size_t)b * (NWT + 1)], &hp.Qsh[(size_t)b * (NW + 1)], (size_t)(NW + 1) * 8);
@@ -164,6 +168,7 @@ void upload_tables(pvw_ctx* c) {
   DevTables& T = c->T;
   T.lc = reinterpret_cast<const LimbConst*>(base + o_lc);
   T.tw = base + o_tw; T.tw_sh = base + o_tws; T.twi = base + o_twi; T.twi_sh = base + o_twis; T.gadget_hat = base + o_g; T.gadget_hat_sh = base + o_gs; T.dec_c = base + o_dc;
+  T.lgad = base + o_lg; T.lgad_sh = base + o_lgs;
   T.qhat = base + o_qhat; T.Qsh = base + o_qsh;
   T.Qw = base + o_Q; T.halfQ = base + o_hQ; T.Mw = base + o_M; T.halfM = base + o_hM; T.Dw = base + o_D;
   T.divM_v = base + o_dM; T.div2D_v = base + o_d2D;
@@ -174,6 +179,14 @@ void upload_tables(pvw_ctx* c) {
   T.sh_c = base + o_shc; T.sh_c_sh = base + o_shcs; T.sh_qhat = base + o_shq; T.sh_Q = base + o_shQ; T.sh_halfQ = base + o_shh;
   T.sh_v = base + o_shv; T.sh_v_sh = base + o_shvs; T.sh_r = base + o_shr; T.sh_r_sh = base + o_shrs;
   T.shortL = hp.shortL; T.shortSW = hp.shortSW; T.lift_fast = hp.shortL > 0 ? 1 : 0;
+  FusedConst& F = c->F;
+  memset(&F, 0, sizeof(F));
+  F.enabled = hp.fused_ok ? 1 : 0;
+  F.impl = 2;
+  if (hp.fused_ok) {
+    F.nd = hp.divD.n; F.shift = hp.divD.shift; F.vinv = hp.divD.vinv; F.cmax = hp.fused_cmax;
+    for (uint32_t i = 0; i < 4; i++) { F.dv[i] = i < hp.divD.v.size() ? hp.divD.v[i] : 0; F.half_d[i] = hp.half_delta[i]; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -499,7 +512,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
     b->release();
   delete c;
 }
@@ -835,11 +848,23 @@ static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds,
   const uint64_t S = (uint64_t)Pc * D;
   c->y.ensure(decode_scratch_words_y(c->T, S) * 8);
   c->X.ensure(decode_scratch_words_X(c->T, S) * 8);
+  // fast path first: one kernel decodes every share a correct run produces and lists the others; the chain then runs on the list
+  FallbackList fb{nullptr, nullptr};
+  if (c->F.enabled && c->decode_fused && S < (1ull << 32)) {
+    c->fb.ensure(16 + S * 4);
+    uint32_t* count = c->fb.as<uint32_t>();
+    uint32_t* list = count + 4;
+    CUDA_CHECK(cudaMemsetAsync(count, 0, 4, c->stream));
+    bool fused = false;
+    launch(c, PVW_KERNEL_DECODE_FUSED, 0.0, [&] { fused = launch_decode_fused(c->T, c->F, z, z_ls, z_ds, Pc, D, out, out_ps, list, count, c->stream, z_cs, sub); });
+    if (fused) fb = FallbackList{list, count};
+  }
+  const FallbackList* fbp = fb.count ? &fb : nullptr;
   bool ok = true;
-  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { ok = launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream, z_cs, sub); });
+  launch(c, PVW_KERNEL_DECODE_RNS, 0.0, [&] { ok = launch_decode_rns(c->T, z, z_ls, z_ds, Pc, D, c->y.as<u64>(), c->stream, z_cs, sub, fbp); });
   require(ok, PVW_ERR_INTERNAL, "decode: unsupported shape");
-  launch(c, PVW_KERNEL_CRT_LIFT, 0.0, [&] { launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream); });
-  launch(c, PVW_KERNEL_DECODE_TAIL, 0.0, [&] { launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream); });
+  launch(c, PVW_KERNEL_CRT_LIFT, 0.0, [&] { launch_crt_lift(c->T, c->y.as<u64>(), c->X.as<u64>(), S, c->stream, fbp); });
+  launch(c, PVW_KERNEL_DECODE_TAIL, 0.0, [&] { launch_decode_tail(c->T, c->X.as<u64>(), Pc, D, out, out_ps, c->stream, fbp); });
 }
 
 int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint32_t P, const uint32_t* party_idx, const void* sk,
@@ -893,6 +918,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     c->z.ensure((size_t)Dstep * L * Pc_max * ell * 8);
     c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * Dstep) * 8);   // sized for the largest chunk up front: growing a
     c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * Dstep) * 8);   // buffer mid-call would synchronise the device
+    c->fb.ensure(16 + (size_t)Pc_max * Dstep * 4);
     // host inputs: a short first chunk, so that little of the secret-key copy is exposed before the kernels start, then chunks
     // growing threefold: a party's share of the work takes about 3.5x as long as the copy of its key, so chunk i+1 (<= 3x chunk i)
     // has arrived by the time chunk i is done
@@ -1473,6 +1499,8 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     else if (n == "gemm_tile") { require(value >= 0 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..3"); c->gemm_tile = (int)value; }
     else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
     else if (n == "lift_fast") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "lift_fast must be 0 or 1"); c->T.lift_fast = (value && c->hp.shortL > 0) ? 1 : 0; }
+    else if (n == "decode_fused") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "decode_fused must be 0 or 1"); c->decode_fused = (int)value; }
+    else if (n == "decode_fused_impl") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "decode_fused_impl must be 0, 1 or 2"); c->F.impl = (int)value; }
     else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }

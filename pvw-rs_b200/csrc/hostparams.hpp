@@ -197,6 +197,7 @@ struct HostParams {
   uint32_t NW = 0;                           // words of Q
   std::vector<LimbConst> lc;                 // [L]
   std::vector<uint64_t> tw, tw_sh, twi, twi_sh, gadget_hat, gadget_hat_sh;  // [L][ell] each
+  std::vector<uint64_t> lgad, lgad_sh;                                      // [L][ell] ell * Delta^i mod q_j (+ Shoup): fused decode check
   // CRT lift: qhat[j] = Q / q_j  ([L][NW]),  Qsh[b] = Q << b  ([LB][NW+1])
   std::vector<uint64_t> qhat, Qsh; uint32_t LB = 0;
   // decode tail constants (NW words each unless noted)
@@ -212,6 +213,9 @@ struct HostParams {
   // Knuth-D divisors, normalised so that the top bit of the top word is set
   struct Divisor { std::vector<uint64_t> v; uint32_t n = 0, shift = 0; uint64_t vinv = 0; };
   Divisor divM, div2D;
+  // fused decode fast path (decode.cu (0)): Delta as a normalised divisor, floor(Delta/2), the bound on the final carry, and
+  // whether the parameter set admits it at all (a sub-basis exists, it is well below Q, Delta >= 2 and fits four words)
+  Divisor divD; std::vector<uint64_t> half_delta; uint64_t fused_cmax = 0; bool fused_ok = false;
 
   static uint64_t reciprocal_2by1(uint64_t d) {  // floor((2^128 - 1) / d) - 2^64 for normalised d (Moller-Granlund)
     u128 num = ~(u128)0;
@@ -272,7 +276,7 @@ struct HostParams {
     NW = (uint32_t)Q.w.size();
 
     lc.resize(L);
-    tw.assign((size_t)L * ell, 0); tw_sh = tw; twi = tw; twi_sh = tw; gadget_hat = tw; gadget_hat_sh = tw;
+    tw.assign((size_t)L * ell, 0); tw_sh = tw; twi = tw; twi_sh = tw; gadget_hat = tw; gadget_hat_sh = tw; lgad = tw; lgad_sh = tw;
     qhat.assign((size_t)L * NW, 0);
     for (uint32_t j = 0; j < L; j++) {
       uint64_t q = moduli[j]; LimbConst& c = lc[j];
@@ -303,6 +307,10 @@ struct HostParams {
       for (uint32_t t = 0; t < ell; t++) { g[t] = pw; pw = h_mulmod(pw, c.delta, q); }
       host_ntt_fwd(g, j);
       for (uint32_t t = 0; t < ell; t++) gadget_hat_sh[(size_t)j * ell + t] = h_shoup(g[t], q);
+      {
+        uint64_t pw2 = ell % q;
+        for (uint32_t t = 0; t < ell; t++) { lgad[(size_t)j * ell + t] = pw2; lgad_sh[(size_t)j * ell + t] = h_shoup(pw2, q); pw2 = h_mulmod(pw2, c.delta, q); }
+      }
     }
     LB = 1; while ((1u << LB) <= L) LB++;
     Qsh.assign((size_t)LB * (NW + 1), 0);
@@ -324,7 +332,13 @@ struct HostParams {
     }
     shortL = 0; shortSW = 0;
     {
-      const size_t need_bits = delta.bits() + 64 + 2;
+      // what a decodable share needs: |t_i| ~ Delta * |noise| with the noise bound of the correctness condition (parameters.rs:510-551),
+      // and |-z_0| = m + noise < 2^65.  (Larger values are legal -- anything below Delta/2 decodes -- but they fail the verification
+      // of the short lift and simply take the general path.)
+      const double nf = (double)n, kf = (double)k, lf = (double)ell;
+      const double noise = (double)b2 * std::sqrt(nf * lf) * (1.0 + std::sqrt(nf)) + 2.0 * (double)b1 * kf * lf + 14.0 * (double)b1 * std::sqrt(nf * kf * lf);
+      const size_t noise_bits = (noise >= 1.0 && std::isfinite(noise)) ? (size_t)std::ilogb(noise) + 1 : 64;
+      const size_t need_bits = std::max<size_t>(delta.bits() + std::min<size_t>(noise_bits, 64) + 3, 67);
       BigU Qs(1);
       for (uint32_t s = 1; s < L; s++) {
         Qs = BigU::mul_small(Qs, moduli[s - 1]);
@@ -347,6 +361,35 @@ struct HostParams {
         }
       }
     }
+    build_fused();
+  }
+
+  void build_fused() {
+    fused_ok = false; fused_cmax = 0;
+    half_delta.assign(4, 0);
+    if (shortL == 0 || delta.bits() < 2 || delta.w.size() > 4) return;
+    if (ell != 8 && ell != 16 && ell != 32) return;
+    BigU Qs(1);
+    for (uint32_t j = 0; j < shortL; j++) Qs = BigU::mul_small(Qs, moduli[j]);
+    if (Qs.bits() + 2 > Q.bits()) return;                     // every fast-path integer (< Q_s / 2 + 2^64) must stay below Q / 2
+    if (delta.bits() + 67 > Q.bits()) return;                 // |e_{i+1} - Delta e_i| with one-word e's must be a centred value mod Q
+    divD = make_divisor(delta);
+    BigU::shr1(delta).to_words(half_delta.data(), 4);
+    // largest x with x * M + floor(Delta/2) + 1 <= floor(Q/2), M = Delta^(l-1)
+    const BigU halfQ_ = BigU::shr1(Q), slack = BigU::add(BigU::shr1(delta), BigU(1));
+    if (BigU::cmp(slack, halfQ_) > 0) return;
+    const BigU room = BigU::sub(halfQ_, slack);
+    BigU x;
+    const size_t top = room.bits() > delta_pow.bits() ? room.bits() - delta_pow.bits() + 1 : 1;
+    for (size_t b = top + 1; b-- > 0;) {
+      BigU t = x; const size_t wi = b / 64;
+      if (t.w.size() <= wi) t.w.resize(wi + 1, 0);
+      t.w[wi] |= 1ull << (b % 64);
+      if (BigU::cmp(BigU::mul(t, delta_pow), room) <= 0) x = t;
+    }
+    x.trim();
+    fused_cmax = x.w.empty() ? 0 : (x.w.size() > 1 ? ~0ull : x.w[0]);
+    fused_ok = true;
   }
 
   // verify_correctness_condition, parameters.rs:510-551 (f64, same evaluation order)

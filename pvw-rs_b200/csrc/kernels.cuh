@@ -25,6 +25,8 @@ struct DevTables {
   const u64* gadget_hat;   // [L][ell] NTT([1, D, .., D^(l-1)] mod q) (parameters.rs:288-308)
   const u64* gadget_hat_sh;  //        Shoup companions
   const u64* dec_c;        // [L][4] multipliers of decode_rns (hostparams.hpp dec_c)
+  const u64* lgad;         // [L][ell] ell * Delta^i mod q (power basis, times the unscaled inverse NTT's factor): fused decode check
+  const u64* lgad_sh;
   // CRT lift
   const u64* qhat;         // [L][NWT]   Q/q_j, zero padded to the template width
   const u64* Qsh;          // [LB][NWT+1] Q << b
@@ -90,12 +92,31 @@ size_t mac_gemm_launches(const GemmArgs& a);
 // sub (optional): the polynomial to subtract first -- z holds <s, c1> only and sub describes c2 (decryption.rs:270-274):
 //   S[sd*S_ds + limb*S_ls + srow*ell + c], sd = dmap ? dmap[d] : d, srow = rowmap ? rowmap[p] : p
 struct DecodeSub { const u64* S; size_t S_ls, S_ds; const uint32_t* rowmap; const uint32_t* dmap; };
+// FallbackList (optional, every kernel of the chain): run only on the shares listed by the fused fast path (device-side count),
+// with a grid that does not depend on the count; scratch (y, X) stays indexed by the share number
+struct FallbackList { const uint32_t* list; const uint32_t* count; };
 bool launch_decode_rns(const DevTables& T, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* y, cudaStream_t st,
-                       size_t z_cs = 0, const DecodeSub* sub = nullptr);
+                       size_t z_cs = 0, const DecodeSub* sub = nullptr, const FallbackList* fb = nullptr);
 // X[(i*NW + w)*S + s'] = CRT lift of y[.][i][s']
-void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st);
+void launch_crt_lift(const DevTables& T, const u64* y, u64* X, uint64_t S, cudaStream_t st, const FallbackList* fb = nullptr);
 // out[p*out_ps + d] for s' = d*Pc + p
-void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t D, u64* out, size_t out_ps, cudaStream_t st);
+void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t D, u64* out, size_t out_ps, cudaStream_t st, const FallbackList* fb = nullptr);
+// The fused fast path (decode.cu (0)): clean shares are decoded in one kernel, the others are appended to fb_list (count in
+// *fb_count, which the caller zeroes) for the list-driven chain above.  false: not launched (disabled for this parameter set, or
+// the shape does not fit) -- the caller then runs the chain on every share.
+struct FusedConst {
+  u64 dv[4];       // Delta, normalised (top bit of word nd-1 set)
+  u64 half_d[4];   // floor(Delta / 2)
+  u64 vinv;        // reciprocal of dv[nd-1] (Moller-Granlund)
+  u64 cmax;        // largest one-word x with x * Delta^(l-1) + floor(Delta/2) + 1 <= floor(Q/2)
+  uint32_t nd, shift;
+  int enabled;
+  int impl;        // 2 (default): thread = share, candidates from the sub-basis, then the claim z_i = -(m D^i + e_i) checked in every
+                   // other limb; 1: thread = share, every lifted value verified in every limb; 0: the shared-memory staged form of 1
+                   // (always used for l = 32)
+};
+bool launch_decode_fused(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps,
+                         uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, size_t z_cs = 0, const DecodeSub* sub = nullptr);
 size_t decode_scratch_words_y(const DevTables& T, uint64_t S);
 size_t decode_scratch_words_X(const DevTables& T, uint64_t S);
 

@@ -56,6 +56,11 @@ PVW_DEV u64 mulmod_shoup(u64 a, u64 w, u64 w_sh, u64 q) {
   u64 r = a * w - __umul64hi(a, w_sh) * q;  // in [0, 2q)
   return r >= q ? r - q : r;
 }
+// the same without the final correction: result in [0, 2q) for any a < 2^64 (Harvey's lazy butterflies; q < 2^62, so sums of
+// up to four such values still fit 64 bits)
+PVW_DEV u64 mulmod_shoup_lazy(u64 a, u64 w, u64 w_sh, u64 q) { return a * w - __umul64hi(a, w_sh) * q; }
+// x in [0, 2q) -> [0, q);  x in [0, 4q) -> [0, 2q) with q2 = 2q
+PVW_DEV u64 csub(u64 x, u64 q) { return x >= q ? x - q : x; }
 // i64 -> canonical residue: ((x % q) + q) % q   (parameters.rs:437-452, Poly::from_coefficients)
 PVW_DEV u64 reduce_i64(long long x, const LimbConst& c) {
   const u64 m = x >= 0 ? (u64)x : (u64)(-(x + 1)) + 1ull;  // |x| without overflow

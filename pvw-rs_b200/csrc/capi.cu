@@ -182,9 +182,8 @@ void upload_tables(pvw_ctx* c) {
   FusedConst& F = c->F;
   memset(&F, 0, sizeof(F));
   F.enabled = hp.fused_ok ? 1 : 0;
-  F.impl = 2;
   if (hp.fused_ok) {
-    F.nd = hp.divD.n; F.shift = hp.divD.shift; F.vinv = hp.divD.vinv; F.cmax = hp.fused_cmax;
+    F.nd = hp.divD.n; F.shift = hp.divD.shift; F.vinv = hp.divD.vinv; F.cmax = hp.fused_cmax; F.emax = hp.fused_emax;
     for (uint32_t i = 0; i < 4; i++) { F.dv[i] = i < hp.divD.v.size() ? hp.divD.v[i] : 0; F.half_d[i] = hp.half_delta[i]; }
   }
 }
@@ -1500,7 +1499,6 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
     else if (n == "lift_fast") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "lift_fast must be 0 or 1"); c->T.lift_fast = (value && c->hp.shortL > 0) ? 1 : 0; }
     else if (n == "decode_fused") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "decode_fused must be 0 or 1"); c->decode_fused = (int)value; }
-    else if (n == "decode_fused_impl") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "decode_fused_impl must be 0, 1 or 2"); c->F.impl = (int)value; }
     else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }

@@ -27,6 +27,11 @@
 #ifndef PVW_TAIL_MINB
 #define PVW_TAIL_MINB 4
 #endif
+// resident CTAs per SM asked for the fused decode kernel at l = 8: 4 (128 registers, ~400 bytes spilled) measured 1.40 ms per
+// bench step against 1.52 ms for 3 (168 registers, no spills) -- the kernel is latency bound and wants the warps
+#ifndef PVW_FUSED_MINB8
+#define PVW_FUSED_MINB8 4
+#endif
 
 namespace pvw {
 
@@ -1057,11 +1062,7 @@ __global__ void __launch_bounds__(128) decode_fused_kernel(const u64* __restrict
   }
 }
 
-// The same fast path with thread = share and a loop over the limbs: nothing goes through shared memory but constants, no barrier,
-// every global load is unit stride across the warp.  Pass 1 walks the sub-basis limbs and accumulates the short lift of all l
-// values; pass 2 walks the remaining limbs and verifies the candidates against the residues as they are produced; phase C as
-// above.  (The shared-memory form above ran at 2.5 ms per bench step -- phases serialised behind barriers, one warp in four
-// busy during phase C; it is kept for l = 32, where l * (SW + 1) accumulator words do not fit the register file.)
+// Residues of t_0..t_{l-2} and -z_0 of one share in one limb (the per-limb step shared by the kernels below).
 template <int ELL, bool LAZY = false>   // LAZY: results only below 4q (callers that multiply them anyway), Harvey butterflies
 PVW_DEV void share_residues(const u64* __restrict__ z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sub, uint64_t d, uint64_t p, uint32_t sd,
                             uint32_t srow, uint32_t limb, u64 q, const u64* tw, const u64* tw_sh, const u64* dc, u64 (&y)[ELL]) {
@@ -1107,176 +1108,12 @@ PVW_DEV void share_residues(const u64* __restrict__ z, size_t z_ls, size_t z_ds,
   }
 }
 
-template <int ELL, int SW, int ND, int MINB>
-__global__ void __launch_bounds__(128, MINB) decode_fused_share_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub sub,
-                                                                       uint32_t Pc, uint64_t S, u64* __restrict__ out, size_t out_ps, const DevTables T,
-                                                                       const FusedConst F, uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
-  extern __shared__ __align__(16) u64 sm[];
-  const uint32_t L = T.L, Ls = T.shortL;
-  u64* s_twi = sm;                                   // [L][ELL]
-  u64* s_twi_sh = s_twi + (size_t)L * ELL;           // [L][ELL]
-  u64* s_vc = s_twi_sh + (size_t)L * ELL;            // [L][10]  q, floor(2^64/q), sh_c, sh_c_sh (sub-basis limbs), 2^64 / 2^128 / 2^192 mod q + Shoup
-  u64* s_dc = s_vc + (size_t)L * 10;                 // [L][4]   decode_rns multipliers
-  u64* s_qh = s_dc + (size_t)L * 4;                  // [Ls][SW] Q_s / q_j, then Q_s [SW], floor(Q_s / 2) [SW]
-  for (uint32_t i = threadIdx.x; i < L * ELL; i += blockDim.x) { s_twi[i] = T.twi[i]; s_twi_sh[i] = T.twi_sh[i]; }
-  for (uint32_t j = threadIdx.x; j < L; j += blockDim.x) {
-    u64* cj = s_vc + (size_t)j * 10;
-    cj[0] = T.lc[j].q; cj[1] = T.lc[j].mu64;
-    cj[2] = j < Ls ? T.sh_c[j] : 0; cj[3] = j < Ls ? T.sh_c_sh[j] : 0;
-    for (int t = 0; t < 3; t++) { cj[4 + 2 * t] = T.sh_r[(size_t)j * 3 + t]; cj[5 + 2 * t] = T.sh_r_sh[(size_t)j * 3 + t]; }
-    for (int t = 0; t < 4; t++) s_dc[(size_t)j * 4 + t] = T.dec_c[(size_t)j * 4 + t];
-  }
-  for (uint32_t i = threadIdx.x; i < Ls * SW; i += blockDim.x) s_qh[i] = T.sh_qhat[i];
-  for (uint32_t i = threadIdx.x; i < SW; i += blockDim.x) { s_qh[Ls * SW + i] = T.sh_Q[i]; s_qh[Ls * SW + SW + i] = T.sh_halfQ[i]; }
-  __syncthreads();
-  const u64* sQ = s_qh + Ls * SW;
-  const u64* sHQ = sQ + SW;
-  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t d = s / Pc, p = s % Pc;
-    const uint32_t sd = sub.S ? (sub.dmap ? sub.dmap[d] : (uint32_t)d) : 0, srow = sub.S ? (sub.rowmap ? sub.rowmap[p] : (uint32_t)p) : 0;
-    // ---- pass 1: short lift of the l values over the sub-basis
-    u64 acc[ELL][SW + 1];
-#pragma unroll
-    for (int i = 0; i < ELL; i++)
-#pragma unroll
-      for (int w = 0; w <= SW; w++) acc[i][w] = 0;
-#pragma unroll 1
-    for (uint32_t j = 0; j < Ls; j++) {
-      const u64* cj = s_vc + (size_t)j * 10;
-      const u64 q = cj[0];
-      u64 y[ELL];
-      share_residues<ELL>(z, z_ls, z_ds, z_cs, sub, d, p, sd, srow, j, q, s_twi + (size_t)j * ELL, s_twi_sh + (size_t)j * ELL, s_dc + 4 * j, y);
-      u64 qw[SW];
-#pragma unroll
-      for (int w = 0; w < SW; w++) qw[w] = s_qh[j * SW + w];
-#pragma unroll
-      for (int i = 0; i < ELL; i++) {
-        const u64 t = mulmod_shoup(y[i], cj[2], cj[3], q);
-        u64 carry = 0;
-#pragma unroll
-        for (int w = 0; w < SW; w++) {
-          const u64 lo = t * qw[w], hi = __umul64hi(t, qw[w]);
-          u64 x = acc[i][w] + carry;
-          const u64 k1 = x < carry;
-          x += lo;
-          const u64 k2 = x < lo;
-          acc[i][w] = x;
-          carry = hi + k1 + k2;
-        }
-        acc[i][SW] += carry;
-      }
-    }
-    // reduce below Q_s (the sum is < Ls * Q_s), centre: magnitudes stay in acc[i][0..SW), signs in `negs`
-    uint32_t negs = 0;
-#pragma unroll
-    for (int i = 0; i < ELL; i++) {
-      for (uint32_t r = 1; r < Ls; r++) {
-        bool ge = acc[i][SW] != 0;
-        if (!ge) {
-          ge = true;
-#pragma unroll
-          for (int w = SW - 1; w >= 0; w--)
-            if (acc[i][w] != sQ[w]) { ge = acc[i][w] > sQ[w]; break; }
-        }
-        if (ge) {
-          u64 borrow = 0;
-#pragma unroll
-          for (int w = 0; w < SW; w++) {
-            const u64 qv = sQ[w], d1 = acc[i][w] - qv, b1 = acc[i][w] < qv, d2 = d1 - borrow, b2 = d1 < borrow;
-            acc[i][w] = d2;
-            borrow = b1 | b2;
-          }
-          acc[i][SW] -= borrow;
-        }
-      }
-      bool neg = false;
-#pragma unroll
-      for (int w = SW - 1; w >= 0; w--)
-        if (acc[i][w] != sHQ[w]) { neg = acc[i][w] > sHQ[w]; break; }
-      if (neg) {
-        u64 borrow = 0;
-#pragma unroll
-        for (int w = 0; w < SW; w++) {
-          const u64 qv = sQ[w], d1 = qv - acc[i][w], b1 = qv < acc[i][w], d2 = d1 - borrow, b2 = d1 < borrow;
-          acc[i][w] = d2;
-          borrow = b1 | b2;
-        }
-        negs |= 1u << i;
-      }
-    }
-    // ---- pass 2: every other limb must agree with the candidates (CRT uniqueness: then they ARE the centred values mod Q)
-    bool ok = true;
-#pragma unroll 1
-    for (uint32_t j = Ls; j < L; j++) {
-      const u64* cj = s_vc + (size_t)j * 10;
-      const u64 q = cj[0];
-      u64 y[ELL];
-      share_residues<ELL>(z, z_ls, z_ds, z_cs, sub, d, p, sd, srow, j, q, s_twi + (size_t)j * ELL, s_twi_sh + (size_t)j * ELL, s_dc + 4 * j, y);
-#pragma unroll
-      for (int i = 0; i < ELL; i++) {
-        u64 r = acc[i][0] - __umul64hi(acc[i][0], cj[1]) * q;   // < 3q
-        r = r >= 2 * q ? r - 2 * q : r;
-        r = r >= q ? r - q : r;
-#pragma unroll
-        for (int w = 1; w < SW; w++) r += mulmod_shoup(acc[i][w], cj[2 + 2 * w], cj[3 + 2 * w], q);   // < SW * q < 2^64
-#pragma unroll
-        for (int w = 1; w < SW; w++) r = r >= q ? r - q : r;
-        if ((negs >> i) & 1u) r = r ? q - r : 0;
-        ok = ok && r == y[i];
-      }
-    }
-    // ---- phase C
-    auto value = [&](int i) {
-      Small v;
-#pragma unroll
-      for (int w = 0; w < 4; w++) v.m[w] = 0;
-#pragma unroll
-      for (int ii = 0; ii < ELL; ii++)
-        if (ii == i) {
-#pragma unroll
-          for (int w = 0; w < SW; w++) v.m[w] = acc[ii][w];
-        }
-      v.neg = ((negs >> i) & 1u) != 0;
-      return v;
-    };
-    u64 x = 0;
-    bool xneg = false;
-    if (ok) {
-      const Small t = value(ELL - 2);
-      u64 q0;
-      bool rz, rgh;
-      ok = div_small<ND>(t.m, F, q0, rz, rgh);
-      if (ok && rgh) { q0++; ok = q0 != 0; }
-      x = q0; xneg = t.neg && q0 != 0;
-#pragma unroll
-      for (int j = 1; j <= ELL - 2; j++) {
-        if (ok) {
-          const Small c = add_small(value(ELL - 2 - j), x, xneg);
-          u64 qj;
-          ok = div_small<ND>(c.m, F, qj, rz, rgh) && rz;
-          x = qj; xneg = c.neg && qj != 0;
-        }
-      }
-      ok = ok && x <= F.cmax;
-    }
-    u64 result = 0;
-    if (ok) {
-      const Small pt = add_small(value(ELL - 1), x, xneg);
-      const bool hi = (pt.m[1] | pt.m[2] | pt.m[3]) != 0;
-      if (pt.neg) {
-        if (!hi && pt.m[0] <= 1000) result = 0;
-        else ok = false;
-      } else {
-        result = hi ? 0 : pt.m[0];
-      }
-    }
-    if (ok) out[p * out_ps + d] = result;
-    else fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)s;
-  }
-}
-
-// Third form, the default: the same pass 1 and the same carry chain, but the chain runs BEFORE the other limbs are looked at and
-// yields the share's message m and noise e_0..e_{l-1} (one-word integers); pass 2 then checks the CLAIM
+// The default form (l = 8, 16): thread = share, a loop over the limbs, nothing but constants in shared memory, no barrier, every
+// global load unit stride across the warp.  (The staged kernel above ran at 2.5 ms per bench step -- phases serialised behind
+// barriers, one warp in four busy during phase C -- and a thread-per-share form that verified every lifted value in every limb at
+// 2.25 ms; this one: 1.4 ms.  The staged kernel is kept for l = 32, whose l * (SW + 1) accumulator words do not fit the registers.)
+// Pass 1 walks the sub-basis limbs and accumulates the short lift of the l values; the carry chain then runs BEFORE the other
+// limbs are looked at and yields the share's message m and noise e_0..e_{l-1} (one-word integers); pass 2 checks the CLAIM
 //     z_i = -(m D^i + e_i)  (mod q_j)   for every remaining limb j and every i
 // on the unscaled inverse transform directly: one Shoup multiply (m * (l D^i)) and one word reduction (l e_i) per coefficient
 // instead of forming t_i, -z_0 in that limb and reducing a multi-word candidate (51 -> 29 modular multiplies per limb).
@@ -1309,7 +1146,7 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
   __syncthreads();
   const u64* sQ = s_qh + Ls * SW;
   const u64* sHQ = sQ + SW;
-  constexpr u64 E_MAX = (1ull << 63) / ELL;            // |e_i| below this: l * e_i fits a word
+  const u64 E_MAX = F.emax;                            // |e_i| up to this: l * e_i < q_j for every limb, no reduction needed
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t d = s / Pc, p = s % Pc;
     const uint32_t sd = sub.S ? (sub.dmap ? sub.dmap[d] : (uint32_t)d) : 0, srow = sub.S ? (sub.rowmap ? sub.rowmap[p] : (uint32_t)p) : 0;
@@ -1414,14 +1251,14 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
           }
           dneg = !dneg;
         }
-        ok = ok && (rem[1] | rem[2] | rem[3]) == 0 && rem[0] < E_MAX;
+        ok = ok && (rem[1] | rem[2] | rem[3]) == 0 && rem[0] <= E_MAX;
         em[ELL - 1] = rem[0];
         if (dneg && rem[0] != 0) eneg |= 1u << (ELL - 1);
       } else {
         ok = ok && rz;
       }
       x = qj; xneg = c.neg && qj != 0;
-      ok = ok && x < E_MAX;
+      ok = ok && x <= E_MAX;
       em[ELL - 2 - j] = x;
       if (!xneg && x != 0) eneg |= 1u << (ELL - 2 - j);      // e = -x
     }
@@ -1473,9 +1310,7 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
       for (int i = 0; i < ELL; i++) {
         u64 t1 = mulmod_shoup(mr, lg[i], lg_sh[i], q);           // |m| l D^i
         if (mneg) t1 = t1 ? q - t1 : 0;
-        const u64 le = em[i] * (u64)ELL;
-        u64 t2 = le - __umul64hi(le, mu) * q;                    // l |e_i| mod q
-        t2 = csub(csub(t2, 2 * q), q);
+        u64 t2 = em[i] * (u64)ELL;                               // l |e_i| < q (emax)
         if ((eneg >> i) & 1u) t2 = t2 ? q - t2 : 0;
         const u64 sgm = csub(t1 + t2, q);                        // l (m D^i + e_i) mod q
         const u64 ai = csub(a[i], q);
@@ -1518,48 +1353,9 @@ template <int ELL, int MINB>
 static bool launch_fused_claim_sw(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
                                   uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st) {
   switch (T.shortSW) {
-    case 1: return launch_fused_claim<ELL, 1, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 2: return launch_fused_claim<ELL, 2, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 3: return launch_fused_claim<ELL, 3, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 4: return launch_fused_claim<ELL, 4, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-  }
-  return false;
-}
-
-template <int ELL, int SW, int MINB>
-static bool launch_fused_share(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
-                               uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st) {
-  const size_t smem = ((size_t)T.L * ELL * 2 + (size_t)T.L * 14 + (size_t)T.shortL * SW + 2 * SW) * 8;
-  if (smem > 96 * 1024) return false;
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-#define PVW_FUSED_SHARE_ND(N)                                                                                                    \
-  case N: {                                                                                                                      \
-    auto kern = decode_fused_share_kernel<ELL, SW, N, MINB>;                                                                     \
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;         \
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem) != cudaSuccess || per_sm < 1) return false;      \
-    const unsigned grid = (unsigned)std::min<uint64_t>((S + 127) / 128, (uint64_t)sms * per_sm * 4);                             \
-    kern<<<grid, 128, smem, st>>>(z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, T, F, fb_list, fb_count);                         \
-    return true;                                                                                                                 \
-  }
-  switch (F.nd) {
-    PVW_FUSED_SHARE_ND(1)
-    PVW_FUSED_SHARE_ND(2)
-    PVW_FUSED_SHARE_ND(3)
-    PVW_FUSED_SHARE_ND(4)
-  }
-#undef PVW_FUSED_SHARE_ND
-  return false;
-}
-
-template <int ELL, int MINB>
-static bool launch_fused_share_sw(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
-                                  uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st) {
-  switch (T.shortSW) {
-    case 1: return launch_fused_share<ELL, 1, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 2: return launch_fused_share<ELL, 2, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 3: return launch_fused_share<ELL, 3, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 4: return launch_fused_share<ELL, 4, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
   }
   return false;
 }
@@ -1595,7 +1391,6 @@ template <int ELL, int G>
 static bool launch_fused_sw(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
                             uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st) {
   switch (T.shortSW) {
-    case 1: return launch_fused_nd<ELL, G, 1>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 2: return launch_fused_nd<ELL, G, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 3: return launch_fused_nd<ELL, G, 3>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 4: return launch_fused_nd<ELL, G, 4>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
@@ -1610,14 +1405,8 @@ bool launch_decode_fused(const DevTables& T, const FusedConst& F, const u64* z, 
   if (!F.enabled || S >= (1ull << 32)) return false;
   const DecodeSub sb = sub ? *sub : DecodeSub{nullptr, 0, 0, nullptr, nullptr};
   switch (T.ell) {
-    case 8:
-      if (F.impl == 0) return launch_fused_sw<8, 32>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-      if (F.impl == 1) return launch_fused_share_sw<8, 3>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-      return launch_fused_claim_sw<8, 3>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 16:
-      if (F.impl == 0) return launch_fused_sw<16, 16>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-      if (F.impl == 1) return launch_fused_share_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-      return launch_fused_claim_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
+    case 8: return launch_fused_claim_sw<8, PVW_FUSED_MINB8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
+    case 16: return launch_fused_claim_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
     case 32: return launch_fused_sw<32, 8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
   }
   return false;

@@ -215,7 +215,7 @@ struct HostParams {
   Divisor divM, div2D;
   // fused decode fast path (decode.cu (0)): Delta as a normalised divisor, floor(Delta/2), the bound on the final carry, and
   // whether the parameter set admits it at all (a sub-basis exists, it is well below Q, Delta >= 2 and fits four words)
-  Divisor divD; std::vector<uint64_t> half_delta; uint64_t fused_cmax = 0; bool fused_ok = false;
+  Divisor divD; std::vector<uint64_t> half_delta; uint64_t fused_cmax = 0, fused_emax = 0; bool fused_ok = false;
 
   static uint64_t reciprocal_2by1(uint64_t d) {  // floor((2^128 - 1) / d) - 2^64 for normalised d (Moller-Granlund)
     u128 num = ~(u128)0;
@@ -389,6 +389,11 @@ struct HostParams {
     }
     x.trim();
     fused_cmax = x.w.empty() ? 0 : (x.w.size() > 1 ? ~0ull : x.w[0]);
+    uint64_t qmin = ~0ull;
+    for (uint64_t q : moduli) qmin = std::min(qmin, q);
+    fused_emax = std::min<uint64_t>(qmin, 1ull << 63) / ell;
+    if (fused_emax < 2) return;
+    fused_emax -= 1;
     fused_ok = true;
   }
 

@@ -401,7 +401,7 @@ imma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t stg = 0, bcnt = 0;
+      uint32_t st = 0, ph = 1, bcnt = 0;                                   // ph: parity to wait for on the empty barriers
       for (uint32_t tile = pair; tile < total; tile += npairs) {
         const uint32_t rt = tile % n_rt, dt = (tile / n_rt) % n_dt, plane = tile / (n_rt * n_dt);
         for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
@@ -409,40 +409,52 @@ imma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(b_empty(bb), (bit & 1) ^ 1);
           if (leader) mbar_expect_tx(b_full(bb), 2 * B_HALF);            // both halves complete on the leader's barrier
           tma_load_4d_2sm(b_base + bb * B_HALF, &tmB, (int)(kc * KC), (int)(g.d_first + dt * DT), (int)(4 * rank), (int)plane, b_full(bb) & PEER_MASK);
-          for (uint32_t s = 0; s < 8; s++, stg++) {
-            const uint32_t st = stg % nstages, it = stg / nstages;
-            mbar_wait(a_empty(st), (it & 1) ^ 1);
+          for (uint32_t s = 0; s < 8; s++) {
+            mbar_wait(a_empty(st), ph);
             if (leader) mbar_expect_tx(a_full(st), 2 * A_STAGE);
             tma_load_4d_2sm(a_base + st * A_STAGE, &tmA, (int)(kc * KC), (int)s, (int)(rt * 2 * RT + rank * RT), (int)plane, a_full(st) & PEER_MASK);
+            if (++st == nstages) { st = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     if (leader) {
-      uint32_t stg = 0, bcnt = 0, i = 0;
+      // the same lean issue loop as the one-SM kernel: counters for ring position and phase, descriptors as base + offset, the
+      // issuing lane chosen by elect.sync (the first version of this kernel rebuilt descriptors and divided per stage, and ran at
+      // the pace of that scalar code, which hid what the pair buys: each SM fetches 4 + 4 KB of operands per MMA instead of 4 + 8)
+      constexpr uint64_t DESC_HI = ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t a_lo = (a_base & 0x3FFFFu) >> 4, b_lo = (b_base & 0x3FFFFu) >> 4;
+      uint32_t st = 0, ph = 0, bcnt = 0, i = 0;
       for (uint32_t tile = pair; tile < total; tile += npairs, i++) {
         mbar_wait(tmem_empty, i & 1);                                    // both epilogues have read and cleared the previous tile (phase 0: the initial clearing)
         tc_fence_after();
         for (uint32_t kc = 0; kc < nkc; kc++, bcnt++) {
           const uint32_t bb = bcnt & 1, bit = bcnt >> 1;
           mbar_wait(b_full(bb), bit & 1);
-          for (uint32_t s = 0; s < 8; s++, stg++) {
-            const uint32_t st = stg % nstages, it = stg / nstages;
-            mbar_wait(a_full(st), it & 1);
+          for (uint32_t s = 0; s < 8; s++) {
+            mbar_wait(a_full(st), ph);
             tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = a_base + st * A_STAGE, b_addr = b_base + bb * B_HALF, d_addr = tmem_base + DT * s;
+            if (elect_one()) {
+              const uint64_t adesc = DESC_HI | (uint64_t)(a_lo + st * (A_STAGE >> 4));
+              const uint64_t bdesc = DESC_HI | (uint64_t)(b_lo + bb * (B_HALF >> 4));
+              const uint32_t d_addr = tmem_base + DT * s;
+              if ((kc | s) == 0) {
+                tc_mma_i8_2sm(d_addr, adesc, bdesc, idesc2_n(NB), 0);
 #pragma unroll
-              for (uint32_t k4 = 0; k4 < KC / 32; k4++)
-                tc_mma_i8_2sm(d_addr, umma_desc(a_addr + 32 * k4), umma_desc(b_addr + 32 * k4), idesc2_n(NB), (kc | k4 | s) != 0);
+                for (uint32_t k4 = 1; k4 < KC / 32; k4++) tc_mma_i8_2sm(d_addr, adesc + 2 * k4, bdesc + 2 * k4, idesc2_n(NB), 1);
+              } else {
+#pragma unroll
+                for (uint32_t k4 = 0; k4 < KC / 32; k4++) tc_mma_i8_2sm(d_addr, adesc + 2 * k4, bdesc + 2 * k4, idesc2_n(NB), 1);
+              }
               tc_commit_2sm(a_empty(st));
               if (s == 7) tc_commit_2sm(b_empty(bb));
             }
             __syncwarp();
+            if (++st == nstages) { st = 0; ph ^= 1; }
           }
         }
-        if (lane == 0) tc_commit_2sm(tmem_full);
+        if (elect_one()) tc_commit_2sm(tmem_full);
         __syncwarp();
       }
     }
@@ -642,7 +654,7 @@ bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k) {
 bool launch_imma_gemm(const ImmaArgs& a, cudaStream_t st) {
   if (!imma_shape_ok(a.rows, a.D, a.k)) return false;
   if (a.pair) return launch_pair(a, st);
-  return launch_dt<32>(a, st);
+  return a.dt == 16 ? launch_dt<16>(a, st) : launch_dt<32>(a, st);
 }
 
 static bool launch_planes(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb, size_t Mb_plane,

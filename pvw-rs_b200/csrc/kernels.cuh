@@ -109,11 +109,9 @@ struct FusedConst {
   u64 half_d[4];   // floor(Delta / 2)
   u64 vinv;        // reciprocal of dv[nd-1] (Moller-Granlund)
   u64 cmax;        // largest one-word x with x * Delta^(l-1) + floor(Delta/2) + 1 <= floor(Q/2)
+  u64 emax;        // noise magnitudes the claim check takes: l * e < min_j q_j and < 2^63, so that l * e needs no reduction
   uint32_t nd, shift;
   int enabled;
-  int impl;        // 2 (default): thread = share, candidates from the sub-basis, then the claim z_i = -(m D^i + e_i) checked in every
-                   // other limb; 1: thread = share, every lifted value verified in every limb; 0: the shared-memory staged form of 1
-                   // (always used for l = 32)
 };
 bool launch_decode_fused(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps,
                          uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, size_t z_cs = 0, const DecodeSub* sub = nullptr);

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const void* __restrict__
 #pragma unroll
     for (int t = 0; t < ELL; t++) a[t] = reduce_i64(x[t], lc);
   }
-  ntt_forward_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
+  ntt_forward_lazy_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
   if (m != nullptr) {
     u64 mr = reduce_i64((long long)m[idx], lc);  // `scalars[p] as i64`, encryption.rs:195
 #pragma unroll
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) ntt_planes4_kernel(const void* __restrict
     load_small<ELL>(coef, cbytes, idx + p, x);
 #pragma unroll
     for (int t = 0; t < ELL; t++) a[p][t] = reduce_i64(x[t], lc);
-    ntt_forward_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
+    ntt_forward_lazy_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
   }
   const uint64_t r = idx / inner, j = idx % inner;
   const size_t first = SIDE == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;

@@ -74,17 +74,15 @@ def test_fused_decode_matches_the_oracle_on_both_sides_of_every_check(name):
     for i in rng.choice(len(cs), size=min(12, len(cs)), replace=False):       # the exact (literal) restatement agrees with the C one
         assert O.decode_scalar_pvw_rns(P, polys[i]) == int(co.decode(zhat[i:i + 1])[0])
     eng = pvw.Engine(**engine_kwargs(P))
-    for fused, impl in ((1, 2), (1, 1), (1, 0), (0, 2)):  # claim-checking kernel (default), per-value verification (per share / staged), chain only
+    for fused in (1, 0):                                  # fast path + per-share fallback, general chain only
         eng.set_option("decode_fused", fused)
-        eng.set_option("decode_fused_impl", impl)
         eng.set_option("profile", 2)
         got = eng.decode_batch(batch)
         prof = eng.profile()
         eng.set_option("profile", 0)
-        assert (got == want).all(), f"decode_fused={fused}, impl={impl}: {(got != want).sum()} of {len(want)} differ"
+        assert (got == want).all(), f"decode_fused={fused}: {(got != want).sum()} of {len(want)} differ"
         if fused == 0:
             assert prof["decode_fused"][1] == 0
-    eng.set_option("decode_fused_impl", 2)
     if name in ("VDs", "P128s", "P256s", "L32"):
         eng.set_option("decode_fused", 1)
         eng.set_option("profile", 2)

@@ -87,7 +87,7 @@ def workloads():
         "C1": Workload("C1", "C1 examples/pvw.rs defaults", 7, 32, 8, list(O.EX_MODULI), 0.5, 50, 50, 7, "share", False, 7, 7),
         "C2": Workload("C2", "C2 P128", 1024, 256, 8, p128, 0.5, 100, 200, 256, "u62", False, 128, 1024),
         "C3": Workload("C3", "C3 P128", 4096, 256, 8, p128, 0.5, 100, 200, 256, "u62", False, 64, 4096),
-        "C4": Workload("C4", "C4 P256", 8192, 512, 16, O.largest_ntt_primes(34), 0.5, 100, 200, 32, "u62", False, 8, 4096),
+        "C4": Workload("C4", "C4 P256", 8192, 512, 16, O.largest_ntt_primes(34), 0.5, 100, 200, 128, "u62", False, 8, 4096),
         "C5": Workload("C5", "C5 pvw_valid_dec-style", 4096, 1024, 8, list(O.VD_MODULI), 10.0, 1, 1172385, 256, "share", True, 64, 4096),
     }
 
@@ -319,10 +319,8 @@ def run_b200(args, W: Workload):
 
     def step(m_, r_, e1_, e2_, sk_, out_):
         """encrypt + c1 exchange + decrypt; the arguments are all device tensors or all host arrays"""
-        if exchange == "ce":        # c1 slice first, its peer copies run on the copy engines under the c2 product
-            eng.encrypt_batch(0, None, r_, e1_, None, c1_range=(c1_lo, c1_hi), part="c1")
-            xch.push(0, D)
-            eng.encrypt_batch(0, m_, r_, None, e2_, part="c2")
+        if exchange == "ce":        # one call: c1 slice, its peer copies queued on the copy engines (PVW_ENC_PUSH_C1), then the c2 product over them
+            eng.encrypt_batch(0, m_, r_, e1_, e2_, c1_range=(c1_lo, c1_hi), push_c1=True)
             xch.wait()
         elif exchange == "nccl":    # one call, then the in-place all-gather ordered on the library's stream
             eng.encrypt_batch(0, m_, r_, e1_, e2_, c1_range=(c1_lo, c1_hi))

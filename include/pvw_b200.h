@@ -50,6 +50,9 @@ enum { PVW_IO_HOST = 0u, PVW_IO_DEVICE = 1u,
        /* pvw_encrypt_batch only: compute just c1 (dealers c1_lo..c1_hi) or just c2, so that a multi-GPU host layer can start the
           all-gather of the c1 slices while the (much larger) c2 product runs; m / e2 may be NULL with C1_ONLY, e1 with C2_ONLY */
        PVW_ENC_C1_ONLY = 2u, PVW_ENC_C2_ONLY = 4u,
+       /* pvw_encrypt_batch on a connected shard exchange (pvw_shard_connect): queue pvw_shard_push_c1 for the slice right after its
+          product, inside the call, so that one call (host buffers included) overlaps the peer copies with the c2 product */
+       PVW_ENC_PUSH_C1 = 8u,
        /* element type of the small signed inputs.  Default: int64_t, the reference's `i64` coefficient type (SecretKey.secret_coeffs,
           secret_key.rs:14-18; Poly::from_coefficients(&[i64]), encryption.rs:148).  The values are tiny -- CBD(variance <= 16) secrets
           and randomness lie in [-32, 32], errors within the bounds of parameters.rs:110-114 -- so a host that feeds many dealers per

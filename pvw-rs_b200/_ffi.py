@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libpvw_b200.so")
 
 PVW_OK = 0
 PVW_IO_HOST, PVW_IO_DEVICE = 0, 1
-PVW_ENC_C1_ONLY, PVW_ENC_C2_ONLY = 2, 4
+PVW_ENC_C1_ONLY, PVW_ENC_C2_ONLY, PVW_ENC_PUSH_C1 = 2, 4, 8
 PVW_IN_SECRET_I8, PVW_IN_ERROR_I32, PVW_IN_ERROR_I16 = 0x100, 0x200, 0x400
 STATUS_NAMES = {
     0: "Ok", -1: "InvalidParameters", -2: "DimensionMismatch", -3: "IndexOutOfBounds", -4: "EncryptionError",

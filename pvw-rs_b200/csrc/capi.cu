@@ -457,6 +457,8 @@ int guarded(pvw_ctx* c, F&& f) {
 
 extern "C" {
 
+static void shard_push_c1(pvw_ctx* c, uint32_t slot0, uint32_t count);
+
 int pvw_ctx_create(pvw_ctx** out, const pvw_params_desc* d) {
   if (!out || !d) { g_create_error = "null argument"; return PVW_ERR_INVALID_PARAMETERS; }
   *out = nullptr;
@@ -711,6 +713,8 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     const HostParams& hp = c->hp;
     const uint32_t L = hp.L, k = hp.k, ell = hp.ell, nrows = c->nrows;
     require(!((flags & PVW_ENC_C1_ONLY) && (flags & PVW_ENC_C2_ONLY)), PVW_ERR_INVALID_PARAMETERS, "C1_ONLY and C2_ONLY exclude each other");
+    require(!(flags & PVW_ENC_PUSH_C1) || (c->sh.connected && !(flags & PVW_ENC_C2_ONLY)), PVW_ERR_INVALID_PARAMETERS,
+            "PVW_ENC_PUSH_C1 needs a connected shard exchange (pvw_shard_connect) and a call that computes c1");
     require(c1_lo <= c1_hi && c1_hi <= D, PVW_ERR_INVALID_PARAMETERS, "bad c1 dealer range");
     const bool do_c2 = !(flags & PVW_ENC_C1_ONLY);
     if (flags & PVW_ENC_C2_ONLY) c1_lo = c1_hi = 0;
@@ -771,6 +775,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
         imma_launch(c, g);
       }
+      if (flags & PVW_ENC_PUSH_C1) shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);   // peer copies start now, under the c2 product
       if (do_c2) {
         // The product goes to a slot-major scratch (lanes of a warp = consecutive parties: full-sector stores), a chunk of
         // dealers at a time; the NTT kernel then writes c2 = NTT(e2) + m g_hat + product in the store layout, reading the product
@@ -799,6 +804,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
         gemm(c, g);
       }
+      if (flags & PVW_ENC_PUSH_C1) shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);
       if (do_c2) {
         GemmArgs g{};
         g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
@@ -1429,7 +1435,11 @@ int pvw_shard_disconnect(pvw_ctx* c) {
 }
 
 int pvw_shard_push_c1(pvw_ctx* c, uint32_t slot0, uint32_t count) {
-  return guarded(c, [&] {
+  return guarded(c, [&] { shard_push_c1(c, slot0, count); });
+}
+
+static void shard_push_c1(pvw_ctx* c, uint32_t slot0, uint32_t count) {
+  {
     pvw_ctx::Shard& sh = c->sh;
     require(sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_push_c1: not connected");
     require((uint64_t)slot0 + count <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + count, c->cap));
@@ -1450,7 +1460,7 @@ int pvw_shard_push_c1(pvw_ctx* c, uint32_t slot0, uint32_t count) {
       const uint32_t r = (sh.rank + i) % sh.world;
       CUDA_CHECK(cudaMemcpyAsync(sh.peer_flags[r] + sh.rank, stage, 8, cudaMemcpyDeviceToDevice, sh.xstream));   // "my slice of exchange seq has landed"
     }
-  });
+  }
 }
 
 int pvw_shard_wait_c1(pvw_ctx* c) {

@@ -273,13 +273,14 @@ class Engine:
         self._check(self.lib.pvw_ct_reserve(self.h, capacity))
         self.capacity = capacity
 
-    def encrypt_batch(self, slot0: int, m, r, e1, e2, c1_range=None, part: str = "both"):
+    def encrypt_batch(self, slot0: int, m, r, e1, e2, c1_range=None, part: str = "both", push_c1: bool = False):
         """m [D][nrows] u64; r, e1 [D][k][l] i64; e2 [D][nrows][l] i64 -- all host or all device.
         part: "both", or "c1" / "c2" alone (PVW_ENC_C1_ONLY / PVW_ENC_C2_ONLY: a multi-GPU host layer all-gathers the c1 slices
-        while the c2 product runs); m / e2 may be None with "c1", e1 with "c2"."""
+        while the c2 product runs); m / e2 may be None with "c1", e1 with "c2".
+        push_c1: on a connected shard exchange, queue the peer copies of the c1 slice inside the call (PVW_ENC_PUSH_C1)."""
         D = int(r.shape[0])
         lo, hi = (0, D) if c1_range is None else c1_range
-        pflag = {"both": 0, "c1": _ffi.PVW_ENC_C1_ONLY, "c2": _ffi.PVW_ENC_C2_ONLY}[part]
+        pflag = {"both": 0, "c1": _ffi.PVW_ENC_C1_ONLY, "c2": _ffi.PVW_ENC_C2_ONLY}[part] | (_ffi.PVW_ENC_PUSH_C1 if push_c1 else 0)
         am = _Arg(m, np.uint64, (D, self.nrows), "m") if m is not None else None
         ar = _SmallArg(r, (D, self.k, self.l), "r", "secret")
         ae2 = _SmallArg(e2, (D, self.nrows, self.l), "e2", "error") if e2 is not None else None

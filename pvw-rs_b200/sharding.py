@@ -87,6 +87,9 @@ class CopyEngineExchange:
         engine.shard_connect(plan.world, plan.rank, [row.tobytes() for row in table])
         self.connected = True
 
+    def note_pushed(self):
+        """the push was queued inside pvw_encrypt_batch (PVW_ENC_PUSH_C1): nothing to do here, kept for symmetry / call counting"""
+
     def push(self, slot0: int, D: int):
         """after the c1 product of this rank's slice of the D dealers stored from slot0 has been queued"""
         if self.plan.world == 1:

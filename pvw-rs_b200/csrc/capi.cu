@@ -103,7 +103,7 @@ struct pvw_ctx {
   int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
   // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
-  int use_imma = 1, imma_pair = 0;
+  int use_imma = 1, imma_pair = 0, imma_stages = 0;
   int64_t imma_min_dealers = 8, imma_min_rows = 16, imma_chunk_dealers = 512;
   DevBuf As, Bs, Vx, shat_s, prod;
   bool As_valid = false, Bs_valid = false;
@@ -419,6 +419,7 @@ const uint8_t* planes_B(pvw_ctx* c) {
 }
 void imma_launch(pvw_ctx* c, ImmaArgs g) {
   g.pair = c->imma_pair;
+  g.stages = c->imma_stages;
   bool ok = true;
   launch(c, PVW_KERNEL_MAC, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
   require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
@@ -1501,6 +1502,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     std::string n(name);
     if (n == "imma") c->use_imma = value != 0;
     else if (n == "imma_pair") c->imma_pair = value != 0;
+    else if (n == "imma_stages") { require(value == 0 || (value >= 2 && value <= 10), PVW_ERR_INVALID_PARAMETERS, "imma_stages must be 0 (auto) or 2..10"); c->imma_stages = (int)value; }
     else if (n == "imma_min_dealers") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_dealers must be >= 1"); c->imma_min_dealers = value; }
     else if (n == "imma_min_rows") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_rows must be >= 1"); c->imma_min_rows = value; }
     else if (n == "imma_chunk_dealers") { require(value >= 16 && value <= (1 << 20), PVW_ERR_INVALID_PARAMETERS, "imma_chunk_dealers must be in [16, 2^20]"); c->imma_chunk_dealers = value; }

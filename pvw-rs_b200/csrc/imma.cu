@@ -611,10 +611,14 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   const uint32_t b_tile = nkc * 8 * DT * KC;
   const uint32_t resident = (2 * b_tile + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 1u : 0u;
   const uint32_t b_bytes = resident ? 2 * b_tile : 2 * 8 * DT * KC;
-  const uint32_t nstages = std::max(2u, std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
+  const uint32_t cap = a.stages >= 2 ? std::min<uint32_t>((uint32_t)a.stages, MAX_STAGES) : MAX_STAGES;
+  const uint32_t nstages = std::max(2u, std::min<uint32_t>(cap, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
   auto kern = resident ? imma_gemm_kernel<DT, true> : imma_gemm_kernel<DT, false>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return false;  // per device
+  // the whole 228 KB as shared memory whatever this launch asks for: with a shorter ring (ImmaArgs::stages) the rest stays free for
+  // the CTAs of kernels on other streams (the driver would otherwise pick the smallest carve-out that fits this kernel alone)
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) return false;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   const uint64_t tiles = (uint64_t)((a.rows + RT - 1) / RT) * ((a.D + DT - 1) / DT) * planes;

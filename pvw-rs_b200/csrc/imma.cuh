@@ -31,6 +31,8 @@ struct ImmaArgs {
   int mode, O_packed;
   const LimbConst* lc;   // [L]
   int pair;              // 1: the two-SM form (tcgen05.mma.cta_group::2 on CTA pairs) -- measured, not faster; default 0
+  int stages;            // depth of the shared-memory ring of M stages: 0 = as deep as fits (the kernel then owns the SM's shared memory);
+                         // 2..10 = at most that many, which leaves shared memory for kernels of other streams to co-reside
   int dt;                // dealers per tile: 0 = 32 (default), 16 = the half-width tile (probe: tools/csrc/imma_probe.cu)
 };
 // false when the shape cannot be served (tensor-map creation failed): the caller must have checked imma_shape_ok

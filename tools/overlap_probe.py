@@ -41,9 +41,18 @@ def make():
     return eng, args, sk, out
 
 
+STAGES = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 a, aargs, ask, aout = make()
+a.set_option("imma_stages", STAGES)
 b, bargs, bsk, bout = make()
 parties = np.arange(n, dtype=np.uint32)
+# The Engine wrapper orders every device-tensor call after torch's current stream and torch's stream after the call, which
+# serialises two contexts through that stream.  The inputs here are long finished: drop the ordering so that the two library
+# streams are really independent (the first version of this probe did not, and "measured" no overlap for that reason alone).
+torch.cuda.synchronize()
+for e in (a, b):
+    e._before_device_call = lambda: None
+    e._after_device_call = lambda: None
 
 
 def t(fn, reps=5):
@@ -59,8 +68,23 @@ def t(fn, reps=5):
 enc = lambda: a.encrypt_batch(0, *aargs)
 dec = lambda: b.decrypt_batch(parties, bsk, D=D, out=bout)
 both = lambda: (enc(), dec())
-print({"encrypt_ms": t(enc), "decrypt_ms": t(dec), "both_concurrent_ms": t(both)})
+print({"imma_stages": STAGES, "encrypt_ms": t(enc), "decrypt_ms": t(dec), "both_concurrent_ms": t(both)})
 # a pure CUDA-core kernel on the other stream: the wire-format packer of context B against context A's tensor-core product
 buf = torch.empty(D * b.wire_layout.ciphertext_bytes, dtype=torch.uint8, device=dev)
 ser = lambda: b.wire_ct_serialize(0, D, out=buf)
 print({"encrypt_ms": t(enc), "serialize_ms": t(ser), "both_concurrent_ms": t(lambda: (enc(), ser(), ser()))})
+# a memory-bound torch kernel (torch's own stream, tiny shared-memory / register footprint) against the tensor-core product
+x = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+side = torch.cuda.Stream(device=dev)
+def axpy():
+    with torch.cuda.stream(side):
+        for _ in range(4):
+            x.mul_(1.0001)
+def ta(fn, reps=5):
+    fn(); a.synchronize(); side.synchronize(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    a.synchronize(); side.synchronize(); torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+print({"encrypt_ms": ta(enc), "torch_elementwise_ms": ta(axpy), "both_concurrent_ms": ta(lambda: (enc(), axpy()))})

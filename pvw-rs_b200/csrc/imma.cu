@@ -532,7 +532,8 @@ imma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // contiguous bytes per instruction (the first version stored single bytes: 8x the store instructions, 32-byte bursts).
 //   src  = M + rowmap(row) * M_rs + limb * M_ls + j * ell + c            (canonical residues, or packed halves)
 //   dst  = Mb + (limb * ell + c) * Mb_plane + row * dst_rs + s * dst_bs + j          s = byte index
-// matrix side (A, B, s_hat): dst_rs = 8 * kp, dst_bs = kp;  dealer side (r_hat, c1): dst_rs = kp, dst_bs = rows * kp
+// both sides (A, B, s_hat; r_hat, c1): dst_rs = 8 * kp, dst_bs = kp.  (The dealer side first kept byte plane t of all dealers
+// together, rows * kp apart: 64 stores per polynomial 512 KB apart at 2048 dealers ran at a third of the matrix side's rate.)
 IMMA_DEV void transpose_4x8(const u64 (&v)[4], uint32_t (&w)[8]) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -605,8 +606,9 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   // M byte planes: [plane][row][s][kp]; box = 128 bytes of one plane s of 128 rows
   if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
-  // V byte planes: [plane][t][d][kp]; box = 128 bytes of DT dealers of all 8 planes t -> rows (t, d) of the B tile
-  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
+  // V byte planes: [plane][d][t][kp] (the same layout as the matrix side: a dealer's eight planes are 8 * kp contiguous bytes);
+  // box = 128 bytes of DT dealers of all 8 planes t, t outermost -> rows (t, d) of the B tile in shared memory
+  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {8ull * kp, kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
   // two whole B tiles resident when at least four ring stages still fit (k <= 256 at DT = 32), else two K-chunk slots
   const uint32_t b_tile = nkc * 8 * DT * KC;
   const uint32_t resident = (2 * b_tile + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 1u : 0u;
@@ -634,7 +636,7 @@ bool launch_pair(const ImmaArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
   // each CTA of the pair loads four of the eight byte planes t of the DT dealers
-  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {kp, (cuuint64_t)a.Vb_D * kp, a.Vb_plane}, {KC, 32, 4, 1})) return false;
+  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {8ull * kp, kp, a.Vb_plane}, {KC, 32, 4, 1})) return false;
   const uint32_t b_bytes = 2 * 4 * 32 * KC;
   const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE);
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
@@ -680,7 +682,7 @@ bool launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows,
 bool launch_imma_planes_v(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vb, size_t Vb_plane,
                           bool packed, const uint32_t* dmap, cudaStream_t st) {
   const uint32_t kp = imma_kp(k);
-  return launch_planes(V, V_ls, V_ds, D, k, L, ell, Vb, Vb_plane, kp, (size_t)D * kp, packed, dmap, st);
+  return launch_planes(V, V_ls, V_ds, D, k, L, ell, Vb, Vb_plane, (size_t)8 * kp, kp, packed, dmap, st);
 }
 
 }  // namespace pvw

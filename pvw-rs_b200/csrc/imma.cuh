@@ -15,7 +15,7 @@ __host__ __device__ inline uint32_t imma_kp(uint32_t k) { return (k + 15u) & ~15
 
 // Operands of the tensor-core path are BYTE PLANES (plane index p = limb*ell + c):
 //   Mb[p*Mb_plane + (row*8 + s)*kp + j] = byte s of M[row][limb][j][c]         (rows of the matrix: A, A^T, B, s_hat)
-//   Vb[p*Vb_plane + (t*Vb_D + d)*kp + j] = byte t of V[d][limb][j][c]           (dealer side: r_hat, c1)
+//   Vb[p*Vb_plane + (d*8 + t)*kp + j] = byte t of V[d][limb][j][c]              (dealer side: r_hat, c1; same form)
 //   O  u64   O[d*O_ds + limb*O_ls + row*O_rs + c*O_cs]  canonical, or packed halves when O_packed
 //   S  u64   S[sd*S_ds + limb*S_ls + srow*ell + c] canonical, sd = V_dmap ? V_dmap[d] : d, srow = S_rowmap ? S_rowmap[row] : row
 // mode 0: O = acc + O, 1: O = acc - S, 2: O = acc          (as GemmArgs::mode)

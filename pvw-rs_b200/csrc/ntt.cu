@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const void* __restrict__
     // idx = r*inner + j (inner = k): r is a matrix row (MODE 3) or a dealer (MODE 4); vstride = kp, lstride = plane stride in bytes.
     const uint64_t r = idx / inner, j = idx % inner, kp = vstride;
     uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (size_t)limb * ELL * lstride;
-    const size_t first = MODE == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;        // byte plane 0
-    const size_t step = MODE == 3 ? kp : (size_t)(count / inner) * kp;                  // to the next byte plane
+    const size_t first = (size_t)r * 8 * kp + j;                                        // byte plane 0 (both sides share the layout)
+    const size_t step = kp;                                                             // to the next byte plane
 #pragma unroll
     for (int t = 0; t < ELL; t++) {
       uint8_t* o = o8 + (size_t)t * lstride + first;
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(128) ntt_planes4_kernel(const void* __restrict
     ntt_forward_lazy_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
   }
   const uint64_t r = idx / inner, j = idx % inner;
-  const size_t first = SIDE == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;
-  const size_t step = SIDE == 3 ? kp : (size_t)(count / inner) * kp;
+  const size_t first = (size_t)r * 8 * kp + j;      // SIDE 3 and 4 share the layout: row / dealer r, byte plane b, polynomial j
+  const size_t step = kp;
   uint8_t* o8 = out + (size_t)limb * ELL * pstride + first;
 #pragma unroll
   for (int t = 0; t < ELL; t++) {
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(64) ntt_small_generic_kernel(const int mode, c
   if (mode == 3 || mode == 4) {
     const uint64_t r = idx / inner, j = idx % inner, kp = vstride;
     uint8_t* o8 = reinterpret_cast<uint8_t*>(out) + (size_t)limb * ell * lstride;
-    const size_t first = mode == 3 ? (size_t)r * 8 * kp + j : (size_t)r * kp + j;
-    const size_t step = mode == 3 ? kp : (size_t)(count / inner) * kp;
+    const size_t first = (size_t)r * 8 * kp + j;
+    const size_t step = kp;
     for (uint32_t t = 0; t < ell; t++)
       for (int b = 0; b < 8; b++) o8[(size_t)t * lstride + first + (size_t)b * step] = (uint8_t)(a[t] >> (8 * b));
     return;

@@ -301,9 +301,14 @@ def run_b200(args, W: Workload):
     xch = pvw.sharding.CopyEngineExchange(eng, plan, device=dev) if exchange == "ce" else None
 
     # ---- the step's synthetic inputs: same dealers on every rank (r, e1), local columns of m / e2 ---------------
-    gen.manual_seed(77)
+    # the dealers' randomness is sampled once (rank 0) and broadcast over NCCL / NVLink: every rank encrypts under the SAME r, e1
+    # (north_star: "A and r are replicated via NCCL broadcast"); m and e2 are per party, i.e. local to the rank that owns the rows
+    gen.manual_seed(77 + 1000 * rank)
     r = synth_device(torch, dev, gen, (D, k, l), "cbd", variance=W.variance)
     e1 = synth_device(torch, dev, gen, (D, k, l), "uniform", W.b1)
+    if world > 1:
+        dist.broadcast(r, 0)
+        dist.broadcast(e1, 0)
     gen.manual_seed(78 + rank)
     if W.msg == "share":
         m = (torch.arange(D, device=dev, dtype=torch.int64).reshape(D, 1) * 1000 + torch.arange(row0, row0 + nrows, device=dev, dtype=torch.int64).reshape(1, nrows) + 1).contiguous()

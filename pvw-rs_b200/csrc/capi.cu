@@ -107,6 +107,8 @@ struct pvw_ctx {
   int64_t imma_min_dealers = 8, imma_min_rows = 16, imma_chunk_dealers = 512;
   DevBuf As, Bs, Vx, shat_s, prod;
   bool As_valid = false, Bs_valid = false;
+  int planes_only = 0;           // option "planes_only": once the byte planes of B exist, free its u64 copy (rebuilt on demand)
+  bool B_released = false;
   int64_t decrypt_chunk_shares = 1 << 19;
   int64_t upload_chunk_bytes = 256ll << 20;
   // multi-GPU c1 exchange over the copy engines (pvw_shard_*): peers' ciphertext stores and flag arrays mapped through CUDA IPC
@@ -415,6 +417,11 @@ const uint8_t* planes_B(pvw_ctx* c) {
     require(ok, PVW_ERR_INTERNAL, "byte-plane conversion of B: launch grid too large");
     c->Bs_valid = true;
   }
+  if (c->planes_only && !c->B_released && c->B.p) {   // the batched path reads the planes only: keep ONE resident copy of B
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->B.release();
+    c->B_released = true;
+  }
   return c->Bs.as<uint8_t>();
 }
 void imma_launch(pvw_ctx* c, ImmaArgs g) {
@@ -597,6 +604,15 @@ int pvw_crs_generate_from_tag(pvw_ctx* c, const char* tag, uint64_t* A_out) {
 
 static void ensure_B(pvw_ctx* c) {
   const size_t bytes = (size_t)c->hp.L * c->nrows * c->hp.k * c->hp.ell * 8;
+  if (c->B_released) {   // a single call, a download or a key update needs the u64 operand again: rebuild it from the planes
+    const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows, kp = imma_kp(k);
+    c->B.ensure(bytes);
+    bool ok = true;
+    launch(c, PVW_KERNEL_PERMUTE, 0.0, [&] { ok = launch_imma_unplanes_m(c->B.as<u64>(), (size_t)nrows * k * ell, (size_t)k * ell, nrows, k, L, ell, c->Bs.as<uint8_t>(), (size_t)nrows * 8 * kp, true, c->stream); });
+    require(ok, PVW_ERR_INTERNAL, "rebuilding B from its byte planes: launch grid too large");
+    c->B_released = false;
+    return;
+  }
   if (c->B.bytes >= bytes) return;
   c->B.ensure(bytes);
   CUDA_CHECK(cudaMemsetAsync(c->B.p, 0, bytes, c->stream));  // GlobalPublicKey::new fills with zero polys, public_key.rs:196-208
@@ -807,6 +823,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       }
       if (flags & PVW_ENC_PUSH_C1) shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);
       if (do_c2) {
+        ensure_B(c);
         GemmArgs g{};
         g.M = c->B.as<u64>(); g.M_ls = (size_t)nrows * k * ell; g.M_rs = (size_t)k * ell;
         g.V = c->rhat.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = w1;
@@ -1502,6 +1519,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     std::string n(name);
     if (n == "imma") c->use_imma = value != 0;
     else if (n == "imma_pair") c->imma_pair = value != 0;
+    else if (n == "planes_only") c->planes_only = value != 0;
     else if (n == "imma_stages") { require(value == 0 || (value >= 2 && value <= 10), PVW_ERR_INVALID_PARAMETERS, "imma_stages must be 0 (auto) or 2..10"); c->imma_stages = (int)value; }
     else if (n == "imma_min_dealers") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_dealers must be >= 1"); c->imma_min_dealers = value; }
     else if (n == "imma_min_rows") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_rows must be >= 1"); c->imma_min_rows = value; }

@@ -575,6 +575,36 @@ __global__ void __launch_bounds__(256) imma_planes_kernel(const u64* __restrict_
   }
 }
 
+// the inverse: byte planes -> limb-major operand (used when the u64 copy of B was released and a single call / download needs it)
+__global__ void __launch_bounds__(256) imma_unplanes_kernel(u64* __restrict__ M, size_t M_ls, size_t M_rs, uint32_t k, uint32_t ell, uint32_t jc,
+                                                            const uint8_t* __restrict__ Mb, size_t Mb_plane, size_t src_rs, size_t src_bs, int packed,
+                                                            uint32_t nchunks) {
+  extern __shared__ u64 s_v[];                                            // [jc][ell + 1]
+  const uint32_t row = blockIdx.x, limb = blockIdx.y / nchunks, j0 = (blockIdx.y - limb * nchunks) * jc;
+  const uint32_t jn = min(jc, k - j0), pitch = ell + 1, groups = (jn + 3) / 4;
+  for (uint32_t t = threadIdx.x; t < groups * ell; t += blockDim.x) {
+    const uint32_t c = t / groups, jg = t - c * groups;
+    const uint8_t* in = Mb + (size_t)(limb * ell + c) * Mb_plane + (size_t)row * src_rs + j0 + 4 * jg;
+    uint32_t w[8];
+#pragma unroll
+    for (uint32_t b = 0; b < 8; b++) w[b] = *reinterpret_cast<const uint32_t*>(in + (size_t)b * src_bs);
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+      u64 v = 0;
+#pragma unroll
+      for (uint32_t b = 0; b < 8; b++) v |= (u64)((w[b] >> (8 * i)) & 0xffu) << (8 * b);
+      if (4 * jg + i < jn) s_v[(4 * jg + i) * pitch + c] = v;
+    }
+  }
+  __syncthreads();
+  u64* dst = M + (size_t)row * M_rs + (size_t)limb * M_ls + (size_t)j0 * ell;
+  for (uint32_t t = threadIdx.x; t < jn * ell; t += blockDim.x) {
+    const uint32_t j = t / ell, c = t - j * ell;
+    const u64 v = s_v[j * pitch + c];
+    dst[t] = packed ? pack_halves(v) : v;
+  }
+}
+
 typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 encode_fn tensor_map_encoder() {
@@ -677,6 +707,15 @@ bool launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows,
                           size_t Mb_plane, bool packed, cudaStream_t st) {
   const uint32_t kp = imma_kp(k);
   return launch_planes(M, M_ls, M_rs, rows, k, L, ell, Mb, Mb_plane, (size_t)8 * kp, kp, packed, nullptr, st);
+}
+
+bool launch_imma_unplanes_m(u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, const uint8_t* Mb, size_t Mb_plane,
+                            bool packed, cudaStream_t st) {
+  if (rows == 0) return true;
+  const uint32_t kp = imma_kp(k), jc = std::max(4u, 2048u / ell), nchunks = (k + jc - 1) / jc;
+  if ((uint64_t)L * nchunks > 65535u) return false;
+  imma_unplanes_kernel<<<dim3(rows, L * nchunks), 256, (size_t)jc * (ell + 1) * 8, st>>>(M, M_ls, M_rs, k, ell, jc, Mb, Mb_plane, (size_t)8 * kp, kp, packed ? 1 : 0, nchunks);
+  return true;
 }
 
 bool launch_imma_planes_v(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vb, size_t Vb_plane,

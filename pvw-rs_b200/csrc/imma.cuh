@@ -42,6 +42,9 @@ bool imma_shape_ok(uint32_t rows, uint32_t D, uint32_t k);
 // limb-major operand M[limb*M_ls + row*M_rs + j*ell + c] (canonical, or packed halves) -> Mb
 bool launch_imma_planes_m(const u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, uint8_t* Mb,
                           size_t Mb_plane, bool packed, cudaStream_t st);
+// the inverse of launch_imma_planes_m: rebuilds the limb-major operand from its byte planes
+bool launch_imma_unplanes_m(u64* M, size_t M_ls, size_t M_rs, uint32_t rows, uint32_t k, uint32_t L, uint32_t ell, const uint8_t* Mb, size_t Mb_plane,
+                            bool packed, cudaStream_t st);
 // V[sd*V_ds + limb*V_ls + j*ell + c] (canonical, or packed halves), sd = dmap ? dmap[d] : d, d < D  ->  Vb (Vb_D = D)
 bool launch_imma_planes_v(const u64* V, size_t V_ds, size_t V_ls, uint32_t ell, uint32_t D, uint32_t k, uint32_t L, uint8_t* Vb,
                           size_t Vb_plane, bool packed, const uint32_t* dmap, cudaStream_t st);

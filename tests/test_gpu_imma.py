@@ -147,3 +147,30 @@ def test_odd_k_falls_back_to_the_imad_kernel(pkg):
     eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)
     assert all((eng.ct_download(d)[0] == c1[d]).all() and (eng.ct_download(d)[1] == c2[d]).all() for d in range(9))
     assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=9) == S.m.T).all()
+
+
+def test_planes_only_keeps_one_copy_of_the_public_key(pkg):
+    """option planes_only: the u64 operand copy of B is freed once its byte planes exist and rebuilt from them on demand"""
+    P = SETS["WIDE"]()
+    D = 20
+    S = System(P, D, "u63")
+    c1, c2 = S.encrypt()
+    want = S.co.decrypt(S.sk, c1, c2)
+    eng = load(forced(pkg, P), S, D)
+    eng.set_option("planes_only", 1)
+    eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)                       # tensor-core path: builds the planes, releases the u64 copy
+    assert all((eng.ct_download(d)[1] == c2[d]).all() for d in (0, D - 1))
+    assert (eng.pk_download_rows(0, P.n) == S.B).all()               # rebuilt from the planes, bit for bit
+    eng.set_option("imma", 0)
+    eng.encrypt_batch(0, S.m[:1], S.r[:1], S.e1[:1], S.e2[:1])       # a single call on the CUDA cores needs the operand form again
+    assert (eng.ct_download(0)[1] == c2[0]).all()
+    eng.set_option("imma", 1)
+    eng.pk_upload_rows(3, S.B[5:6])                                  # a key update invalidates the planes; they are rebuilt from the new B
+    eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)
+    B2 = S.B.copy()
+    B2[3] = S.B[5]
+    c1b, c2b = S.co.encrypt(S.A, B2, S.m, S.r, S.e1, S.e2)
+    assert all((eng.ct_download(d)[1] == c2b[d]).all() for d in (0, D - 1))
+    eng.pk_upload_rows(3, S.B[3:4])
+    eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)
+    assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=D) == want).all()

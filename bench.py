@@ -483,7 +483,8 @@ def run_b200(args, W: Workload):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    mac_ms, mac_n, mac_bytes = prof["mac_gemm"]
+    imma_on = os.environ.get("PVW_OPTS", "").replace(" ", "").find("imma=0") < 0
+    mac_ms, mac_n, mac_bytes = (prof["imma_gemm"] if imma_on and prof["imma_gemm"][1] else prof["mac_gemm"])   # tensor-core / CUDA-core product
     achieved = mac_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     kernel_ms = {kname: round(v[0] / args.steps, 4) for kname, v in prof.items()}
 
@@ -516,7 +517,7 @@ def run_b200(args, W: Workload):
     # kernel's roof is the tensor pipe.  Peak: the rate measured on this part with the kernel's own MMA stream and nothing else
     # (tools/csrc/imma_probe.cu mode 4: operands resident in shared memory, no epilogue -> profiles/r02_int8_peak.json) when that
     # file exists, else twice the measured cuBLAS bf16 burst (kind::i8 issues K = 32 per instruction where bf16 issues 16).
-    imma_on = os.environ.get("PVW_OPTS", "").replace(" ", "").find("imma=0") < 0
+    imma_on = imma_on and prof["imma_gemm"][1] > 0
     bf16 = float(peaks.get("bf16_tflops", 2250.0))
     int8_meas = json_lines("r02_int8_peak.json", "int8_tops_mma_only")
     int8_peak = int8_meas if int8_meas else 2.0 * bf16
@@ -526,7 +527,7 @@ def run_b200(args, W: Workload):
                 "what": "SURVEY 8d algorithmic bytes (one operand row read per (dealer, row) + one polynomial written) over the kernel "
                         "time: > 1 because dealers are batched -- every staged tile serves 32 dealers from shared memory"}
     if imma_on:
-        roofline = {"bound": "tensor", "kernel": "mac_gemm (imma_gemm_kernel: tcgen05.mma kind::i8)", "achieved": int8_ops, "peak": int8_peak,
+        roofline = {"bound": "tensor", "kernel": "imma_gemm (imma_gemm_kernel: tcgen05.mma kind::i8)", "achieved": int8_ops, "peak": int8_peak,
                     "unit": "TOP/s (u8 x u8 -> s32, dense)", "frac": int8_ops / int8_peak,
                     "peak_source": ("measured on B200: the kernel's MMA stream alone, operands resident, no epilogue (profiles/r02_int8_peak.json)" if int8_meas
                                     else "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "2 x nominal dense bf16 (fallback)"),

@@ -79,7 +79,10 @@ struct pvw_ctx {
   bool A_set = false, At_valid = false;
   uint32_t num_keys = 0;         // max uploaded global index + 1 (public_key.rs:245-247)
   uint32_t cap = 0;
-  DevBuf c1s, c2s;
+  DevBuf c1s, c2s;               // c1s: per slot [packed residues u64[L][k][ell]][byte planes u8[L*ell][8][kp]] (c1_stride() words)
+  std::vector<uint8_t> c1p_valid;  // per slot: the byte planes behind the residues are current (written by the c1 finisher / a peer's push)
+  bool c1_external = false;        // the raw store pointer was handed out (pvw_ct_c1_device_ptr): planes can go stale behind our back
+  DevBuf prod1;                    // slot-major c1 product of one encrypt call
   // grow-only scratch
   DevBuf stage, rhat, in_small, in_small2, in_m, shat, z, y, X, outd, idxd, idxp;
   // wire format (wire.cu): record tables, envelope templates (device copies at wire_env) and a staging buffer
@@ -120,12 +123,17 @@ struct pvw_ctx {
                                         //        [2 world], [2 world + 1] staging words for the values this rank sends
     uint32_t flags_world = 0;           // the world size `flags` was allocated for
     u64 push_seq = 0, wait_seq = 0;
+    uint32_t batch_slot0 = 0, batch_D = 0;   // the encrypt call whose c1 slice was pushed last (PVW_ENC_PUSH_C1) ...
+    bool batch_direct = false;               // ... and whether its slots carry current byte planes (every rank takes the same path)
     cudaStream_t xstream = nullptr;     // the exchange stream (copy engines only)
     cudaEvent_t ev_c1 = nullptr;
     bool connected = false;
   } sh;
 
   size_t poly() const { return (size_t)hp.L * hp.ell; }
+  size_t c1_words() const { return (size_t)hp.L * hp.k * hp.ell; }                                   // residues of one c1
+  size_t c1_stride() const { return c1_words() + (size_t)hp.L * hp.ell * imma_kp(hp.k); }            // + its byte planes, in u64 words
+  void c1_planes_invalidate(uint32_t slot0, uint32_t count) { for (uint32_t i = slot0; i < slot0 + count && i < c1p_valid.size(); i++) c1p_valid[i] = 0; }
   void use() { CUDA_CHECK(cudaSetDevice(device)); }
 };
 
@@ -428,7 +436,7 @@ void imma_launch(pvw_ctx* c, ImmaArgs g) {
   g.pair = c->imma_pair;
   g.stages = c->imma_stages;
   bool ok = true;
-  launch(c, PVW_KERNEL_MAC, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
+  launch(c, PVW_KERNEL_IMMA, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
   require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
 }
 
@@ -521,7 +529,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->prod1, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
     b->release();
   delete c;
 }
@@ -709,17 +717,18 @@ int pvw_crs_multiply_by_randomness(pvw_ctx* c, uint32_t D, const uint64_t* r_hat
 
 int pvw_ct_reserve(pvw_ctx* c, uint32_t capacity) {
   return guarded(c, [&] {
-    const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell, w2 = (size_t)c->hp.L * c->nrows * c->hp.ell;
+    const size_t w1 = c->c1_stride(), w2 = (size_t)c->hp.L * c->nrows * c->hp.ell;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     require(!c->sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_ct_reserve: peers hold IPC mappings of this store; call pvw_shard_disconnect on every rank first");
     c->c1s.release(); c->c2s.release();
-    c->cap = 0;
+    c->cap = 0; c->c1p_valid.clear();
     if (capacity == 0) return;
     c->c1s.ensure((size_t)capacity * w1 * 8);
     c->c2s.ensure((size_t)capacity * w2 * 8);
     CUDA_CHECK(cudaMemsetAsync(c->c1s.p, 0, (size_t)capacity * w1 * 8, c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->c2s.p, 0, (size_t)capacity * w2 * 8, c->stream));
     c->cap = capacity;
+    c->c1p_valid.assign(capacity, 0);
   });
 }
 
@@ -745,7 +754,7 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
             "Parameters do not satisfy correctness condition - decryption may fail");
     require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS,
             fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
-    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell, s1 = c->c1_stride();
     const bool host = !(flags & PVW_IO_DEVICE);
     // copy order matters (one host-to-device DMA queue): the small inputs the first kernels need go first, then the big
     // ones (e2, m) on the copy stream, waited for only after the c2 product
@@ -770,11 +779,15 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       c->rhat.ensure((size_t)D * w1 * 8);
       ntt(c, d_r, sb, nullptr, (uint64_t)D * k, k, c->rhat.as<u64>(), w1, (size_t)k * ell, false, true);
     }
-    u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * w1;
+    u64* c1 = c->c1s.as<u64>() + (size_t)slot0 * s1;
     u64* c2 = c->c2s.as<u64>() + (size_t)slot0 * w2;
-    // c1 <- NTT(e1)   (encryption.rs:161-167); c1 += A r_hat below   (crs.rs:187-199, encryption.rs:171-173)
-    if (c1_hi > c1_lo)
-      ntt(c, d_e1, eb, nullptr, (uint64_t)(c1_hi - c1_lo) * k, k, c1 + (size_t)c1_lo * w1, w1, (size_t)k * ell);
+    // tensor-core path, usual shapes: the c1 product goes to a slot-major scratch and ONE kernel finishes c1 = NTT(e1) + product
+    // into the store, as residues and as byte planes (ntt_c1_finish_kernel).  Otherwise: c1 <- NTT(e1) (encryption.rs:161-167)
+    // here and c1 += A r_hat in the product's epilogue (crs.rs:187-199, encryption.rs:171-173).
+    const bool c1_direct = imma && c1_hi > c1_lo && k % 4 == 0 && ell <= 16;
+    if (c1_hi > c1_lo && !c1_direct)
+      ntt(c, d_e1, eb, nullptr, (uint64_t)(c1_hi - c1_lo) * k, k, c1 + (size_t)c1_lo * s1, s1, (size_t)k * ell);
+    if (c1_hi > c1_lo && !c1_direct) c->c1_planes_invalidate(slot0 + c1_lo, c1_hi - c1_lo);
     // device inputs: c2 <- NTT(e2) + (m as i64) * g_hat   (encryption.rs:195-196), then c2 += B r_hat   (:185-192, :198)
     // host inputs:   c2 <- B r_hat first (it does not need e2 / m, whose copy is still in flight), then c2 += NTT(e2) + m g_hat
     auto preload = [&](bool accumulate) {
@@ -789,10 +802,24 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       if (c1_hi > c1_lo) {
         g.Mb = planes_A(c); g.Mb_plane = (size_t)k * 8 * kp; g.rows = k;
         g.d_first = c1_lo - v_first; g.D = c1_hi - c1_lo;
-        g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
-        imma_launch(c, g);
+        if (c1_direct) {
+          const uint32_t Dc1 = c1_hi - c1_lo;
+          c->prod1.ensure((size_t)Dc1 * w1 * 8);
+          g.O = c->prod1.as<u64>(); g.O_ls = (size_t)ell * k; g.O_ds = (size_t)L * ell * k; g.O_rs = 1; g.O_cs = k; g.O_packed = 0; g.mode = 2;
+          imma_launch(c, g);
+          bool ok = true;
+          launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_ntt_c1_finish(c->T, d_e1, eb, (uint64_t)Dc1 * k, k, c1 + (size_t)c1_lo * s1, s1, c->prod1.as<u64>(), kp, c->stream); });
+          require(ok, PVW_ERR_INTERNAL, "c1 finisher: unsupported shape");
+          for (uint32_t i = slot0 + c1_lo; i < slot0 + c1_hi; i++) c->c1p_valid[i] = 1;
+        } else {
+          g.O = c1 + (size_t)c1_lo * s1; g.O_ls = (size_t)k * ell; g.O_ds = s1; g.O_rs = ell; g.O_cs = 1; g.O_packed = 1; g.mode = 0;
+          imma_launch(c, g);
+        }
       }
-      if (flags & PVW_ENC_PUSH_C1) shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);   // peer copies start now, under the c2 product
+      if (flags & PVW_ENC_PUSH_C1) {   // peer copies start now, under the c2 product
+        shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);
+        c->sh.batch_slot0 = slot0; c->sh.batch_D = D; c->sh.batch_direct = c1_direct;
+      }
       if (do_c2) {
         // The product goes to a slot-major scratch (lanes of a warp = consecutive parties: full-sector stores), a chunk of
         // dealers at a time; the NTT kernel then writes c2 = NTT(e2) + m g_hat + product in the store layout, reading the product
@@ -817,11 +844,14 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
         GemmArgs g{};
         g.M = c->A.as<u64>(); g.M_ls = (size_t)k * k * ell; g.M_rs = (size_t)k * ell;
         g.V = c->rhat.as<u64>() + (size_t)c1_lo * w1; g.V_ls = (size_t)k * ell; g.V_ds = w1;
-        g.O = c1 + (size_t)c1_lo * w1; g.O_ls = (size_t)k * ell; g.O_ds = w1; g.O_packed = 1;  // c1 is an operand of the decrypt product
+        g.O = c1 + (size_t)c1_lo * s1; g.O_ls = (size_t)k * ell; g.O_ds = s1; g.O_packed = 1;  // c1 is an operand of the decrypt product
         g.rows = k; g.D = Dc; g.k = k; g.L = L; g.ell = ell; g.mode = 0; g.lc = c->T.lc;
         gemm(c, g);
       }
-      if (flags & PVW_ENC_PUSH_C1) shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);
+      if (flags & PVW_ENC_PUSH_C1) {
+        shard_push_c1(c, slot0 + c1_lo, c1_hi - c1_lo);
+        c->sh.batch_slot0 = slot0; c->sh.batch_D = D; c->sh.batch_direct = false;
+      }
       if (do_c2) {
         ensure_B(c);
         GemmArgs g{};
@@ -844,7 +874,7 @@ int pvw_ct_download(pvw_ctx* c, uint32_t slot, uint64_t* c1, uint64_t* c2) {
   return guarded(c, [&] {
     require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
-    if (c1) download_polys(c, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, k, c1, true);
+    if (c1) download_polys(c, c->c1s.as<u64>() + (size_t)slot * c->c1_stride(), (size_t)k * ell, k, c1, true);
     if (c2) download_polys(c, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, nrows, c2, false);
   });
 }
@@ -852,7 +882,7 @@ int pvw_ct_upload(pvw_ctx* c, uint32_t slot, const uint64_t* c1, const uint64_t*
   return guarded(c, [&] {
     require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
-    if (c1) upload_polys(c, c1, k, c->c1s.as<u64>() + (size_t)slot * L * k * ell, (size_t)k * ell, PVW_IO_HOST, true);
+    if (c1) { upload_polys(c, c1, k, c->c1s.as<u64>() + (size_t)slot * c->c1_stride(), (size_t)k * ell, PVW_IO_HOST, true); c->c1_planes_invalidate(slot, 1); }
     if (c2) upload_polys(c, c2, nrows, c->c2s.as<u64>() + (size_t)slot * L * nrows * ell, (size_t)nrows * ell, PVW_IO_HOST, false);
   });
 }
@@ -860,9 +890,10 @@ int pvw_ct_c1_device_ptr(pvw_ctx* c, uint32_t slot, void** ptr, uint64_t* slot_s
   return guarded(c, [&] {
     require(ptr != nullptr, PVW_ERR_INVALID_PARAMETERS, "null argument");
     require(slot < c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slot %u exceeds the reserved capacity %u", slot, c->cap));
-    const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell;
+    const size_t w1 = c->c1_stride();
     *ptr = c->c1s.as<u64>() + (size_t)slot * w1;
     if (slot_stride) *slot_stride = w1;
+    c->c1_external = true;   // the caller may now write c1 residues (an NCCL all-gather): the planes behind them are no longer trusted
   });
 }
 
@@ -895,6 +926,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
   return guarded(c, [&] {
     if (D == 0 || P == 0) return;
     const uint32_t L = c->hp.L, k = c->hp.k, ell = c->hp.ell, nrows = c->nrows;
+    const size_t s1 = c->c1_stride();
     require(party_idx && sk && out, PVW_ERR_INVALID_PARAMETERS, "null argument");
     if (dealer_slots) {
       for (uint32_t d = 0; d < D; d++)
@@ -966,11 +998,15 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     }
     for (uint32_t dc0 = 0; dc0 < D; dc0 += Dstep) {
       const uint32_t Dc = std::min(Dstep, D - dc0);
-      if (imma) {  // byte planes of this chunk's c1 (the store holds the operand form)
+      // byte planes of this chunk's c1: read in place when the slots are consecutive and their planes are current (written by the
+      // c1 finisher or pushed by a peer), else converted from the residues into a dense buffer
+      bool in_place = imma && !d_slots && !c->c1_external;
+      for (uint32_t d = dc0; in_place && d < dc0 + Dc; d++) in_place = c->c1p_valid[d] != 0;
+      if (imma && !in_place) {
         planes_clear(c, c->Vx, (size_t)L * ell * Dc * 8 * kp);
         bool ok = true;
         launch(c, PVW_KERNEL_EXPAND, (double)Dc * L * k * ell * 16.0, [&] {
-          ok = launch_imma_planes_v(d_slots ? c->c1s.as<u64>() : c->c1s.as<u64>() + (size_t)dc0 * L * k * ell, (size_t)L * k * ell, (size_t)k * ell, ell, Dc, k, L,
+          ok = launch_imma_planes_v(d_slots ? c->c1s.as<u64>() : c->c1s.as<u64>() + (size_t)dc0 * s1, s1, (size_t)k * ell, ell, Dc, k, L,
                                c->Vx.as<uint8_t>(), (size_t)Dc * 8 * kp, true, d_slots ? d_slots + dc0 : nullptr, c->stream);
         });
         require(ok, PVW_ERR_INTERNAL, "byte-plane conversion of c1: launch grid too large");
@@ -987,7 +1023,13 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
           // subtracted by the decode kernel, which reads both with unit stride
           ImmaArgs g{};
           g.Mb = c->shat_s.as<uint8_t>(); g.Mb_plane = (size_t)Pc * 8 * kp; g.rows = Pc;
-          g.Vb = c->Vx.as<uint8_t>(); g.Vb_plane = (size_t)Dc * 8 * kp; g.Vb_D = Dc; g.d_first = 0; g.D = Dc;
+          if (in_place) {
+            g.Vb = reinterpret_cast<const uint8_t*>(c->c1s.as<u64>() + (size_t)dc0 * s1 + (size_t)L * k * ell);
+            g.Vb_plane = (size_t)8 * kp; g.Vb_dstride = s1 * 8;
+          } else {
+            g.Vb = c->Vx.as<uint8_t>(); g.Vb_plane = (size_t)Dc * 8 * kp;
+          }
+          g.Vb_D = Dc; g.d_first = 0; g.D = Dc;
           g.O = c->z.as<u64>(); g.O_ls = (size_t)ell * Pc; g.O_ds = (size_t)L * ell * Pc; g.O_rs = 1; g.O_cs = Pc;
           g.k = k; g.L = L; g.ell = ell; g.mode = 2; g.lc = c->T.lc;
           imma_launch(c, g);
@@ -995,7 +1037,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
           ntt(c, at_bytes(d_sk, (size_t)p0 * k * ell * sb), sb, nullptr, (uint64_t)Pc * k, Pc * k, c->shat.as<u64>(), 0, (size_t)Pc * k * ell, false, true);
           GemmArgs g{};
           g.M = c->shat.as<u64>(); g.M_ls = (size_t)Pc * k * ell; g.M_rs = (size_t)k * ell;
-          g.V = c->c1s.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = (size_t)L * k * ell; g.V_dmap = d_slots;
+          g.V = c->c1s.as<u64>(); g.V_ls = (size_t)k * ell; g.V_ds = s1; g.V_dmap = d_slots;
           g.O = c->z.as<u64>(); g.O_ls = (size_t)Pc * ell; g.O_ds = (size_t)L * Pc * ell;
           g.S = c->c2s.as<u64>(); g.S_ls = (size_t)nrows * ell; g.S_ds = (size_t)L * nrows * ell; g.S_rowmap = c->idxp.as<uint32_t>() + p0;
           g.rows = Pc; g.D = D; g.k = k; g.L = L; g.ell = ell; g.mode = 1; g.lc = c->T.lc;
@@ -1143,7 +1185,7 @@ int pvw_wire_ct_serialize(pvw_ctx* c, uint32_t slot0, uint32_t D, uint8_t* out, 
     require(out != nullptr, PVW_ERR_INVALID_PARAMETERS, "out is null");
     require(stride >= z.ct, PVW_ERR_INVALID_PARAMETERS, fmt("stride %llu is smaller than one serialised ciphertext (%llu bytes)", (unsigned long long)stride, (unsigned long long)z.ct));
     require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
-    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const size_t w1 = c->c1_stride(), w2 = (size_t)L * nrows * ell;
     const bool host = !(flags & PVW_IO_DEVICE);
     const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.ct) : D;
     for (uint32_t d0 = 0; d0 < D; d0 += per) {
@@ -1176,7 +1218,8 @@ int pvw_wire_ct_deserialize(pvw_ctx* c, uint32_t slot0, uint32_t D, const uint8_
     require(in != nullptr, PVW_ERR_INVALID_PARAMETERS, "in is null");
     require(stride >= z.ct, PVW_ERR_INSUFFICIENT_DATA, fmt("expected %llu bytes per ciphertext, got %llu", (unsigned long long)z.ct, (unsigned long long)stride));
     require((uint64_t)slot0 + D <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + D, c->cap));
-    const size_t w1 = (size_t)L * k * ell, w2 = (size_t)L * nrows * ell;
+    const size_t w1 = c->c1_stride(), w2 = (size_t)L * nrows * ell;
+    c->c1_planes_invalidate(slot0, D);
     const bool host = !(flags & PVW_IO_DEVICE);
     const uint32_t per = host ? (uint32_t)std::max<uint64_t>(1, (uint64_t)c->upload_chunk_bytes / z.ct) : D;
     // Host input larger than one staging chunk: validate EVERY chunk before the first store write, so that a malformed blob
@@ -1411,7 +1454,7 @@ int pvw_shard_export(pvw_ctx* c, uint32_t world, pvw_shard_handle* out) {
     memset(&b, 0, sizeof(b));
     CUDA_CHECK(cudaIpcGetMemHandle(&b.c1, c->c1s.p));
     CUDA_CHECK(cudaIpcGetMemHandle(&b.flags, sh.flags));
-    b.cap = c->cap; b.w1 = (uint64_t)c->hp.L * c->hp.k * c->hp.ell; b.world = world; b.magic = SHARD_MAGIC;
+    b.cap = c->cap; b.w1 = c->c1_stride(); b.world = world; b.magic = SHARD_MAGIC;
     memset(out, 0, sizeof(*out));
     memcpy(out, &b, sizeof(b));
   });
@@ -1423,7 +1466,7 @@ int pvw_shard_connect(pvw_ctx* c, uint32_t world, uint32_t rank, const pvw_shard
     pvw_ctx::Shard& sh = c->sh;
     require(!sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_connect: already connected");
     require(sh.flags && sh.flags_world == world, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_connect: call pvw_shard_export(world) first");
-    const uint64_t w1 = (uint64_t)c->hp.L * c->hp.k * c->hp.ell;
+    const uint64_t w1 = c->c1_stride();
     sh.peer_c1.assign(world, nullptr); sh.peer_flags.assign(world, nullptr);
     sh.world = world; sh.rank = rank;
     sh.connected = true;                       // from here on a failure is cleaned up by shard_disconnect
@@ -1461,7 +1504,8 @@ static void shard_push_c1(pvw_ctx* c, uint32_t slot0, uint32_t count) {
     pvw_ctx::Shard& sh = c->sh;
     require(sh.connected, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_push_c1: not connected");
     require((uint64_t)slot0 + count <= c->cap, PVW_ERR_INDEX_OUT_OF_BOUNDS, fmt("ciphertext slots [%u, %u) exceed the reserved capacity %u", slot0, slot0 + count, c->cap));
-    const size_t w1 = (size_t)c->hp.L * c->hp.k * c->hp.ell;
+    const size_t w1 = c->c1_stride();   // residues and byte planes of a slot travel together
+    sh.batch_D = 0;                     // (set again by the encrypt call when the push came from PVW_ENC_PUSH_C1)
     const u64 seq = ++sh.push_seq;
     u64* stage = sh.flags + 2 * (size_t)sh.world;
     // the slice is final once everything queued on the compute stream so far (its c1 product) has run
@@ -1489,6 +1533,8 @@ int pvw_shard_wait_c1(pvw_ctx* c) {
     require(seq <= sh.push_seq, PVW_ERR_INVALID_PARAMETERS, "pvw_shard_wait_c1 without a matching pvw_shard_push_c1 on this rank");
     for (uint32_t r = 0; r < sh.world; r++)
       if (r != sh.rank) stream_wait_geq(c->stream, sh.flags + r, seq);
+    // the peers' slices of the batch have landed (in stream order): their byte planes are as current as this rank's own
+    for (uint32_t i = sh.batch_slot0; i < sh.batch_slot0 + sh.batch_D && i < c->c1p_valid.size(); i++) c->c1p_valid[i] = sh.batch_direct ? 1 : 0;
   });
 }
 

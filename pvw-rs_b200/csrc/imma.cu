@@ -638,7 +638,7 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
   // V byte planes: [plane][d][t][kp] (the same layout as the matrix side: a dealer's eight planes are 8 * kp contiguous bytes);
   // box = 128 bytes of DT dealers of all 8 planes t, t outermost -> rows (t, d) of the B tile in shared memory
-  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {8ull * kp, kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
+  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {a.Vb_dstride ? (cuuint64_t)a.Vb_dstride : 8ull * kp, kp, a.Vb_plane}, {KC, DT, 8, 1})) return false;
   // two whole B tiles resident when at least four ring stages still fit (k <= 256 at DT = 32), else two K-chunk slots
   const uint32_t b_tile = nkc * 8 * DT * KC;
   const uint32_t resident = (2 * b_tile + 4 * A_STAGE + 1024 + BAR_BYTES <= SMEM_LIMIT) ? 1u : 0u;
@@ -666,7 +666,7 @@ bool launch_pair(const ImmaArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   if (!make_map(&tmA, a.Mb, {kp, 8, a.rows, planes}, {kp, 8ull * kp, a.Mb_plane}, {KC, 1, RT, 1})) return false;
   // each CTA of the pair loads four of the eight byte planes t of the DT dealers
-  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {8ull * kp, kp, a.Vb_plane}, {KC, 32, 4, 1})) return false;
+  if (!make_map(&tmB, a.Vb, {kp, a.Vb_D, 8, planes}, {a.Vb_dstride ? (cuuint64_t)a.Vb_dstride : 8ull * kp, kp, a.Vb_plane}, {KC, 32, 4, 1})) return false;
   const uint32_t b_bytes = 2 * 4 * 32 * KC;
   const uint32_t nstages = std::min<uint32_t>(MAX_STAGES, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE);
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;

@@ -23,6 +23,8 @@ __host__ __device__ inline uint32_t imma_kp(uint32_t k) { return (k + 15u) & ~15
 struct ImmaArgs {
   const uint8_t* Mb; size_t Mb_plane;
   const uint8_t* Vb; size_t Vb_plane; uint32_t Vb_D, d_first;
+  size_t Vb_dstride;     // bytes between consecutive dealers of Vb: 0 = 8 * kp (a dense buffer); the ciphertext store's slot stride when
+                         // the planes are read in place (then Vb_plane = 8 * kp: a dealer's planes are contiguous)
   u64* O; size_t O_ls, O_ds, O_rs, O_cs;
   const u64* S; size_t S_ls, S_ds;
   const uint32_t* S_rowmap;

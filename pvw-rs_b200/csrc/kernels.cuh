@@ -53,6 +53,10 @@ struct DevTables {
 bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out,
                       size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false, bool pack_out = false, int planes = 0,
                       const u64* addend = nullptr);
+// c1 finisher of the tensor-core path (ntt.cu): slot d of the store = [packed residues u64[L][k][ell]][byte planes u8[L*ell][8][kp]];
+// addend = the slot-major product [d][limb][c][k].  false: shape not served (k % 4 != 0, ring degree above 16) -- nothing queued.
+bool launch_ntt_c1_finish(const DevTables& T, const void* coef, int cbytes, uint64_t count, uint32_t k, u64* c1, size_t slot_stride, const u64* addend,
+                          uint32_t kp, cudaStream_t st);
 // addend: out = value + addend[(vec*L + limb)*ell*inner + c*inner + j], the slot-major product of the tensor-core kernel
 // planes 1 / 2: write the byte planes of the tensor-core product (imma.cuh), matrix-row side (Mb) / dealer side (Vb); then
 // inner = k, vstride = kp (bytes per plane row), lstride = plane stride in bytes, out is a byte buffer

@@ -168,6 +168,72 @@ __global__ void __launch_bounds__(128) ntt_planes4_kernel(const void* __restrict
   }
 }
 
+// c1 = NTT(e1) + A r_hat, finished where both halves meet: the tensor-core product arrives slot-major (unit stride across the
+// threads), the result leaves twice -- as packed-halves residues into the ciphertext store (operand of the CUDA-core kernels,
+// source of downloads and of the wire format) and as byte planes right behind them in the same store slot (operand of the
+// tensor-core decryption, and what the multi-GPU exchange ships), so that decryption needs no conversion pass over c1.
+// Four polynomials (rows j of c1) per thread; k % 4 == 0.
+template <int ELL>
+__global__ void __launch_bounds__(128) ntt_c1_finish_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t k, u64* __restrict__ c1,
+                                                            size_t slot_stride, const u64* __restrict__ addend, uint32_t kp,
+                                                            const LimbConst* __restrict__ lcs, const u64* __restrict__ tw, const u64* __restrict__ tw_sh,
+                                                            const uint32_t L) {
+  __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
+  const uint32_t limb = blockIdx.x % L, blk = blockIdx.x / L;
+  if (threadIdx.x < ELL) {
+    s_tw[threadIdx.x] = tw[(size_t)limb * ELL + threadIdx.x];
+    s_tw_sh[threadIdx.x] = tw_sh[(size_t)limb * ELL + threadIdx.x];
+  }
+  __syncthreads();
+  const LimbConst lc = lcs[limb];
+  const uint64_t idx = 4 * ((uint64_t)blk * blockDim.x + threadIdx.x);
+  if (idx >= count) return;
+  const uint64_t d = idx / k, j = idx % k;
+  u64 a[4][ELL];
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    long long x[ELL];
+    load_small<ELL>(coef, cbytes, idx + p, x);
+#pragma unroll
+    for (int t = 0; t < ELL; t++) a[p][t] = reduce_i64(x[t], lc);
+    ntt_forward_lazy_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
+  }
+  const u64* ad = addend + ((size_t)d * L + limb) * ELL * k + j;
+#pragma unroll
+  for (int t = 0; t < ELL; t++) {
+    const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(ad + (size_t)t * k), v1 = *reinterpret_cast<const ulonglong2*>(ad + (size_t)t * k + 2);
+    a[0][t] = addmod(a[0][t], v0.x, lc.q); a[1][t] = addmod(a[1][t], v0.y, lc.q);
+    a[2][t] = addmod(a[2][t], v1.x, lc.q); a[3][t] = addmod(a[3][t], v1.y, lc.q);
+  }
+  u64* slot = c1 + d * slot_stride;
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(slot + (size_t)limb * k * ELL + (j + p) * ELL);
+#pragma unroll
+    for (int t = 0; t < ELL / 2; t++) dst[t] = make_ulonglong2(pack_halves(a[p][2 * t]), pack_halves(a[p][2 * t + 1]));
+  }
+  uint8_t* o8 = reinterpret_cast<uint8_t*>(slot + (size_t)L * k * ELL) + (size_t)limb * ELL * 8 * kp + j;   // planes [L*ELL][8][kp] behind the residues
+#pragma unroll
+  for (int t = 0; t < ELL; t++) {
+    const u64 v[4] = {a[0][t], a[1][t], a[2][t], a[3][t]};
+    uint32_t w[8];
+    bytes_4x8(v, w);
+#pragma unroll
+    for (int b8 = 0; b8 < 8; b8++) *reinterpret_cast<uint32_t*>(o8 + ((size_t)t * 8 + b8) * kp) = w[b8];
+  }
+}
+
+bool launch_ntt_c1_finish(const DevTables& T, const void* coef, int cbytes, uint64_t count, uint32_t k, u64* c1, size_t slot_stride, const u64* addend,
+                          uint32_t kp, cudaStream_t st) {
+  if (count == 0) return true;
+  if (k % 4 != 0 || (T.ell != 8 && T.ell != 16) || (cbytes != 1 && cbytes != 2 && cbytes != 4 && cbytes != 8)) return false;
+  const uint64_t blocks = ((count / 4 + 127) / 128) * T.L;
+  if (blocks >= (1ull << 31)) return false;
+  if (T.ell == 8) ntt_c1_finish_kernel<8><<<(unsigned)blocks, 128, 0, st>>>(coef, cbytes, count, k, c1, slot_stride, addend, kp, T.lc, T.tw, T.tw_sh, T.L);
+  else ntt_c1_finish_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(coef, cbytes, count, k, c1, slot_stride, addend, kp, T.lc, T.tw, T.tw_sh, T.L);
+  return true;
+}
+
 // Any power-of-two ring degree up to GEN_MAX_ELL (the reference accepts every power of two >= 8, parameters.rs:140-144; its
 // tests and examples use 8, 16, 32): the same transform with the coefficients in a per-thread local-memory array and run-time
 // loops.  Correct for every mode, not tuned -- the register-resident kernels above serve the parameter sets in use.

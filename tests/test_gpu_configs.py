@@ -58,7 +58,7 @@ def test_full_inner_dimension_matches_oracle(pkg, case, imma):
         assert (g2 == c2[d]).all(), f"c2 of dealer {d}"
     got = eng.decrypt_batch(np.arange(P.n), S.sk, D=D)
     assert (got == want).all()
-    used_tensor_cores = eng.profile()["expand"][1] >= 1    # the byte-plane conversion of c1 only runs on that path
+    used_tensor_cores = eng.profile()["imma_gemm"][1] >= 1
     assert used_tensor_cores == bool(imma)
     eng.set_option("profile", 0)
     # threshold-style subset (pvw_valid_dec.rs:161-210): a random "valid" subset of the dealers, in random order

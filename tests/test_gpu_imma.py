@@ -63,10 +63,10 @@ def test_encrypt_decrypt_match_oracle_and_imad(pkg, name, D):
     assert (got == want).all()
     if name != "L32b":
         assert (got == S.m.T).all()
-    # the expansion kernel ran: this really was the tensor-core path
+    # the tensor-core product ran
     eng.set_option("profile", 2)
     eng.decrypt_batch(np.arange(P.n), S.sk, dealer_slots=slots)
-    assert eng.profile()["expand"][1] >= 1
+    assert eng.profile()["imma_gemm"][1] >= 1
     eng.set_option("profile", 0)
     # permuted subsets of dealers and parties (examples/pvw_valid_dec.rs:198-210), identical on the IMAD kernel
     ds = np.array(sorted(set([D, 1, 1 + D // 2])), dtype=np.uint32)[::-1].copy()
@@ -131,9 +131,9 @@ def test_few_rows_take_the_cuda_core_kernel_by_default(pkg):
     eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)            # 24 rows x 40 dealers: tensor cores
     eng.set_option("profile", 2)
     one = eng.decrypt_batch(np.array([5], dtype=np.uint32), S.sk[5:6], D=D)
-    assert eng.profile()["expand"][1] == 0                # no byte-plane conversion: the CUDA-core kernel ran
+    assert eng.profile()["imma_gemm"][1] == 0             # the CUDA-core kernel ran
     many = eng.decrypt_batch(np.arange(P.n, dtype=np.uint32), S.sk, D=D)
-    assert eng.profile()["expand"][1] >= 1                # 24 parties: tensor cores
+    assert eng.profile()["imma_gemm"][1] >= 1             # 24 parties: tensor cores
     eng.set_option("profile", 0)
     want = S.co.decrypt(S.sk, c1, c2)
     assert (one == want[5:6]).all() and (many == want).all()

@@ -106,7 +106,7 @@ struct pvw_ctx {
   int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
   // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
-  int use_imma = 1, imma_pair = 0, imma_stages = 0;
+  int use_imma = 1, imma_pair = 0, imma_stages = 0, imma_epi_warps = 0, imma_fast_reduce = 1;
   int64_t imma_min_dealers = 8, imma_min_rows = 16, imma_chunk_dealers = 512;
   DevBuf As, Bs, Vx, shat_s, prod;
   bool As_valid = false, Bs_valid = false;
@@ -435,6 +435,8 @@ const uint8_t* planes_B(pvw_ctx* c) {
 void imma_launch(pvw_ctx* c, ImmaArgs g) {
   g.pair = c->imma_pair;
   g.stages = c->imma_stages;
+  g.epi_warps = c->imma_epi_warps;
+  g.fast_reduce = c->imma_fast_reduce;
   bool ok = true;
   launch(c, PVW_KERNEL_IMMA, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
   require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");
@@ -1565,6 +1567,8 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     std::string n(name);
     if (n == "imma") c->use_imma = value != 0;
     else if (n == "imma_pair") c->imma_pair = value != 0;
+    else if (n == "imma_fast_reduce") c->imma_fast_reduce = value != 0;
+    else if (n == "imma_epilogue_warps") { require(value == 0 || value == 8 || value == 16, PVW_ERR_INVALID_PARAMETERS, "imma_epilogue_warps must be 0 (default: 8), 8 or 16"); c->imma_epi_warps = (int)value; }
     else if (n == "planes_only") c->planes_only = value != 0;
     else if (n == "imma_stages") { require(value == 0 || (value >= 2 && value <= 10), PVW_ERR_INVALID_PARAMETERS, "imma_stages must be 0 (auto) or 2..10"); c->imma_stages = (int)value; }
     else if (n == "imma_min_dealers") { require(value >= 1, PVW_ERR_INVALID_PARAMETERS, "imma_min_dealers must be >= 1"); c->imma_min_dealers = value; }

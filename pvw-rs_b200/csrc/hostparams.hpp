@@ -287,6 +287,7 @@ struct HostParams {
       c.mu64 = (uint64_t)((((u128)1) << 64) / q);
       uint64_t r64 = (uint64_t)((((u128)1) << 64) % q);
       c.r128 = h_mulmod(r64, r64, q);
+      c.c124 = (uint64_t)((((u128)1) << 124) % q);
       c.ninv = h_powmod(ell, q - 2, q); c.ninv_sh = h_shoup(c.ninv, q);
       c.delta = delta.mod_small(q); c.delta_sh = h_shoup(c.delta, q);
       BigU qh = BigU::divmod_small(Q, q, nullptr);

@@ -112,14 +112,25 @@ IMMA_DEV u64 reduce160(const uint32_t (&w)[5], const LimbConst& lc) {
   const u64 h = reduce128(reduce64((u64)w[4], lc), hi, lc);
   return reduce128(h, lo, lc);
 }
+// The same for q >= 2^61 and W < 2^136 (k <= 4096), one Barrett step instead of two and a half: the bits above 2^124 (at most 12)
+// are folded down with 2^124 mod q, which leaves t < 2^124 + 2^74, and t / q < 2^64 is what reduce128's quotient estimate needs.
+IMMA_DEV u64 reduce160_q62(const uint32_t (&w)[5], const LimbConst& lc) {
+  const uint32_t h = (w[3] >> 28) | (w[4] << 4);
+  const u64 lo = ((u64)w[1] << 32) | w[0], hi = ((u64)(w[3] & 0x0fffffffu) << 32) | w[2];
+  const u64 p0 = (u64)h * (uint32_t)lc.c124, p1 = (u64)h * (uint32_t)(lc.c124 >> 32);      // h * c124 = p0 + (p1 << 32) < 2^74
+  const u64 a = lo + p0, b = a + (p1 << 32);
+  const u64 t_hi = hi + (p1 >> 32) + (a < lo) + (b < a);
+  return reduce128(t_hi, b, lc);
+}
 IMMA_DEV void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 
 // DT dealers per tile (32: 15 * 32 = 480 of the 512 TMEM columns)
-template <uint32_t DT, bool RES>
-__global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+// EW epilogue warps (8 or 16): EW / 4 warps share a TMEM lane group and split the DT dealers
+template <uint32_t DT, bool RES, uint32_t EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) imma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const ImmaArgs g, const uint32_t nstages) {
   constexpr uint32_t resident = RES ? 1u : 0u;
   // resident != 0: a B slot holds the whole B tile (all K-chunks) and the loop runs plane-major (s outer, K-chunk inner): one B
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
     for (uint32_t s = 0; s < nstages; s++) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (uint32_t b = 0; b < 2; b++) { mbar_init(b_full(b), 1); mbar_init(b_empty(b), 1); }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 32 * EPI_WARPS);                               // every epilogue thread arrives
+    mbar_init(tmem_empty, 32 * EW);                                      // every epilogue thread arrives
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -256,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
       __syncwarp();
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31; thread = one row; the two warps of a lane group split the dealers
+    // epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31; thread = one row; the EW / 4 warps of a lane group split the dealers
     const uint32_t lg = warp & 3, half = (warp - 2) >> 2;
     uint32_t i = 0;
     for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, i++) {
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
         continue;
       }
       // phase 1 (TMEM is busy): this thread's DT/2 dealers, four at a time -- 15 diagonal sums each -> one 160-bit integer
-      constexpr uint32_t ND = DT / 2;
+      constexpr uint32_t ND = DT / (EW / 4);
       uint32_t W[ND][5];
 #pragma unroll
       for (uint32_t q4 = 0; q4 < ND / 4; q4++) {
@@ -294,11 +305,13 @@ __global__ void __launch_bounds__(THREADS, 1) imma_gemm_kernel(const __grid_cons
       tc_fence_before();
       mbar_arrive(tmem_empty);                                           // TMEM goes back to the MMA warp: the next tile starts
       // phase 2 (overlaps the next tile's MMAs): reduce and store
+      const bool q62 = (lc.q >> 61) != 0 && g.fast_reduce;
 #pragma unroll
       for (uint32_t dd = 0; dd < ND; dd++) {
         const uint32_t d = d0 + half * ND + dd;
         if (row_ok && d < g.D) {
-          u64 r = reduce160(W[dd], lc);
+          // (mode -1, timing probe: the read-out and the stores without the reduction)
+          u64 r = g.mode == -1 ? ((u64)(W[dd][4] ^ W[dd][3] ^ W[dd][2]) << 32 | (W[dd][1] ^ W[dd][0])) : q62 ? reduce160_q62(W[dd], lc) : reduce160(W[dd], lc);
           u64* o = g.O + (size_t)d * g.O_ds + o_row;
           if (g.mode == 0) r = addmod(r, *o, lc.q);
           else if (g.mode == 1) {
@@ -646,7 +659,12 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   const uint32_t cap = a.stages >= 2 ? std::min<uint32_t>((uint32_t)a.stages, MAX_STAGES) : MAX_STAGES;
   const uint32_t nstages = std::max(2u, std::min<uint32_t>(cap, (SMEM_LIMIT - 1024 - BAR_BYTES - b_bytes) / A_STAGE));
   const uint32_t smem = b_bytes + nstages * A_STAGE + 1024 + BAR_BYTES;
-  auto kern = resident ? imma_gemm_kernel<DT, true> : imma_gemm_kernel<DT, false>;
+  // 8 epilogue warps unless asked otherwise.  Measured (c2-sized product, one box): 8 warps + the general reduction 1.989 ms, 16 warps
+  // 1.809 (the reductions of a tile are latency bound with two warps per scheduler); with the one-step reduction 1.732 / 1.759 -- the
+  // read-out itself is slower with 16 warps (1.664 against 1.564 ms without any reduction), so 8 stays the default
+  const bool wide = a.epi_warps == 16;
+  auto kern = wide ? (resident ? imma_gemm_kernel<DT, true, 16> : imma_gemm_kernel<DT, false, 16>)
+                   : (resident ? imma_gemm_kernel<DT, true, 8> : imma_gemm_kernel<DT, false, 8>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return false;  // per device
   // the whole 228 KB as shared memory whatever this launch asks for: with a shorter ring (ImmaArgs::stages) the rest stays free for
   // the CTAs of kernels on other streams (the driver would otherwise pick the smallest carve-out that fits this kernel alone)
@@ -655,7 +673,7 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   const uint64_t tiles = (uint64_t)((a.rows + RT - 1) / RT) * ((a.D + DT - 1) / DT) * planes;
   if (tiles >= (1ull << 32)) return false;
-  kern<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), THREADS, smem, st>>>(tmA, tmB, a, nstages);
+  kern<<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)std::max(sms, 1)), 64 + 32 * (wide ? 16 : 8), smem, st>>>(tmA, tmB, a, nstages);
   return true;
 }
 

@@ -23,7 +23,9 @@ struct LimbConst {
   u64 delta_sh;
   u64 qhinv;    // (Q/q)^-1 mod q          (CRT lift, fhe-math RnsContext)
   u64 qhinv_sh;
-  u64 pad;
+  u64 pad;      // always 0 (mac.cu)
+  u64 c124;     // 2^124 mod q   (one-step reduction of the tensor-core product's 160-bit sums, imma.cu)
+  u64 pad2;
 };
 
 #define PVW_DEV __device__ __forceinline__

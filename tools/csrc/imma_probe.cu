@@ -4,7 +4,7 @@
 // A 64-bit operand is its 8 little-endian bytes, so  M*V = sum_u 2^(8u) sum_{s+t=u} m_s v_t: byte-plane GEMMs accumulated on
 // overlapping windows of the TMEM accumulator (imma.cu); the epilogue recombines the 15 diagonal sums of every output.
 //
-// usage: imma_probe [rows] [D] [k] [planes] [reps] [ell] [mode] [dt]     (rows % 256 == 0, D % 16 == 0, k % 16 == 0)
+// usage: imma_probe [rows] [D] [k] [planes] [reps] [ell] [mode] [dt] [epilogue warps]     (rows % 256 == 0, D % 16 == 0, k % 16 == 0)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -45,6 +45,7 @@ static LimbConst make_lc(u64 q) {
   c.mu_hi = (u64)(hi >> 64); c.mu_lo = (u64)hi;
   c.mu64 = (u64)(((one << 64)) / q);
   c.r128 = (u64)((((~(unsigned __int128)0) % q) + 1) % q);
+  c.c124 = (u64)((one << 124) % q);
   return c;
 }
 
@@ -54,6 +55,8 @@ int main(int argc, char** argv) {
   const uint32_t ell = argc > 6 ? atoi(argv[6]) : 1;     // > 1: the library's output layout O[d][limb][row][c] (timing only)
   const int mode = argc > 7 ? atoi(argv[7]) : 2;
   const int dt = argc > 8 ? atoi(argv[8]) : 0;           // 16: half-width tile (N = 128 per MMA)
+  const int ew = argc > 9 ? atoi(argv[9]) : 0;           // 16: four epilogue warps per TMEM lane group; default 8
+  const int fr = argc > 10 ? atoi(argv[10]) : 1;         // 0: the general reduction of the 160-bit sums
   const u64 q = 0x3ffffffffffffdc1ull;
   const LimbConst lc = make_lc(q);
   u64 *M, *V, *O, *Oref;
@@ -86,7 +89,7 @@ int main(int argc, char** argv) {
   a.Mb = Mb; a.Mb_plane = (size_t)rows * 8 * kp; a.rows = rows; a.k = k; a.L = planes; a.ell = 1;   // plane = limb (ell = 1 view)
   a.Vb = Vb; a.Vb_plane = (size_t)D * 8 * kp; a.Vb_D = D; a.d_first = 0; a.D = D;
   a.O = O; a.O_ds = rows; a.O_ls = (size_t)D * rows; a.O_rs = 1; a.O_cs = 0;
-  a.lc = dlc; a.mode = 2; a.dt = dt == 2 ? 0 : dt; a.pair = dt == 2 ? 1 : 0;   // dt == 2: the two-SM kernel
+  a.lc = dlc; a.mode = 2; a.epi_warps = ew; a.fast_reduce = fr; a.dt = dt == 2 ? 0 : dt; a.pair = dt == 2 ? 1 : 0;   // dt == 2: the two-SM kernel
   ImmaArgs b = a;                                                        // timing variant
   if (ell > 1) { b.L = planes / ell; b.ell = ell; b.O_ds = (size_t)b.L * rows * ell; b.O_ls = (size_t)rows * ell; b.O_rs = ell; b.O_cs = 1; }
   b.mode = mode;

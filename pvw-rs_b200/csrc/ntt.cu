@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const void* __restrict__
 // four goes out as one 4-byte word and a warp stores 128 contiguous bytes per instruction.  (The first version stored single
 // bytes: 64 store instructions of 32 bytes per polynomial and limb.)  SIDE 3: matrix-row side, SIDE 4: dealer side (imma.cuh).
 template <int ELL, int SIDE>
-__global__ void __launch_bounds__(128) ntt_planes4_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t inner, uint8_t* __restrict__ out,
+__global__ void __launch_bounds__(128, ELL == 8 ? 5 : 1) ntt_planes4_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t inner, uint8_t* __restrict__ out,
                                                           size_t kp, size_t pstride, const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
                                                           const u64* __restrict__ tw_sh, const uint32_t L) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
@@ -145,26 +145,60 @@ __global__ void __launch_bounds__(128) ntt_planes4_kernel(const void* __restrict
   const LimbConst lc = lcs[limb];
   const uint64_t idx = 4 * ((uint64_t)blk * blockDim.x + threadIdx.x);   // first of this thread's four polynomials (same row: inner % 4 == 0)
   if (idx >= count) return;
-  u64 a[4][ELL];
-#pragma unroll
-  for (int p = 0; p < 4; p++) {
-    long long x[ELL];
-    load_small<ELL>(coef, cbytes, idx + p, x);
-#pragma unroll
-    for (int t = 0; t < ELL; t++) a[p][t] = reduce_i64(x[t], lc);
-    ntt_forward_lazy_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
-  }
   const uint64_t r = idx / inner, j = idx % inner;
   const size_t first = (size_t)r * 8 * kp + j;      // SIDE 3 and 4 share the layout: row / dealer r, byte plane b, polynomial j
   const size_t step = kp;
   uint8_t* o8 = out + (size_t)limb * ELL * pstride + first;
+  if constexpr (ELL == 8) {
+    // The four transforms run in a ROLLED loop (one copy of the butterflies: the straight-line form was 4 100 instructions executed
+    // once per warp and a fifth of its stall cycles waited for instruction fetch); byte b of slot t of polynomial p is dropped into
+    // byte p of word w[t][b] with one PRMT whose selector depends on p only.
+    uint32_t w[ELL][8];
 #pragma unroll
-  for (int t = 0; t < ELL; t++) {
-    const u64 v[4] = {a[0][t], a[1][t], a[2][t], a[3][t]};
-    uint32_t w[8];
-    bytes_4x8(v, w);
+    for (int t = 0; t < ELL; t++)
 #pragma unroll
-    for (int b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(o8 + (size_t)t * pstride + (size_t)b * step) = w[b];
+      for (int b = 0; b < 8; b++) w[t][b] = 0;
+#pragma unroll 1
+    for (int p = 0; p < 4; p++) {
+      u64 a[ELL];
+      long long x[ELL];
+      load_small<ELL>(coef, cbytes, idx + p, x);
+#pragma unroll
+      for (int t = 0; t < ELL; t++) a[t] = reduce_i64(x[t], lc);
+      ntt_forward_lazy_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
+      const uint32_t keep = 0x3210u & ~(0xFu << (4 * p));                  // every byte of w but byte p
+      uint32_t sel[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) sel[b] = keep | ((4u + b) << (4 * p));   // byte p <- byte b of the source word
+#pragma unroll
+      for (int t = 0; t < ELL; t++) {
+        const uint32_t lo = (uint32_t)a[t], hi = (uint32_t)(a[t] >> 32);
+#pragma unroll
+        for (int b = 0; b < 4; b++) { w[t][b] = __byte_perm(w[t][b], lo, sel[b]); w[t][4 + b] = __byte_perm(w[t][4 + b], hi, sel[b]); }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < ELL; t++)
+#pragma unroll
+      for (int b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(o8 + (size_t)t * pstride + (size_t)b * step) = w[t][b];
+  } else {   // 8 * ELL output words do not fit the registers next to a transform: straight-line, four transforms side by side
+    u64 a[4][ELL];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      long long x[ELL];
+      load_small<ELL>(coef, cbytes, idx + p, x);
+#pragma unroll
+      for (int t = 0; t < ELL; t++) a[p][t] = reduce_i64(x[t], lc);
+      ntt_forward_lazy_regs<ELL>(a[p], s_tw, s_tw_sh, lc.q);
+    }
+#pragma unroll
+    for (int t = 0; t < ELL; t++) {
+      const u64 v[4] = {a[0][t], a[1][t], a[2][t], a[3][t]};
+      uint32_t w[8];
+      bytes_4x8(v, w);
+#pragma unroll
+      for (int b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(o8 + (size_t)t * pstride + (size_t)b * step) = w[b];
+    }
   }
 }
 

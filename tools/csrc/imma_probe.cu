@@ -36,6 +36,14 @@ __global__ void ref_kernel(const u64* M, const u64* V, u64* O, uint32_t rows, ui
   O[((size_t)plane * D + d) * rows + row] = acc;
 }
 
+// co-residency probe: a CUDA-core kernel (Shoup multiplies in registers, 128 threads, few registers, no shared memory) to run on a
+// second stream beside the persistent tensor-core kernel
+__global__ void __launch_bounds__(128) busy_kernel(u64* out, uint32_t iters, u64 q) {
+  u64 a = threadIdx.x + blockIdx.x * 131ull + 3, w = 0x123456789abcdefull % q, w_sh = (u64)(((unsigned __int128)w << 64) / q);
+  for (uint32_t i = 0; i < iters; i++) a = mulmod_shoup(a, w, w_sh, q) + i;
+  if (a == 0x5555) out[0] = a;
+}
+
 static LimbConst make_lc(u64 q) {
   LimbConst c{};
   c.q = q;
@@ -129,6 +137,34 @@ int main(int argc, char** argv) {
     const double macs = (double)rows * D * k * planes * reps;
     if (pass == 0) printf("imma_gemm: %.3f ms per launch, %.3e 62-bit MAC/s, %.1f int8 TOPS\n", ms / reps, macs / (ms * 1e-3), macs * 64 * 2 / (ms * 1e-3) / 1e12);
     else printf("imma_planes_v: %.3f ms per launch (%.1f GB/s written)\n", ms / reps, (double)planes * D * 8 * kp * reps / (ms * 1e-3) / 1e9);
+  }
+  // co-residency: imma_probe ... [stages] [co-resident CTAs' carve-out: 0 default, 1 max shared]
+  if (argc > 11) {
+    const int stages = atoi(argv[11]), carve = argc > 12 ? atoi(argv[12]) : 0;
+    b.stages = stages;
+    cudaStream_t s1, s2;
+    CK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    if (carve) CK(cudaFuncSetAttribute(busy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const uint32_t iters = 20000, grid = 148 * 16;
+    auto run = [&](bool gemm, bool busy) {
+      float best = 1e9f;
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0, s1));
+        CK(cudaStreamWaitEvent(s2, e0, 0));
+        if (gemm) launch_imma_gemm(b, s1);
+        if (busy) busy_kernel<<<grid, 128, 0, s2>>>(O, iters, q);
+        cudaEvent_t j; CK(cudaEventCreate(&j)); CK(cudaEventRecord(j, s2)); CK(cudaStreamWaitEvent(s1, j, 0));
+        CK(cudaEventRecord(e1, s1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best;
+        CK(cudaEventDestroy(j));
+      }
+      return best;
+    };
+    const float tg = run(true, false), tb = run(false, true), tgb = run(true, true);
+    printf("co-residency (ring stages %d, carve-out %d): imma %.3f ms, busy %.3f ms, both %.3f ms (sum %.3f)\n", stages, carve, tg, tb, tgb, tg + tb);
   }
   return bad ? 2 : 0;
 }

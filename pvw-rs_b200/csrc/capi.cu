@@ -436,7 +436,7 @@ void imma_launch(pvw_ctx* c, ImmaArgs g) {
   g.pair = c->imma_pair;
   g.stages = c->imma_stages;
   g.epi_warps = c->imma_epi_warps;
-  g.fast_reduce = c->imma_fast_reduce;
+  g.fast_reduce = c->imma_fast_reduce && *std::min_element(c->hp.moduli.begin(), c->hp.moduli.end()) >= (1ull << 61);
   bool ok = true;
   launch(c, PVW_KERNEL_IMMA, (double)g.D * g.rows * (g.k + 1.0) * g.L * g.ell * 8.0, [&] { ok = launch_imma_gemm(g, c->stream); });
   require(ok, PVW_ERR_INTERNAL, "tensor-map creation failed for the tensor-core product");

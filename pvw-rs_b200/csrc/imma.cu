@@ -129,7 +129,10 @@ IMMA_DEV void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 
 // DT dealers per tile (32: 15 * 32 = 480 of the 512 TMEM columns)
 // EW epilogue warps (8 or 16): EW / 4 warps share a TMEM lane group and split the DT dealers
-template <uint32_t DT, bool RES, uint32_t EW>
+// Q62: every modulus of the launch is >= 2^61 (decided on the host): the one-step reduction.  A template parameter, not a per-tile
+// branch: with both reductions in the unrolled store loop the epilogue code grew by a third and the general path ran 17 % slower
+// (instruction fetch), which cancelled what the shorter reduction gains.
+template <uint32_t DT, bool RES, uint32_t EW, bool Q62>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) imma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const ImmaArgs g, const uint32_t nstages) {
   constexpr uint32_t resident = RES ? 1u : 0u;
@@ -305,13 +308,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) imma_gemm_kernel(const __grid
       tc_fence_before();
       mbar_arrive(tmem_empty);                                           // TMEM goes back to the MMA warp: the next tile starts
       // phase 2 (overlaps the next tile's MMAs): reduce and store
-      const bool q62 = (lc.q >> 61) != 0 && g.fast_reduce;
 #pragma unroll
       for (uint32_t dd = 0; dd < ND; dd++) {
         const uint32_t d = d0 + half * ND + dd;
         if (row_ok && d < g.D) {
           // (mode -1, timing probe: the read-out and the stores without the reduction)
-          u64 r = g.mode == -1 ? ((u64)(W[dd][4] ^ W[dd][3] ^ W[dd][2]) << 32 | (W[dd][1] ^ W[dd][0])) : q62 ? reduce160_q62(W[dd], lc) : reduce160(W[dd], lc);
+          u64 r = g.mode == -1 ? ((u64)(W[dd][4] ^ W[dd][3] ^ W[dd][2]) << 32 | (W[dd][1] ^ W[dd][0])) : Q62 ? reduce160_q62(W[dd], lc) : reduce160(W[dd], lc);
           u64* o = g.O + (size_t)d * g.O_ds + o_row;
           if (g.mode == 0) r = addmod(r, *o, lc.q);
           else if (g.mode == 1) {
@@ -663,8 +665,12 @@ bool launch_dt(const ImmaArgs& a, cudaStream_t st) {
   // 1.809 (the reductions of a tile are latency bound with two warps per scheduler); with the one-step reduction 1.732 / 1.759 -- the
   // read-out itself is slower with 16 warps (1.664 against 1.564 ms without any reduction), so 8 stays the default
   const bool wide = a.epi_warps == 16;
-  auto kern = wide ? (resident ? imma_gemm_kernel<DT, true, 16> : imma_gemm_kernel<DT, false, 16>)
-                   : (resident ? imma_gemm_kernel<DT, true, 8> : imma_gemm_kernel<DT, false, 8>);
+  auto pick = [&](auto q62) {
+    constexpr bool Q = decltype(q62)::value;
+    return wide ? (resident ? imma_gemm_kernel<DT, true, 16, Q> : imma_gemm_kernel<DT, false, 16, Q>)
+                : (resident ? imma_gemm_kernel<DT, true, 8, Q> : imma_gemm_kernel<DT, false, 8, Q>);
+  };
+  auto kern = a.fast_reduce ? pick(std::true_type{}) : pick(std::false_type{});
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) return false;  // per device
   // the whole 228 KB as shared memory whatever this launch asks for: with a shorter ring (ImmaArgs::stages) the rest stays free for
   // the CTAs of kernels on other streams (the driver would otherwise pick the smallest carve-out that fits this kernel alone)

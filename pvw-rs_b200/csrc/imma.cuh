@@ -35,7 +35,7 @@ struct ImmaArgs {
   int pair;              // 1: the two-SM form (tcgen05.mma.cta_group::2 on CTA pairs) -- measured, not faster; default 0
   int stages;            // depth of the shared-memory ring of M stages: 0 = as deep as fits (the kernel then owns the SM's shared memory);
                          // 2..10 = at most that many, which leaves shared memory for kernels of other streams to co-reside
-  int fast_reduce;       // 1: moduli >= 2^61 take the one-step reduction of the 160-bit sums (set by the library; 0 = always the general one)
+  int fast_reduce;       // 1: EVERY modulus in lc[0..L) is >= 2^61 (the caller checks): the one-step reduction of the 160-bit sums
   int epi_warps;         // epilogue warps per CTA: 0 / 8 = two per TMEM lane group (default), 16 = four (measured, not faster: imma.cu)
   int dt;                // dealers per tile: 0 = 32 (default), 16 = the half-width tile (probe: tools/csrc/imma_probe.cu)
 };

@@ -106,6 +106,8 @@ struct pvw_ctx {
   int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
   // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
+  int use_tern = 1;
+  const u64* tern_dev = nullptr;
   int use_imma = 1, imma_pair = 0, imma_stages = 0, imma_epi_warps = 0, imma_fast_reduce = 1;
   int64_t imma_min_dealers = 8, imma_min_rows = 16, imma_chunk_dealers = 512;
   DevBuf As, Bs, Vx, shat_s, prod;
@@ -171,7 +173,7 @@ void upload_tables(pvw_ctx* c) {
   size_t o_dM = put(dM.data(), dM.size()), o_d2D = put(d2D.data(), d2D.size());
   auto putv = [&](const std::vector<uint64_t>& v) { pad2(); return v.empty() ? blob.size() : put(v.data(), v.size()); };
   size_t o_shc = putv(hp.sh_c), o_shcs = putv(hp.sh_c_sh), o_shq = putv(hp.sh_qhat), o_shQ = putv(hp.sh_Q), o_shh = putv(hp.sh_halfQ),
-         o_shv = putv(hp.sh_v), o_shvs = putv(hp.sh_v_sh), o_shr = putv(hp.sh_r), o_shrs = putv(hp.sh_r_sh);
+         o_shv = putv(hp.sh_v), o_shvs = putv(hp.sh_v_sh), o_shr = putv(hp.sh_r), o_shrs = putv(hp.sh_r_sh), o_tern = putv(hp.tern);
   c->tables.ensure(blob.size() * 8);
   CUDA_CHECK(cudaMemcpy(c->tables.p, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
   const u64* base = c->tables.as<u64>();
@@ -188,6 +190,8 @@ void upload_tables(pvw_ctx* c) {
   T.tail_impl = 1;
   T.sh_c = base + o_shc; T.sh_c_sh = base + o_shcs; T.sh_qhat = base + o_shq; T.sh_Q = base + o_shQ; T.sh_halfQ = base + o_shh;
   T.sh_v = base + o_shv; T.sh_v_sh = base + o_shvs; T.sh_r = base + o_shr; T.sh_r_sh = base + o_shrs;
+  c->tern_dev = hp.tern.empty() ? nullptr : base + o_tern;
+  T.tern = c->use_tern ? c->tern_dev : nullptr;
   T.shortL = hp.shortL; T.shortSW = hp.shortSW; T.lift_fast = hp.shortL > 0 ? 1 : 0;
   FusedConst& F = c->F;
   memset(&F, 0, sizeof(F));
@@ -1567,6 +1571,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     std::string n(name);
     if (n == "imma") c->use_imma = value != 0;
     else if (n == "imma_pair") c->imma_pair = value != 0;
+    else if (n == "ternary_tables") { c->use_tern = value != 0; c->T.tern = c->use_tern ? c->tern_dev : nullptr; }
     else if (n == "imma_fast_reduce") c->imma_fast_reduce = value != 0;
     else if (n == "imma_epilogue_warps") { require(value == 0 || value == 8 || value == 16, PVW_ERR_INVALID_PARAMETERS, "imma_epilogue_warps must be 0 (default: 8), 8 or 16"); c->imma_epi_warps = (int)value; }
     else if (n == "planes_only") c->planes_only = value != 0;

@@ -41,6 +41,7 @@ struct DevTables {
   uint32_t shortL, shortSW;
   int lift_fast;  // 1 = try the short lift first
   int tail_impl;  // 1 = register-resident decode tail where a specialisation exists, 0 = generic kernel
+  const u64* tern;  // ring degree 8: [L][2][81][8] transforms of the ternary half-polynomials (hostparams.hpp), else nullptr
 };
 
 // ---- ntt.cu -------------------------------------------------------------------------------------------------

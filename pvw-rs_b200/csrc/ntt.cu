@@ -131,16 +131,22 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const void* __restrict__
 // Byte planes of NTT(small polynomial), FOUR consecutive polynomials j per thread (k % 4 == 0): every (slot, byte index) of the
 // four goes out as one 4-byte word and a warp stores 128 contiguous bytes per instruction.  (The first version stored single
 // bytes: 64 store instructions of 32 bytes per polynomial and limb.)  SIDE 3: matrix-row side, SIDE 4: dealer side (imma.cuh).
+constexpr uint32_t TERN_PITCH = 10;
 template <int ELL, int SIDE>
 __global__ void __launch_bounds__(128, ELL == 8 ? 5 : 1) ntt_planes4_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t inner, uint8_t* __restrict__ out,
                                                           size_t kp, size_t pstride, const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
-                                                          const u64* __restrict__ tw_sh, const uint32_t L) {
+                                                          const u64* __restrict__ tw_sh, const uint32_t L, const u64* __restrict__ tern) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
+  // tern != nullptr (one-byte inputs, ring degree 8): this limb's 2 x 81 transforms of ternary half-polynomials, rows TERN_PITCH words
+  // apart (80 bytes: eight consecutive rows start in eight different 16-byte bank groups)
+  extern __shared__ __align__(16) u64 s_tern[];
   const uint32_t limb = blockIdx.x % L, blk = blockIdx.x / L;
   if (threadIdx.x < ELL) {
     s_tw[threadIdx.x] = tw[(size_t)limb * ELL + threadIdx.x];
     s_tw_sh[threadIdx.x] = tw_sh[(size_t)limb * ELL + threadIdx.x];
   }
+  if (ELL == 8 && tern != nullptr)
+    for (uint32_t i = threadIdx.x; i < 162 * 8; i += blockDim.x) s_tern[(i >> 3) * TERN_PITCH + (i & 7)] = tern[(size_t)limb * 162 * 8 + i];
   __syncthreads();
   const LimbConst lc = lcs[limb];
   const uint64_t idx = 4 * ((uint64_t)blk * blockDim.x + threadIdx.x);   // first of this thread's four polynomials (same row: inner % 4 == 0)
@@ -161,11 +167,53 @@ __global__ void __launch_bounds__(128, ELL == 8 ? 5 : 1) ntt_planes4_kernel(cons
 #pragma unroll 1
     for (int p = 0; p < 4; p++) {
       u64 a[ELL];
+      bool done = false;
       long long x[ELL];
-      load_small<ELL>(coef, cbytes, idx + p, x);
+      if (tern == nullptr || cbytes != 1) load_small<ELL>(coef, cbytes, idx + p, x);
+      if (tern != nullptr) {
+        // Secrets and encryption randomness are ternary at the reference's default variance (CBD, parameters.rs:166,251-254): the
+        // transform is linear, so NTT(x) = T_lo[x_0..x_3] + T_hi[x_4..x_7] -- two table rows and eight modular additions instead
+        // of twelve butterflies.  Any other coefficient takes the butterflies below (same canonical result).
+        uint32_t ilo = 0, ihi = 0;
+        bool ternary;
+        if (cbytes == 1) {
+          const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const signed char*>(coef) + (idx + p) * 8);
+          const uint32_t t0 = ((v.x & 0x7f7f7f7fu) + 0x01010101u) ^ (v.x & 0x80808080u);    // x_i + 1 in every byte (no carries across bytes)
+          const uint32_t t1 = ((v.y & 0x7f7f7f7fu) + 0x01010101u) ^ (v.y & 0x80808080u);
+          ternary = (((t0 | t1) & 0xfcfcfcfcu) | (((t0 & (t0 >> 1)) | (t1 & (t1 >> 1))) & 0x01010101u)) == 0;   // every byte in {0, 1, 2}
+          ilo = __dp4a(t0, 0x1b090301u, 0u);
+          ihi = __dp4a(t1, 0x1b090301u, 0u);
+          if (!ternary) load_small<ELL>(coef, cbytes, idx + p, x);
+        } else {
+          u64 worst = 0;
 #pragma unroll
-      for (int t = 0; t < ELL; t++) a[t] = reduce_i64(x[t], lc);
-      ntt_forward_lazy_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
+          for (int t = 0; t < 4; t++) {
+            const u64 u0 = (u64)x[t] + 1, u1 = (u64)x[4 + t] + 1;
+            worst |= u0 | u1;                                                               // {0, 1, 2} or'ed together stay below 4
+            ilo = ilo + (uint32_t)u0 * (t == 0 ? 1u : t == 1 ? 3u : t == 2 ? 9u : 27u);
+            ihi = ihi + (uint32_t)u1 * (t == 0 ? 1u : t == 1 ? 3u : t == 2 ? 9u : 27u);
+          }
+          ternary = worst < 4;
+#pragma unroll
+          for (int t = 0; t < ELL; t++) ternary = ternary && (u64)x[t] + 1 != 3;
+        }
+        if (ternary) {
+          const ulonglong2* lo = reinterpret_cast<const ulonglong2*>(s_tern + (size_t)ilo * TERN_PITCH);
+          const ulonglong2* hi = reinterpret_cast<const ulonglong2*>(s_tern + (size_t)(81u + ihi) * TERN_PITCH);
+#pragma unroll
+          for (int t = 0; t < ELL / 2; t++) {
+            const ulonglong2 l = lo[t], h = hi[t];
+            a[2 * t] = addmod(l.x, h.x, lc.q);
+            a[2 * t + 1] = addmod(l.y, h.y, lc.q);
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int t = 0; t < ELL; t++) a[t] = reduce_i64(x[t], lc);
+        ntt_forward_lazy_regs<ELL>(a, s_tw, s_tw_sh, lc.q);
+      }
       const uint32_t keep = 0x3210u & ~(0xFu << (4 * p));                  // every byte of w but byte p
       uint32_t sel[4];
 #pragma unroll
@@ -337,11 +385,14 @@ bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u6
   // byte planes, four polynomials per thread: needs whole groups of four inside a row and registers for 4 * ell residues
   const bool four = (mode == 3 || mode == 4) && inner % 4 == 0 && T.ell <= 16 && m == nullptr;
   const unsigned grid4 = (unsigned)(((count / 4 + 127) / 128) * T.L);
+  // ring degree 8: the table path for ternary polynomials (secrets, randomness); T.tern is null when switched off
+  const u64* tern = (four && T.ell == 8) ? T.tern : nullptr;
+  const size_t tern_smem = tern ? (size_t)162 * TERN_PITCH * 8 : 0;
 #define PVW_NTT_ARGS coef, cbytes, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L
 #define PVW_NTT_CASE(E)                                                                                                          \
   case E:                                                                                                                        \
-    if (four && mode == 3) ntt_planes4_kernel<(E <= 16 ? E : 8), 3><<<grid4, 128, 0, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L); \
-    else if (four) ntt_planes4_kernel<(E <= 16 ? E : 8), 4><<<grid4, 128, 0, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L);        \
+    if (four && mode == 3) ntt_planes4_kernel<(E <= 16 ? E : 8), 3><<<grid4, 128, tern_smem, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L, tern); \
+    else if (four) ntt_planes4_kernel<(E <= 16 ? E : 8), 4><<<grid4, 128, tern_smem, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L, tern);        \
     else if (mode == 5) ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
     else if (mode == 3) ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
     else if (mode == 4) ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \

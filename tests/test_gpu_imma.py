@@ -174,3 +174,34 @@ def test_planes_only_keeps_one_copy_of_the_public_key(pkg):
     eng.pk_upload_rows(3, S.B[3:4])
     eng.encrypt_batch(0, S.m, S.r, S.e1, S.e2)
     assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=D) == want).all()
+
+
+@pytest.mark.parametrize("name,stype", [("EX", np.int8), ("EX", np.int64), ("P128s", np.int8), ("P128s", np.int64)])
+def test_ternary_tables_and_butterflies_agree(pkg, name, stype):
+    """Ring degree 8: polynomials with coefficients in {-1, 0, 1} are transformed by table lookup (ntt.cu), any other polynomial by
+    the butterflies -- mixed in one call here, for every input element size, against the oracle and against the option switched off."""
+    P = SETS[name]()
+    D = 9
+    S = System(P, D, "u63")
+    rng = np.random.default_rng(77)
+    sk = S.sk.copy()
+    sk[::2, ::3, 5] = 2                                     # every third polynomial of every other party leaves the ternary set
+    sk[1, 1, :] = [-128, 127, -2, 2, 3, -3, 0, 1]           # the edges of the one-byte range
+    sk[3 % P.n] = rng.integers(-1, 2, size=sk[0].shape)     # a fully ternary key that is not the seeded one
+    r = S.r.copy()
+    r[0, 0, :] = [1, -1, 0, 2, -2, 1, 0, -1]
+    c1, c2 = S.co.encrypt(S.A, S.B, S.m, r, S.e1, S.e2)
+    want = S.co.decrypt(sk, c1, c2)                         # (not the messages: sk no longer matches B -- garbage decodes, exactly)
+    outs = []
+    for tables in (1, 0):
+        eng = load(forced(pkg, P), S, D)
+        eng.set_option("ternary_tables", tables)
+        etype = np.int32 if P.error_bound_2 >= (1 << 15) else np.int16
+        eng.encrypt_batch(0, S.m, r.astype(stype), S.e1.astype(etype), S.e2.astype(etype))
+        for d in (0, D - 1):
+            g1, g2 = eng.ct_download(d)
+            assert (g1 == c1[d]).all() and (g2 == c2[d]).all()
+        got = eng.decrypt_batch(np.arange(P.n), sk.astype(stype), D=D)
+        assert (got == want).all()
+        outs.append(got)
+    assert (outs[0] == outs[1]).all()

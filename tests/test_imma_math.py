@@ -89,3 +89,50 @@ def test_first_k_step_split_needs_no_clearing():
                 acc[:, lo:lo + 7 * DT] += prod[:, :7 * DT]                   # N = 7*DT, accumulate
                 acc[:, lo + 7 * DT:lo + 8 * DT] = prod[:, 7 * DT:]           # N = DT (the t = 7 rows of B), overwrite
     assert (acc[:, :DIAGS * DT] == want).all()
+
+
+M64 = (1 << 64) - 1
+
+
+def reduce128_model(h, lo, q):
+    """modarith.cuh reduce128 with 64-bit wrap-around: Barrett estimate from the two high words of mu = floor(2^128 / q)"""
+    mu = (1 << 128) // q
+    mu_hi, mu_lo = mu >> 64, mu & M64
+    qh = (h * mu_hi + ((h * mu_lo) >> 64) + ((lo * mu_hi) >> 64)) & M64
+    r = (lo - qh * q) & M64
+    assert r < 4 * q                                      # what the two conditional subtractions below rely on
+    if r >= 2 * q:
+        r -= 2 * q
+    if r >= q:
+        r -= q
+    return r
+
+
+def reduce160_q62_model(value, q):
+    """imma.cu reduce160_q62: the bits above 2^124 folded down with 2^124 mod q, then ONE Barrett step (moduli >= 2^61)"""
+    w = [(value >> (32 * i)) & 0xFFFFFFFF for i in range(5)]
+    c124 = (1 << 124) % q
+    h = (w[3] >> 28) | ((w[4] << 4) & 0xFFFFFFFF)
+    lo = (w[1] << 32) | w[0]
+    hi = ((w[3] & 0x0FFFFFFF) << 32) | w[2]
+    p0, p1 = h * (c124 & 0xFFFFFFFF), h * (c124 >> 32)
+    a = (lo + p0) & M64
+    b = (a + ((p1 << 32) & M64)) & M64
+    t_hi = hi + (p1 >> 32) + (1 if a < lo else 0) + (1 if b < a else 0)
+    assert t_hi < 1 << 64 and (t_hi << 64 | b) == (value & ((1 << 124) - 1)) + h * c124     # t, exactly, in two words
+    assert ((t_hi << 64) | b) // q < 1 << 64              # the quotient fits one word: q >= 2^61, t < 2^125
+    return reduce128_model(t_hi, b, q)
+
+
+@pytest.mark.parametrize("q", [O.largest_ntt_primes(34)[0], O.largest_ntt_primes(34)[-1], (1 << 61) + 1, (1 << 62) - 57, (1 << 61) + 12345678901])
+def test_one_step_reduction_of_the_160_bit_sums(q):
+    """every modulus >= 2^61 (the library checks before it picks this form), sums up to 4096 * (2^64 - 1)^2 -- whatever bytes
+    the operands hold -- and the extremes of every field"""
+    assert q >= 1 << 61
+    rng = np.random.default_rng(q % 1000003)
+    top = 4096 * M64 * M64                                 # k <= 4096 terms of arbitrary 64-bit operands: < 2^140
+    cases = [0, 1, q - 1, q, (1 << 124) - 1, 1 << 124, (1 << 128) - 1, 1 << 128, top, 4096 * (q - 1) ** 2, 256 * (q - 1) ** 2]
+    cases += [int(rng.integers(0, 1 << 62)) * int(rng.integers(0, 1 << 62)) * int(rng.integers(1, 4097)) for _ in range(3000)]
+    cases += [int.from_bytes(rng.bytes(18), "little") % (top + 1) for _ in range(3000)]
+    for v in cases:
+        assert reduce160_q62_model(v, q) == v % q

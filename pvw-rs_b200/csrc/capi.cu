@@ -72,7 +72,7 @@ struct pvw_ctx {
   std::vector<cudaEvent_t> chunk_ev;
   DevTables T{};
   FusedConst F{};                // decode fast path constants (decode.cu (0))
-  int decode_fused = 1;          // option "decode_fused": 0 = always the three-kernel chain
+  int decode_fused = 1;          // option "decode_fused": 0 = always the three-kernel chain, 1 = fused (two launches at ring degree 8), 2 = fused, one kernel
   DevBuf fb;                     // [count (16 bytes)][list u32[S]] of the shares the fast path hands to the chain
   DevBuf tables;                 // one allocation holding every constant table
   DevBuf A, At, B;
@@ -83,6 +83,7 @@ struct pvw_ctx {
   std::vector<uint8_t> c1p_valid;  // per slot: the byte planes behind the residues are current (written by the c1 finisher / a peer's push)
   bool c1_external = false;        // the raw store pointer was handed out (pvw_ct_c1_device_ptr): planes can go stale behind our back
   DevBuf prod1;                    // slot-major c1 product of one encrypt call
+  DevBuf fscr;                     // fused decode, two-launch form: l + 2 words per share between the launches
   // grow-only scratch
   DevBuf stage, rhat, in_small, in_small2, in_m, shat, z, y, X, outd, idxd, idxp;
   // wire format (wire.cu): record tables, envelope templates (device copies at wire_env) and a staging buffer
@@ -535,7 +536,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->prod1, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->prod1, &c->fscr, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
     b->release();
   delete c;
 }
@@ -916,7 +917,13 @@ static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds,
     uint32_t* list = count + 4;
     CUDA_CHECK(cudaMemsetAsync(count, 0, 4, c->stream));
     bool fused = false;
-    launch(c, PVW_KERNEL_DECODE_FUSED, 0.0, [&] { fused = launch_decode_fused(c->T, c->F, z, z_ls, z_ds, Pc, D, out, out_ps, list, count, c->stream, z_cs, sub); });
+    u64* scr = nullptr;
+    if (c->decode_fused == 1 && c->T.ell == 8) {   // two launches (option decode_fused = 2: the one-kernel form)
+      c->fscr.ensure(decode_fused_scratch_words(c->T, S) * 8);
+      scr = c->fscr.as<u64>();
+    }
+    launch(c, PVW_KERNEL_DECODE_FUSED, 0.0, [&] { fused = launch_decode_fused(c->T, c->F, z, z_ls, z_ds, Pc, D, out, out_ps, list, count, c->stream, z_cs, sub, scr); });
+    if (fused && scr) c->launches++;   // the two-launch form queued a second kernel
     if (fused) fb = FallbackList{list, count};
   }
   const FallbackList* fbp = fb.count ? &fb : nullptr;
@@ -980,6 +987,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
     c->y.ensure(decode_scratch_words_y(c->T, (uint64_t)Pc_max * Dstep) * 8);   // sized for the largest chunk up front: growing a
     c->X.ensure(decode_scratch_words_X(c->T, (uint64_t)Pc_max * Dstep) * 8);   // buffer mid-call would synchronise the device
     c->fb.ensure(16 + (size_t)Pc_max * Dstep * 4);
+    c->fscr.ensure(decode_fused_scratch_words(c->T, (uint64_t)Pc_max * Dstep) * 8);
     // host inputs: a short first chunk, so that little of the secret-key copy is exposed before the kernels start, then chunks
     // growing threefold: a party's share of the work takes about 3.5x as long as the copy of its key, so chunk i+1 (<= 3x chunk i)
     // has arrived by the time chunk i is done
@@ -1583,7 +1591,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     else if (n == "gemm_tile") { require(value >= 0 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..3"); c->gemm_tile = (int)value; }
     else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
     else if (n == "lift_fast") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "lift_fast must be 0 or 1"); c->T.lift_fast = (value && c->hp.shortL > 0) ? 1 : 0; }
-    else if (n == "decode_fused") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "decode_fused must be 0 or 1"); c->decode_fused = (int)value; }
+    else if (n == "decode_fused") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "decode_fused must be 0 (chain), 1 (fused, two launches at ring degree 8) or 2 (fused, one kernel)"); c->decode_fused = (int)value; }
     else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }

@@ -29,6 +29,9 @@
 #endif
 // resident CTAs per SM asked for the fused decode kernel at l = 8: 4 (128 registers, ~400 bytes spilled) measured 1.40 ms per
 // bench step against 1.52 ms for 3 (168 registers, no spills) -- the kernel is latency bound and wants the warps
+#ifndef PVW_FUSED_P2_MINB
+#define PVW_FUSED_P2_MINB 6   // CTAs of 128 threads per SM the claim-check launch of the two-launch form is compiled for (80 registers)
+#endif
 #ifndef PVW_FUSED_MINB8
 #define PVW_FUSED_MINB8 4
 #endif
@@ -1121,10 +1124,14 @@ PVW_DEV void share_residues(const u64* __restrict__ z, size_t z_ls, size_t z_ds,
 // by induction on i); with the check it holds modulo Q, so tmp_i = e_{i+1} - D e_i are the centred values the reference works
 // with (|.| < Q/2), H = e_{l-1} - D^(l-1) e_0 telescopes, |e_{l-1}| <= D/2 (centred remainder) gives red = e_{l-1}, every rounded
 // division of the back-substitution is exact, noise_0 = e_0 and the plaintext is centre(-z_0 - e_0) = m.
-template <int ELL, int SW, int ND, int MINB>
+// PHASE 0: the whole procedure in one kernel.  PHASE 1 / 2: the same split in two launches -- pass 1 and the carry chain (the
+// register-hungry half: l * (SW + 1) accumulator words) leave |e_i|, |m| and the signs in a scratch of l + 2 words per share, and the
+// claim check of the remaining limbs (72 % of the instructions) runs as its own kernel at <= 80 registers, 24 instead of 16 warps
+// per SM, from 1 000 instead of 9 700 instructions (the one-kernel form waits a fifth of its cycles for instruction fetch).
+template <int ELL, int SW, int ND, int MINB, int PHASE>
 __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub sub,
                                                                        uint32_t Pc, uint64_t S, u64* __restrict__ out, size_t out_ps, const DevTables T,
-                                                                       const FusedConst F, uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count) {
+                                                                       const FusedConst F, uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count, u64* __restrict__ scr) {
   extern __shared__ __align__(16) u64 sm[];
   const uint32_t L = T.L, Ls = T.shortL;
   u64* s_twi = sm;                                   // [L][ELL]
@@ -1150,6 +1157,12 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t d = s / Pc, p = s % Pc;
     const uint32_t sd = sub.S ? (sub.dmap ? sub.dmap[d] : (uint32_t)d) : 0, srow = sub.S ? (sub.rowmap ? sub.rowmap[p] : (uint32_t)p) : 0;
+    u64 em[ELL];          // |e_i|
+    uint32_t eneg = 0;    // sign bits of e_i
+    bool ok = true;
+    u64 mmag = 0, result = 0;
+    bool mneg = false;
+    if constexpr (PHASE != 2) {
     // ---- pass 1: short lift of t_0..t_{l-2}, -z_0 over the sub-basis
     u64 acc[ELL][SW + 1];
 #pragma unroll
@@ -1220,9 +1233,6 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
       }
     }
     // ---- the carry chain on the candidates: e_{l-1} = d_0, e_{l-2-j} = -x_j, m = centre(-z_0) + x_{l-2}
-    u64 em[ELL];          // |e_i|
-    uint32_t eneg = 0;    // sign bits of e_i
-    bool ok = true;
     u64 x = 0;
     bool xneg = false;
 #pragma unroll
@@ -1263,8 +1273,6 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
       if (!xneg && x != 0) eneg |= 1u << (ELL - 2 - j);      // e = -x
     }
     ok = ok && x <= F.cmax;                                   // |e_0| D^(l-1) + |e_{l-1}| <= Q/2: `last` does not wrap
-    u64 mmag = 0, result = 0;
-    bool mneg = false;
     {
       Small w;
 #pragma unroll
@@ -1275,6 +1283,25 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
       mmag = pt.m[0]; mneg = pt.neg;
       if (pt.neg) ok = ok && pt.m[0] <= 1000;                 // small negative -> 0 (decryption.rs:226-247); larger ones: general path
       result = pt.neg ? 0 : pt.m[0];
+    }
+    }  // PHASE != 2
+    if constexpr (PHASE == 1) {
+      // scratch, word-major (unit stride across the threads): |e_0| .. |e_{l-1}|, |m|, signs + verdict
+#pragma unroll
+      for (int i = 0; i < ELL; i++) scr[(size_t)i * S + s] = em[i];
+      scr[(size_t)ELL * S + s] = mmag;
+      scr[(size_t)(ELL + 1) * S + s] = (u64)eneg | ((u64)(mneg ? 1 : 0) << 32) | ((u64)(ok ? 1 : 0) << 33);
+      if (!ok) fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)s;
+      continue;
+    }
+    if constexpr (PHASE == 2) {
+      const u64 meta = scr[(size_t)(ELL + 1) * S + s];
+      if (!((meta >> 33) & 1)) continue;                    // listed by the first launch already
+      eneg = (uint32_t)meta; mneg = ((meta >> 32) & 1) != 0;
+      mmag = scr[(size_t)ELL * S + s];
+      result = mneg ? 0 : mmag;
+#pragma unroll
+      for (int i = 0; i < ELL; i++) em[i] = scr[(size_t)i * S + s];
     }
     // ---- pass 2: the claim in every other limb
 #pragma unroll 1
@@ -1325,20 +1352,24 @@ __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64
 
 template <int ELL, int SW, int MINB>
 static bool launch_fused_claim(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
-                               uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st) {
+                               uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, u64* scr) {
   const size_t smem = ((size_t)T.L * ELL * 4 + (size_t)T.L * 8 + (size_t)T.shortL * SW + 2 * SW) * 8;
   if (smem > 96 * 1024) return false;
-  int dev = 0, sms = 0, per_sm = 0;
+  int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+  // one launch of a phase: persistent-style grid, four CTAs' worth of shares per resident CTA
+  auto run = [&](auto kern) {
+    int per_sm = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem) != cudaSuccess || per_sm < 1) return false;
+    const unsigned grid = (unsigned)std::min<uint64_t>((S + 127) / 128, (uint64_t)sms * per_sm * 4);
+    kern<<<grid, 128, smem, st>>>(z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, T, F, fb_list, fb_count, scr);
+    return true;
+  };
 #define PVW_FUSED_CLAIM_ND(N)                                                                                                    \
-  case N: {                                                                                                                      \
-    auto kern = decode_fused_claim_kernel<ELL, SW, N, MINB>;                                                                     \
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;         \
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem) != cudaSuccess || per_sm < 1) return false;      \
-    const unsigned grid = (unsigned)std::min<uint64_t>((S + 127) / 128, (uint64_t)sms * per_sm * 4);                             \
-    kern<<<grid, 128, smem, st>>>(z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, T, F, fb_list, fb_count);                         \
-    return true;                                                                                                                 \
-  }
+  case N:                                                                                                                        \
+    if (scr && ELL == 8) return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 1>) && run(decode_fused_claim_kernel<ELL, SW, N, PVW_FUSED_P2_MINB, 2>); \
+    return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 0>);
   switch (F.nd) {
     PVW_FUSED_CLAIM_ND(1)
     PVW_FUSED_CLAIM_ND(2)
@@ -1351,11 +1382,11 @@ static bool launch_fused_claim(const DevTables& T, const FusedConst& F, const u6
 
 template <int ELL, int MINB>
 static bool launch_fused_claim_sw(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
-                                  uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st) {
+                                  uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, u64* scr) {
   switch (T.shortSW) {
-    case 2: return launch_fused_claim<ELL, 2, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 3: return launch_fused_claim<ELL, 3, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 4: return launch_fused_claim<ELL, 4, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
+    case 2: return launch_fused_claim<ELL, 2, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, scr);
+    case 3: return launch_fused_claim<ELL, 3, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, scr);
+    case 4: return launch_fused_claim<ELL, 4, MINB>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, scr);
   }
   return false;
 }
@@ -1399,14 +1430,14 @@ static bool launch_fused_sw(const DevTables& T, const FusedConst& F, const u64* 
 }
 
 bool launch_decode_fused(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps,
-                         uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, size_t z_cs, const DecodeSub* sub) {
+                         uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, size_t z_cs, const DecodeSub* sub, u64* scr) {
   const uint64_t S = (uint64_t)Pc * D;
   if (S == 0) return true;
   if (!F.enabled || S >= (1ull << 32)) return false;
   const DecodeSub sb = sub ? *sub : DecodeSub{nullptr, 0, 0, nullptr, nullptr};
   switch (T.ell) {
-    case 8: return launch_fused_claim_sw<8, PVW_FUSED_MINB8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
-    case 16: return launch_fused_claim_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
+    case 8: return launch_fused_claim_sw<8, PVW_FUSED_MINB8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, scr);
+    case 16: return launch_fused_claim_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, nullptr);
     case 32: return launch_fused_sw<32, 8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
   }
   return false;
@@ -1425,6 +1456,7 @@ void launch_decode_tail(const DevTables& T, const u64* X, uint32_t Pc, uint32_t 
   decode_tail_kernel<<<blocks, 128, 0, st>>>(X, S, Pc, T.ell, out, out_ps, T, fb);
 }
 
+size_t decode_fused_scratch_words(const DevTables& T, uint64_t S) { return (size_t)(T.ell + 2) * S; }
 size_t decode_scratch_words_y(const DevTables& T, uint64_t S) { return (size_t)T.L * (T.ell + 1) * S; }
 size_t decode_scratch_words_X(const DevTables& T, uint64_t S) { return (size_t)(T.ell + 1) * T.NW * S; }
 

@@ -119,7 +119,10 @@ struct FusedConst {
   int enabled;
 };
 bool launch_decode_fused(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, uint32_t Pc, uint32_t D, u64* out, size_t out_ps,
-                         uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, size_t z_cs = 0, const DecodeSub* sub = nullptr);
+                         uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, size_t z_cs = 0, const DecodeSub* sub = nullptr, u64* scr = nullptr);
+// scr != nullptr (ring degree 8): two launches -- short lift + carry chain, then the claim check at a higher occupancy -- with
+// decode_fused_scratch_words(T, S) words of scratch between them
+size_t decode_fused_scratch_words(const DevTables& T, uint64_t S);
 size_t decode_scratch_words_y(const DevTables& T, uint64_t S);
 size_t decode_scratch_words_X(const DevTables& T, uint64_t S);
 

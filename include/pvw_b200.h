@@ -247,8 +247,9 @@ void *pvw_ctx_stream(pvw_ctx *ctx);
  * defaults 8 / 16), "imma_chunk_dealers" (dealers per scratch
  * chunk, default 512), "imma_pair" (1 = the two-SM cta_group::2 form, a measured alternative), "imma_stages" (depth of the
  * product's shared-memory ring, 0 = as deep as fits), "imma_epilogue_warps" (8 = default, 16), "imma_fast_reduce" (1 = default: the one-step
- * reduction of the product's 160-bit sums when every modulus is >= 2^61), "ternary_tables" (1 = default: at ring degree 8, one-byte secrets /
- * randomness with coefficients in {-1, 0, 1} are transformed by table lookup instead of butterflies; same results), "planes_only" (1 = once the byte planes of B exist, free the u64 operand copy of B --
+ * reduction of the product's 160-bit sums when every modulus is >= 2^61), "ternary_tables" (1 = default: at ring degrees 8 and 16, secrets /
+ * randomness with coefficients in {-1, 0, 1} are transformed by table lookup instead of butterflies; same results), "narrow_inputs" (1 = default:
+ * 64-bit secrets of a batched decryption are copied to one byte per coefficient on the device before the per-limb transforms, when they fit), "planes_only" (1 = once the byte planes of B exist, free the u64 operand copy of B --
  * one resident copy instead of two; it is rebuilt from the planes when a single call, a download or a key update needs it), "gemm_impl" (CUDA-core kernel:
  * 0 = synchronous tiles, 1 = TMA bulk-copy pipeline, 2 = tensor-map boxes), "gemm_tile", "refill_lag", "tail_impl", "lift_fast", "decode_fused" (1 = fused decode of clean shares
  * with the general chain as the per-share fallback, the default -- at ring degree 8 as two launches, short lift + carry chain, then the claim check;

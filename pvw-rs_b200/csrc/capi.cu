@@ -83,6 +83,7 @@ struct pvw_ctx {
   std::vector<uint8_t> c1p_valid;  // per slot: the byte planes behind the residues are current (written by the c1 finisher / a peer's push)
   bool c1_external = false;        // the raw store pointer was handed out (pvw_ct_c1_device_ptr): planes can go stale behind our back
   DevBuf prod1;                    // slot-major c1 product of one encrypt call
+  DevBuf narrow;                   // one-byte copy of a chunk of 64-bit secrets + 64 flag words (ntt.cu narrow_i64_kernel)
   DevBuf fscr;                     // fused decode, two-launch form: l + 2 words per share between the launches
   // grow-only scratch
   DevBuf stage, rhat, in_small, in_small2, in_m, shat, z, y, X, outd, idxd, idxp;
@@ -107,7 +108,7 @@ struct pvw_ctx {
   int gemm_impl = 1, gemm_tile = 1, refill_lag = 2;
   // tensor-core form of the matrix product (imma.cu): slot-major canonical copies of A / B (built lazily from the operand
   // form), the diagonal expansion of the dealer-side operand, the slot-major secret-key transforms of one decrypt chunk
-  int use_tern = 1;
+  int use_tern = 1, narrow_inputs = 1;
   const u64* tern_dev = nullptr;
   int use_imma = 1, imma_pair = 0, imma_stages = 0, imma_epi_warps = 0, imma_fast_reduce = 1;
   int64_t imma_min_dealers = 8, imma_min_rows = 16, imma_chunk_dealers = 512;
@@ -383,9 +384,10 @@ const void* at_bytes(const void* p, size_t bytes) { return reinterpret_cast<cons
 
 // ntt.cu: small signed coefficients (element size cbytes) -> NTT form in one of the device layouts
 void ntt(pvw_ctx* c, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out, size_t vstride, size_t lstride,
-         bool accumulate = false, bool pack_out = false, int planes = 0, const u64* addend = nullptr) {
+         bool accumulate = false, bool pack_out = false, int planes = 0, const u64* addend = nullptr, const void* wide = nullptr,
+         const uint32_t* wide_flag = nullptr) {
   bool ok = true;
-  launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_ntt_small(c->T, coef, cbytes, m, count, inner, out, vstride, lstride, c->stream, accumulate, pack_out, planes, addend); });
+  launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_ntt_small(c->T, coef, cbytes, m, count, inner, out, vstride, lstride, c->stream, accumulate, pack_out, planes, addend, wide, wide_flag); });
   require(ok, PVW_ERR_INTERNAL, "forward NTT: unsupported shape (ring degree above 256 or more than 2^31 thread blocks)");
 }
 
@@ -536,7 +538,7 @@ void pvw_ctx_destroy(pvw_ctx* c) {
   for (auto& r : c->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   for (DevBuf* b : {&c->tables, &c->A, &c->At, &c->B, &c->c1s, &c->c2s, &c->stage, &c->rhat, &c->in_small, &c->in_small2, &c->in_m,
-                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->prod1, &c->fscr, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
+                    &c->shat, &c->z, &c->y, &c->X, &c->outd, &c->idxd, &c->idxp, &c->fb, &c->prod1, &c->fscr, &c->narrow, &c->wire_tab, &c->wire_buf, &c->As, &c->Bs, &c->Vx, &c->shat_s, &c->prod})
     b->release();
   delete c;
 }
@@ -918,7 +920,7 @@ static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds,
     CUDA_CHECK(cudaMemsetAsync(count, 0, 4, c->stream));
     bool fused = false;
     u64* scr = nullptr;
-    if (c->decode_fused == 1 && c->T.ell == 8) {   // two launches (option decode_fused = 2: the one-kernel form)
+    if (c->decode_fused == 1 && (c->T.ell == 8 || c->T.ell == 16)) {   // two launches (option decode_fused = 2: the one-kernel form)
       c->fscr.ensure(decode_fused_scratch_words(c->T, S) * 8);
       scr = c->fscr.as<u64>();
     }
@@ -1032,7 +1034,20 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
         // z[d][limb][p][ell] = sum_j s_hat[p][j] * c1_d[j] - c2_d[party]   (decryption.rs:257-274), with
         // s_hat = SecretKey::get_polynomial (secret_key.rs:98-112) computed once per party, not per ciphertext
         if (imma) {
-          ntt(c, at_bytes(d_sk, (size_t)p0 * k * ell * sb), sb, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, false, false, 1);
+          const void* sk_chunk = at_bytes(d_sk, (size_t)p0 * k * ell * sb);
+          if (sb == 8 && c->narrow_inputs && ntt_planes_take_narrow(c->T, k) && chunk_no < 64) {
+            // 64-bit secrets (the reference's i64): the L limbs of the transform would each fetch 8 bytes per coefficient; a one-byte
+            // copy is made first (and ignored if a coefficient does not fit)
+            c->narrow.ensure((size_t)Pc_max * k * ell + 256);
+            uint32_t* nflag = reinterpret_cast<uint32_t*>(c->narrow.as<uint8_t>() + (size_t)Pc_max * k * ell) + chunk_no;
+            if (chunk_no == 0) CUDA_CHECK(cudaMemsetAsync(c->narrow.as<uint8_t>() + (size_t)Pc_max * k * ell, 0, 256, c->stream));
+            bool ok = true;
+            launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_narrow_i64(sk_chunk, c->narrow.p, (uint64_t)Pc * k * ell, nflag, c->stream); });
+            require(ok, PVW_ERR_INTERNAL, "narrowing of 64-bit secrets: unsupported shape");
+            ntt(c, c->narrow.p, 1, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, false, false, 1, nullptr, sk_chunk, nflag);
+          } else {
+            ntt(c, sk_chunk, sb, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, false, false, 1);
+          }
           // the product is stored alone, slot-major (lanes of a warp = consecutive parties: full-sector stores); c2 is
           // subtracted by the decode kernel, which reads both with unit stride
           ImmaArgs g{};
@@ -1579,6 +1594,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     std::string n(name);
     if (n == "imma") c->use_imma = value != 0;
     else if (n == "imma_pair") c->imma_pair = value != 0;
+    else if (n == "narrow_inputs") c->narrow_inputs = value != 0;
     else if (n == "ternary_tables") { c->use_tern = value != 0; c->T.tern = c->use_tern ? c->tern_dev : nullptr; }
     else if (n == "imma_fast_reduce") c->imma_fast_reduce = value != 0;
     else if (n == "imma_epilogue_warps") { require(value == 0 || value == 8 || value == 16, PVW_ERR_INVALID_PARAMETERS, "imma_epilogue_warps must be 0 (default: 8), 8 or 16"); c->imma_epi_warps = (int)value; }

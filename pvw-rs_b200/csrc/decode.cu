@@ -1368,7 +1368,7 @@ static bool launch_fused_claim(const DevTables& T, const FusedConst& F, const u6
   };
 #define PVW_FUSED_CLAIM_ND(N)                                                                                                    \
   case N:                                                                                                                        \
-    if (scr && ELL == 8) return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 1>) && run(decode_fused_claim_kernel<ELL, SW, N, PVW_FUSED_P2_MINB, 2>); \
+    if (scr) return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 1>) && run(decode_fused_claim_kernel<ELL, SW, N, (ELL == 8 ? PVW_FUSED_P2_MINB : 4), 2>); \
     return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 0>);
   switch (F.nd) {
     PVW_FUSED_CLAIM_ND(1)
@@ -1437,7 +1437,7 @@ bool launch_decode_fused(const DevTables& T, const FusedConst& F, const u64* z, 
   const DecodeSub sb = sub ? *sub : DecodeSub{nullptr, 0, 0, nullptr, nullptr};
   switch (T.ell) {
     case 8: return launch_fused_claim_sw<8, PVW_FUSED_MINB8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, scr);
-    case 16: return launch_fused_claim_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, nullptr);
+    case 16: return launch_fused_claim_sw<16, 2>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st, scr);
     case 32: return launch_fused_sw<32, 8>(T, F, z, z_ls, z_ds, z_cs, sb, Pc, S, out, out_ps, fb_list, fb_count, st);
   }
   return false;

@@ -196,8 +196,8 @@ struct HostParams {
   BigU Q, delta, delta_pow;                 // parameters.rs:151-163
   uint32_t NW = 0;                           // words of Q
   std::vector<LimbConst> lc;                 // [L]
-  std::vector<uint64_t> tern;                // ring degree 8: [L][2][81][8]  NTT of the ternary polynomials supported on coefficients
-                                             // 0..3 (half 0) / 4..7 (half 1); row index = sum (x_i + 1) 3^i over the half (ntt.cu)
+  std::vector<uint64_t> tern;                // ring degrees 8, 16: [L][l/4][81][l]  NTT of the ternary polynomials supported on the four
+                                             // coefficients 4g .. 4g+3 of group g; row index = sum (x_i + 1) 3^i over the group (ntt.cu)
   std::vector<uint64_t> tw, tw_sh, twi, twi_sh, gadget_hat, gadget_hat_sh;  // [L][ell] each
   std::vector<uint64_t> lgad, lgad_sh;                                      // [L][ell] ell * Delta^i mod q_j (+ Shoup): fused decode check
   // CRT lift: qhat[j] = Q / q_j  ([L][NW]),  Qsh[b] = Q << b  ([LB][NW+1])
@@ -316,13 +316,14 @@ struct HostParams {
       }
     }
     tern.clear();
-    if (ell == 8) {
-      tern.assign((size_t)L * 2 * 81 * 8, 0);
+    if (ell == 8 || ell == 16) {
+      const uint32_t groups = ell / 4;                   // groups of four coefficients
+      tern.assign((size_t)L * groups * 81 * ell, 0);
       for (uint32_t j = 0; j < L; j++)
-        for (uint32_t half = 0; half < 2; half++)
+        for (uint32_t g = 0; g < groups; g++)
           for (uint32_t row = 0; row < 81; row++) {
-            uint64_t* a = &tern[(((size_t)j * 2 + half) * 81 + row) * 8];
-            for (uint32_t i = 0, r = row; i < 4; i++, r /= 3) a[4 * half + i] = (r % 3 == 0) ? moduli[j] - 1 : (r % 3 == 1) ? 0 : 1;   // x_i = digit - 1
+            uint64_t* a = &tern[(((size_t)j * groups + g) * 81 + row) * ell];
+            for (uint32_t i = 0, r = row; i < 4; i++, r /= 3) a[4 * g + i] = (r % 3 == 0) ? moduli[j] - 1 : (r % 3 == 1) ? 0 : 1;   // x_i = digit - 1
             host_ntt_fwd(a, j);
           }
     }

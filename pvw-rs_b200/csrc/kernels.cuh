@@ -41,7 +41,7 @@ struct DevTables {
   uint32_t shortL, shortSW;
   int lift_fast;  // 1 = try the short lift first
   int tail_impl;  // 1 = register-resident decode tail where a specialisation exists, 0 = generic kernel
-  const u64* tern;  // ring degree 8: [L][2][81][8] transforms of the ternary half-polynomials (hostparams.hpp), else nullptr
+  const u64* tern;  // ring degrees 8, 16: [L][l/4][81][l] transforms of the ternary four-coefficient groups (hostparams.hpp), else nullptr
 };
 
 // ---- ntt.cu -------------------------------------------------------------------------------------------------
@@ -53,7 +53,12 @@ struct DevTables {
 // returns false when the shape cannot be launched (ring degree above 256, more than 2^31 blocks) -- nothing was queued then
 bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out,
                       size_t vstride, size_t lstride, cudaStream_t st, bool accumulate = false, bool pack_out = false, int planes = 0,
-                      const u64* addend = nullptr);
+                      const u64* addend = nullptr, const void* wide = nullptr, const uint32_t* wide_flag = nullptr);
+// wide / wide_flag (byte-plane kernels, k % 4 == 0, ring degree <= 16): `coef` is the one-byte copy launch_narrow_i64 made of the
+// 64-bit inputs `wide`; *wide_flag != 0 (a value did not fit one byte) makes the kernel read `wide` instead
+bool launch_narrow_i64(const void* in, void* out, uint64_t values, uint32_t* flag, cudaStream_t st);
+// true when launch_ntt_small would take the four-polynomial byte-plane kernel for this shape (the one that accepts wide / wide_flag)
+inline bool ntt_planes_take_narrow(const DevTables& T, uint32_t inner) { return inner % 4 == 0 && T.ell <= 16; }
 // c1 finisher of the tensor-core path (ntt.cu): slot d of the store = [packed residues u64[L][k][ell]][byte planes u8[L*ell][8][kp]];
 // addend = the slot-major product [d][limb][c][k].  false: shape not served (k % 4 != 0, ring degree above 16) -- nothing queued.
 bool launch_ntt_c1_finish(const DevTables& T, const void* coef, int cbytes, uint64_t count, uint32_t k, u64* c1, size_t slot_stride, const u64* addend,

@@ -131,12 +131,17 @@ __global__ void __launch_bounds__(128) ntt_small_kernel(const void* __restrict__
 // Byte planes of NTT(small polynomial), FOUR consecutive polynomials j per thread (k % 4 == 0): every (slot, byte index) of the
 // four goes out as one 4-byte word and a warp stores 128 contiguous bytes per instruction.  (The first version stored single
 // bytes: 64 store instructions of 32 bytes per polynomial and limb.)  SIDE 3: matrix-row side, SIDE 4: dealer side (imma.cuh).
-constexpr uint32_t TERN_PITCH = 10;
+constexpr uint32_t TERN_PITCH = 10;     // ring degree 8: words between table rows in shared memory (8 + 2: rows start in different bank groups)
+constexpr uint32_t TERN_PITCH16 = 18;   // ring degree 16
 template <int ELL, int SIDE>
-__global__ void __launch_bounds__(128, ELL == 8 ? 5 : 1) ntt_planes4_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t inner, uint8_t* __restrict__ out,
+__global__ void __launch_bounds__(128, ELL == 8 ? 5 : ELL == 16 ? 3 : 1) ntt_planes4_kernel(const void* __restrict__ coef, int cbytes, uint64_t count, uint32_t inner, uint8_t* __restrict__ out,
                                                           size_t kp, size_t pstride, const LimbConst* __restrict__ lcs, const u64* __restrict__ tw,
-                                                          const u64* __restrict__ tw_sh, const uint32_t L, const u64* __restrict__ tern) {
+                                                          const u64* __restrict__ tw_sh, const uint32_t L, const u64* __restrict__ tern,
+                                                          const void* __restrict__ wide, const uint32_t* __restrict__ wide_flag) {
   __shared__ u64 s_tw[ELL], s_tw_sh[ELL];
+  // `coef` may be a one-byte copy of 64-bit inputs made by narrow_i64_kernel (an eighth of the bytes for the L limbs to fetch):
+  // when that kernel met a value outside [-128, 127] it raised the flag, and the original goes in instead
+  if (wide_flag != nullptr && *wide_flag != 0) { coef = wide; cbytes = 8; }
   // tern != nullptr (one-byte inputs, ring degree 8): this limb's 2 x 81 transforms of ternary half-polynomials, rows TERN_PITCH words
   // apart (80 bytes: eight consecutive rows start in eight different 16-byte bank groups)
   extern __shared__ __align__(16) u64 s_tern[];
@@ -147,6 +152,8 @@ __global__ void __launch_bounds__(128, ELL == 8 ? 5 : 1) ntt_planes4_kernel(cons
   }
   if (ELL == 8 && tern != nullptr)
     for (uint32_t i = threadIdx.x; i < 162 * 8; i += blockDim.x) s_tern[(i >> 3) * TERN_PITCH + (i & 7)] = tern[(size_t)limb * 162 * 8 + i];
+  if (ELL == 16 && tern != nullptr)
+    for (uint32_t i = threadIdx.x; i < 324 * 16; i += blockDim.x) s_tern[(i >> 4) * TERN_PITCH16 + (i & 15)] = tern[(size_t)limb * 324 * 16 + i];
   __syncthreads();
   const LimbConst lc = lcs[limb];
   const uint64_t idx = 4 * ((uint64_t)blk * blockDim.x + threadIdx.x);   // first of this thread's four polynomials (same row: inner % 4 == 0)
@@ -229,6 +236,82 @@ __global__ void __launch_bounds__(128, ELL == 8 ? 5 : 1) ntt_planes4_kernel(cons
     for (int t = 0; t < ELL; t++)
 #pragma unroll
       for (int b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(o8 + (size_t)t * pstride + (size_t)b * step) = w[t][b];
+  } else if (ELL == 16 && tern != nullptr) {
+    // Ring degree 16 with the ternary tables: 8 * 16 output words do not fit the registers, so the slots go out in two halves; a
+    // ternary polynomial costs four table rows (one per group of four coefficients) and three modular additions per slot in each
+    // half, any other polynomial a full transform per half (rare: secrets and randomness at the default variance are ternary).
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      uint32_t w[8][8];
+#pragma unroll
+      for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) w[t][b] = 0;
+#pragma unroll 1
+      for (int p = 0; p < 4; p++) {
+        u64 a[8];
+        uint32_t gi[4] = {0, 0, 0, 0};
+        bool ternary;
+        if (cbytes == 1) {
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const signed char*>(coef) + (idx + p) * 16);
+          const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+          uint32_t bad = 0;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const uint32_t t = ((vw[g] & 0x7f7f7f7fu) + 0x01010101u) ^ (vw[g] & 0x80808080u);   // x_i + 1 in every byte
+            bad |= (t & 0xfcfcfcfcu) | ((t & (t >> 1)) & 0x01010101u);
+            gi[g] = __dp4a(t, 0x1b090301u, 0u);
+          }
+          ternary = bad == 0;
+        } else {
+          long long x[ELL];
+          load_small<ELL>(coef, cbytes, idx + p, x);
+          ternary = true;
+#pragma unroll
+          for (int i = 0; i < ELL; i++) {
+            const u64 u = (u64)x[i] + 1;
+            ternary = ternary && u <= 2;
+            gi[i >> 2] += (uint32_t)u * ((i & 3) == 0 ? 1u : (i & 3) == 1 ? 3u : (i & 3) == 2 ? 9u : 27u);
+          }
+        }
+        if (ternary) {
+          const u64* r0 = s_tern + (size_t)gi[0] * TERN_PITCH16 + 8 * half;
+          const u64* r1 = s_tern + (size_t)(81u + gi[1]) * TERN_PITCH16 + 8 * half;
+          const u64* r2 = s_tern + (size_t)(162u + gi[2]) * TERN_PITCH16 + 8 * half;
+          const u64* r3 = s_tern + (size_t)(243u + gi[3]) * TERN_PITCH16 + 8 * half;
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const ulonglong2 v0 = reinterpret_cast<const ulonglong2*>(r0)[t], v1 = reinterpret_cast<const ulonglong2*>(r1)[t];
+            const ulonglong2 v2 = reinterpret_cast<const ulonglong2*>(r2)[t], v3 = reinterpret_cast<const ulonglong2*>(r3)[t];
+            a[2 * t] = addmod(addmod(v0.x, v1.x, lc.q), addmod(v2.x, v3.x, lc.q), lc.q);
+            a[2 * t + 1] = addmod(addmod(v0.y, v1.y, lc.q), addmod(v2.y, v3.y, lc.q), lc.q);
+          }
+        } else {
+          long long x[ELL];
+          load_small<ELL>(coef, cbytes, idx + p, x);
+          u64 f[ELL];
+#pragma unroll
+          for (int t = 0; t < ELL; t++) f[t] = reduce_i64(x[t], lc);
+          ntt_forward_lazy_regs<ELL>(f, s_tw, s_tw_sh, lc.q);
+#pragma unroll
+          for (int t = 0; t < 8; t++) a[t] = half ? f[8 + t] : f[t];
+        }
+        const uint32_t keep = 0x3210u & ~(0xFu << (4 * p));
+        uint32_t sel[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) sel[b] = keep | ((4u + b) << (4 * p));
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          const uint32_t lo = (uint32_t)a[t], hi = (uint32_t)(a[t] >> 32);
+#pragma unroll
+          for (int b = 0; b < 4; b++) { w[t][b] = __byte_perm(w[t][b], lo, sel[b]); w[t][4 + b] = __byte_perm(w[t][4 + b], hi, sel[b]); }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) *reinterpret_cast<uint32_t*>(o8 + (size_t)(8 * half + t) * pstride + (size_t)b * step) = w[t][b];
+    }
   } else {   // 8 * ELL output words do not fit the registers next to a transform: straight-line, four transforms side by side
     u64 a[4][ELL];
 #pragma unroll
@@ -305,6 +388,33 @@ __global__ void __launch_bounds__(128) ntt_c1_finish_kernel(const void* __restri
   }
 }
 
+// 64-bit small inputs -> one byte each (eight per thread); *flag is raised when a value does not fit, and the consumer then reads
+// the original (ntt_planes4_kernel).  Secrets are ternary or a few units wide (CBD, parameters.rs:251-254), the reference keeps them as i64.
+__global__ void __launch_bounds__(256) narrow_i64_kernel(const long long* __restrict__ in, signed char* __restrict__ out, uint64_t groups, uint32_t* __restrict__ flag) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups) return;
+  const longlong2* src = reinterpret_cast<const longlong2*>(in + i * 8);
+  uint32_t w[2] = {0, 0};
+  bool bad = false;
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const longlong2 v = src[t];
+    bad = bad || v.x < -128 || v.x > 127 || v.y < -128 || v.y > 127;
+    w[t >> 1] |= ((uint32_t)v.x & 0xffu) << (16 * (t & 1)) | ((uint32_t)v.y & 0xffu) << (16 * (t & 1) + 8);
+  }
+  *reinterpret_cast<uint2*>(out + i * 8) = make_uint2(w[0], w[1]);
+  if (bad) *flag = 1u;
+}
+
+bool launch_narrow_i64(const void* in, void* out, uint64_t values, uint32_t* flag, cudaStream_t st) {
+  if (values == 0) return true;
+  if (values % 8 != 0) return false;
+  const uint64_t groups = values / 8, blocks = (groups + 255) / 256;
+  if (blocks >= (1ull << 31)) return false;
+  narrow_i64_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(in), reinterpret_cast<signed char*>(out), groups, flag);
+  return true;
+}
+
 bool launch_ntt_c1_finish(const DevTables& T, const void* coef, int cbytes, uint64_t count, uint32_t k, u64* c1, size_t slot_stride, const u64* addend,
                           uint32_t kp, cudaStream_t st) {
   if (count == 0) return true;
@@ -375,7 +485,8 @@ __global__ void __launch_bounds__(64) ntt_small_generic_kernel(const int mode, c
 }
 
 bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u64* m, uint64_t count, uint32_t inner, u64* out,
-                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes, const u64* addend) {
+                      size_t vstride, size_t lstride, cudaStream_t st, bool accumulate, bool pack_out, int planes, const u64* addend,
+                      const void* wide, const uint32_t* wide_flag) {
   if (count == 0) return true;
   if (cbytes != 1 && cbytes != 2 && cbytes != 4 && cbytes != 8) return false;
   const int mode = addend ? 5 : planes == 1 ? 3 : planes == 2 ? 4 : accumulate ? 1 : pack_out ? 2 : 0;
@@ -385,14 +496,15 @@ bool launch_ntt_small(const DevTables& T, const void* coef, int cbytes, const u6
   // byte planes, four polynomials per thread: needs whole groups of four inside a row and registers for 4 * ell residues
   const bool four = (mode == 3 || mode == 4) && inner % 4 == 0 && T.ell <= 16 && m == nullptr;
   const unsigned grid4 = (unsigned)(((count / 4 + 127) / 128) * T.L);
+  if (wide_flag != nullptr && !four) return false;          // a narrowed copy is only understood by the four-polynomial byte-plane kernels
   // ring degree 8: the table path for ternary polynomials (secrets, randomness); T.tern is null when switched off
-  const u64* tern = (four && T.ell == 8) ? T.tern : nullptr;
-  const size_t tern_smem = tern ? (size_t)162 * TERN_PITCH * 8 : 0;
+  const u64* tern = (four && (T.ell == 8 || T.ell == 16)) ? T.tern : nullptr;
+  const size_t tern_smem = !tern ? 0 : T.ell == 8 ? (size_t)162 * TERN_PITCH * 8 : (size_t)324 * TERN_PITCH16 * 8;
 #define PVW_NTT_ARGS coef, cbytes, m, count, inner, out, vstride, lstride, T.lc, T.tw, T.tw_sh, T.gadget_hat, T.gadget_hat_sh, addend, T.L
 #define PVW_NTT_CASE(E)                                                                                                          \
   case E:                                                                                                                        \
-    if (four && mode == 3) ntt_planes4_kernel<(E <= 16 ? E : 8), 3><<<grid4, 128, tern_smem, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L, tern); \
-    else if (four) ntt_planes4_kernel<(E <= 16 ? E : 8), 4><<<grid4, 128, tern_smem, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L, tern);        \
+    if (four && mode == 3) ntt_planes4_kernel<(E <= 16 ? E : 8), 3><<<grid4, 128, tern_smem, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L, tern, wide, wide_flag); \
+    else if (four) ntt_planes4_kernel<(E <= 16 ? E : 8), 4><<<grid4, 128, tern_smem, st>>>(coef, cbytes, count, inner, reinterpret_cast<uint8_t*>(out), vstride, lstride, T.lc, T.tw, T.tw_sh, T.L, tern, wide, wide_flag);        \
     else if (mode == 5) ntt_small_kernel<E, 5><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
     else if (mode == 3) ntt_small_kernel<E, 3><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \
     else if (mode == 4) ntt_small_kernel<E, 4><<<grid, 128, 0, st>>>(PVW_NTT_ARGS);                                              \

@@ -176,20 +176,25 @@ def test_planes_only_keeps_one_copy_of_the_public_key(pkg):
     assert (eng.decrypt_batch(np.arange(P.n), S.sk, D=D) == want).all()
 
 
-@pytest.mark.parametrize("name,stype", [("EX", np.int8), ("EX", np.int64), ("P128s", np.int8), ("P128s", np.int64)])
-def test_ternary_tables_and_butterflies_agree(pkg, name, stype):
-    """Ring degree 8: polynomials with coefficients in {-1, 0, 1} are transformed by table lookup (ntt.cu), any other polynomial by
-    the butterflies -- mixed in one call here, for every input element size, against the oracle and against the option switched off."""
+@pytest.mark.parametrize("name,stype,big", [("EX", np.int8, 0), ("EX", np.int64, 0), ("P128s", np.int8, 0), ("P128s", np.int64, 0), ("P128s", np.int64, 1),
+                                            ("T16", np.int8, 0), ("T16", np.int64, 0), ("P256s", np.int8, 0), ("P256s", np.int64, 0), ("P256s", np.int64, 1)])
+def test_ternary_tables_and_butterflies_agree(pkg, name, stype, big):
+    """Ring degrees 8 and 16: polynomials with coefficients in {-1, 0, 1} are transformed by table lookup (ntt.cu), any other polynomial by
+    the butterflies -- mixed in one call here, for every input element size (64-bit secrets are narrowed to one byte on the device when they
+    fit), against the oracle and against the option switched off."""
     P = SETS[name]()
     D = 9
     S = System(P, D, "u63")
     rng = np.random.default_rng(77)
     sk = S.sk.copy()
     sk[::2, ::3, 5] = 2                                     # every third polynomial of every other party leaves the ternary set
-    sk[1, 1, :] = [-128, 127, -2, 2, 3, -3, 0, 1]           # the edges of the one-byte range
+    sk[1, 1, :8] = [-128, 127, -2, 2, 3, -3, 0, 1]          # the edges of the one-byte range
     sk[3 % P.n] = rng.integers(-1, 2, size=sk[0].shape)     # a fully ternary key that is not the seeded one
+    if big:
+        sk[2 % P.n, 0, 0] = 1000                            # 64-bit secrets that do not fit one byte: the narrowed copy is dropped (ntt.cu)
     r = S.r.copy()
-    r[0, 0, :] = [1, -1, 0, 2, -2, 1, 0, -1]
+    r[0, 0, :8] = [1, -1, 0, 2, -2, 1, 0, -1]
+    r[1, 1, P.l - 1] = -2                                   # the last coefficient of the last group
     c1, c2 = S.co.encrypt(S.A, S.B, S.m, r, S.e1, S.e2)
     want = S.co.decrypt(sk, c1, c2)                         # (not the messages: sk no longer matches B -- garbage decodes, exactly)
     outs = []

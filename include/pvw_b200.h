@@ -261,7 +261,8 @@ int pvw_ctx_set_option(pvw_ctx *ctx, const char *name, int64_t value);
  * bytes accumulated since the last reset.  Synchronises the stream. */
 enum { PVW_KERNEL_NTT = 0, PVW_KERNEL_MAC = 1, PVW_KERNEL_DECODE_RNS = 2, PVW_KERNEL_CRT_LIFT = 3, PVW_KERNEL_DECODE_TAIL = 4,
        PVW_KERNEL_PERMUTE = 5, PVW_KERNEL_WIRE = 6, PVW_KERNEL_EXPAND = 7, PVW_KERNEL_DECODE_FUSED = 8, PVW_KERNEL_IMMA = 9 /* the product on the INT8 tensor cores; PVW_KERNEL_MAC = on the CUDA cores */,
-       PVW_KERNEL_KINDS = 10 };
+       PVW_KERNEL_NTT_PLANES = 10 /* secrets / randomness -> byte planes (table lookup for ternary polynomials, else butterflies); PVW_KERNEL_NTT = the other transforms */,
+       PVW_KERNEL_KINDS = 11 };
 int pvw_ctx_profile(pvw_ctx *ctx, int kind, double *ms_total, uint64_t *launches, double *algorithmic_bytes);
 /* number of kernels launched by this context so far */
 uint64_t pvw_ctx_launch_count(const pvw_ctx *ctx);

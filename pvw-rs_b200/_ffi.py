@@ -91,7 +91,7 @@ SIGNATURES = {
     "pvw_version": (C.c_char_p, []),
 }
 
-KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute", "wire", "expand", "decode_fused", "imma_gemm"]
+KERNEL_KINDS = ["ntt_small", "mac_gemm", "decode_rns", "crt_lift", "decode_tail", "permute", "wire", "expand", "decode_fused", "imma_gemm", "ntt_planes"]
 
 _lib = None
 

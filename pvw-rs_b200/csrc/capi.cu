@@ -387,7 +387,7 @@ void ntt(pvw_ctx* c, const void* coef, int cbytes, const u64* m, uint64_t count,
          bool accumulate = false, bool pack_out = false, int planes = 0, const u64* addend = nullptr, const void* wide = nullptr,
          const uint32_t* wide_flag = nullptr) {
   bool ok = true;
-  launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_ntt_small(c->T, coef, cbytes, m, count, inner, out, vstride, lstride, c->stream, accumulate, pack_out, planes, addend, wide, wide_flag); });
+  launch(c, planes ? PVW_KERNEL_NTT_PLANES : PVW_KERNEL_NTT, 0.0, [&] { ok = launch_ntt_small(c->T, coef, cbytes, m, count, inner, out, vstride, lstride, c->stream, accumulate, pack_out, planes, addend, wide, wide_flag); });
   require(ok, PVW_ERR_INTERNAL, "forward NTT: unsupported shape (ring degree above 256 or more than 2^31 thread blocks)");
 }
 
@@ -1042,7 +1042,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
             uint32_t* nflag = reinterpret_cast<uint32_t*>(c->narrow.as<uint8_t>() + (size_t)Pc_max * k * ell) + chunk_no;
             if (chunk_no == 0) CUDA_CHECK(cudaMemsetAsync(c->narrow.as<uint8_t>() + (size_t)Pc_max * k * ell, 0, 256, c->stream));
             bool ok = true;
-            launch(c, PVW_KERNEL_NTT, 0.0, [&] { ok = launch_narrow_i64(sk_chunk, c->narrow.p, (uint64_t)Pc * k * ell, nflag, c->stream); });
+            launch(c, PVW_KERNEL_NTT_PLANES, 0.0, [&] { ok = launch_narrow_i64(sk_chunk, c->narrow.p, (uint64_t)Pc * k * ell, nflag, c->stream); });
             require(ok, PVW_ERR_INTERNAL, "narrowing of 64-bit secrets: unsupported shape");
             ntt(c, c->narrow.p, 1, nullptr, (uint64_t)Pc * k, k, c->shat_s.as<u64>(), kp, (size_t)Pc * 8 * kp, false, false, 1, nullptr, sk_chunk, nflag);
           } else {

@@ -136,3 +136,26 @@ def test_one_step_reduction_of_the_160_bit_sums(q):
     cases += [int.from_bytes(rng.bytes(18), "little") % (top + 1) for _ in range(3000)]
     for v in cases:
         assert reduce160_q62_model(v, q) == v % q
+
+
+def test_ternary_transform_is_two_table_rows():
+    """ntt.cu's table path: the transform is linear, so NTT(x) of a ternary polynomial is the sum of the rows of its four-coefficient
+    groups, row index = sum (x_i + 1) 3^i over the group (hostparams.hpp builds the rows with the same host transform)"""
+    P = O.Params(4, 2, 8, O.TEST_MODULI, error_bound_1=50, error_bound_2=50)
+    rng = np.random.default_rng(3)
+    groups = P.l // 4
+    table = {}
+    for g in range(groups):
+        for row in range(81):
+            coeffs, r = [0] * P.l, row
+            for i in range(4):
+                coeffs[4 * g + i] = r % 3 - 1
+                r //= 3
+            table[g, row] = P.ntt_forward(P.from_coefficients(coeffs))
+    for _ in range(40):
+        x = rng.integers(-1, 2, size=P.l)
+        want = P.ntt_forward(P.from_coefficients([int(v) for v in x]))
+        rows = [table[g, sum((int(x[4 * g + i]) + 1) * 3 ** i for i in range(4))] for g in range(groups)]
+        for j, q in enumerate(P.moduli):
+            got = [sum(int(np.asarray(r_)[j][t]) for r_ in rows) % q for t in range(P.l)]
+            assert got == [int(v) for v in np.asarray(want)[j]]

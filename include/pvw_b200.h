@@ -19,6 +19,9 @@
  *    device (inputs already resident in HBM); otherwise they are host pointers and the call performs the copies.
  *    Device-pointer calls are asynchronous: they are queued on pvw_ctx_stream() and return at once, so the caller must
  *    order its own producers / consumers of those buffers against that stream (events, or pvw_ctx_synchronize()).
+ *    Host-pointer calls return when the caller's buffers may be reused and every host output has been written: a call without
+ *    host outputs (pvw_encrypt_batch) returns once its inputs have been copied, while its kernels are still queued -- the
+ *    ciphertexts live in the device store, and every later call of the context is ordered after them.
  *  - there is no CPU fallback: without a CUDA device pvw_ctx_create fails with PVW_ERR_INTERNAL.
  */
 #ifndef PVW_B200_H

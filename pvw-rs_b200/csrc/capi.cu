@@ -68,7 +68,8 @@ struct pvw_ctx {
   uint32_t row0 = 0, nrows = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // host<->device staging copies of the host-pointer calls, overlapped with kernels
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] e2 / m staged, [1] r / e1 staged, [2] tail of the last host-pointer encryption, [3] a decrypt chunk done
+  bool tail_pending = false;           // ev[2] has been recorded: the copy stream of a later host-pointer call must wait for it
   std::vector<cudaEvent_t> chunk_ev;
   DevTables T{};
   FusedConst F{};                // decode fast path constants (decode.cu (0))
@@ -768,10 +769,13 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
     // copy order matters (one host-to-device DMA queue): the small inputs the first kernels need go first, then the big
     // ones (e2, m) on the copy stream, waited for only after the c2 product
     const int sb = secret_bytes(flags), eb = error_bytes(flags);
+    // the staging buffers may still feed kernels of an earlier host-pointer encryption (which no longer waits for them, see the end)
+    if (host && c->tail_pending) CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev[2], 0));
     const void* d_r = stage_in(c, c->in_small, r, (size_t)D * k * ell * sb, flags);
     const void* d_e1 = nullptr;
     if (c1_hi > c1_lo)
       d_e1 = stage_in(c, c->in_small2, at_bytes(e1, (size_t)c1_lo * k * ell * eb), (size_t)(c1_hi - c1_lo) * k * ell * eb, flags);
+    if (host) CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));   // r and e1 have left the caller's buffers once this has fired
     const void* d_e2 = do_c2 ? stage_in_overlapped(c, c->stage, e2, (size_t)D * nrows * ell * eb, flags, c->ev[0]) : nullptr;
     const u64* d_m = do_c2 ? (const u64*)stage_in_overlapped(c, c->in_m, m, (size_t)D * nrows * 8, flags, c->ev[0]) : nullptr;
     // r_hat (encryption.rs:147-154): operand form [d][limb][j][ell] for the IMAD kernel, byte planes for the tensor-core one
@@ -875,7 +879,16 @@ int pvw_encrypt_batch(pvw_ctx* c, uint32_t slot0, uint32_t D, uint32_t c1_lo, ui
       CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev[0], 0));
       preload(true);
     }
-    if (!(flags & PVW_IO_DEVICE)) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (host) {
+      // The call returns once the caller's buffers have been read -- r, e1 (head of the compute stream) and e2, m (copy stream) --
+      // not once the kernels have run: the ciphertexts stay in the device store, every consumer is ordered on the same stream, and
+      // the host side of the next call (a decryption's index and key copies) is then queued under this call's products.  The
+      // staging buffers are protected by ev[2]: the copy stream of the next host-pointer call waits for it.
+      CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
+      c->tail_pending = true;
+      CUDA_CHECK(cudaEventSynchronize(c->ev[1]));
+      if (do_c2) CUDA_CHECK(cudaEventSynchronize(c->ev[0]));
+    }
   });
 }
 
@@ -1002,6 +1015,7 @@ int pvw_decrypt_batch(pvw_ctx* c, uint32_t D, const uint32_t* dealer_slots, uint
       pc = (uint32_t)std::min<uint64_t>(Pc_max, 3ull * pc);
     }
     if (host) {  // every chunk's secret keys are queued now, in order, each with its own event: chunk i+1 arrives while chunk i computes
+      if (c->tail_pending) CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->ev[2], 0));   // in_small may still hold an encryption's r
       uint32_t i = 0;
       for (uint32_t p0 = 0; p0 < P; i++) {
         const uint32_t Pc = chunks[i];

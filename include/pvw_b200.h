@@ -255,8 +255,8 @@ void *pvw_ctx_stream(pvw_ctx *ctx);
  * 64-bit secrets of a batched decryption are copied to one byte per coefficient on the device before the per-limb transforms, when they fit), "planes_only" (1 = once the byte planes of B exist, free the u64 operand copy of B --
  * one resident copy instead of two; it is rebuilt from the planes when a single call, a download or a key update needs it), "gemm_impl" (CUDA-core kernel:
  * 0 = synchronous tiles, 1 = TMA bulk-copy pipeline, 2 = tensor-map boxes), "gemm_tile", "refill_lag", "tail_impl", "lift_fast", "decode_fused" (1 = fused decode of clean shares
- * with the general chain as the per-share fallback, the default -- at ring degree 8 as two launches, short lift + carry chain, then the claim check;
- * 2 = the same in one kernel; 0 = the general chain for every share),
+ * with the general chain as the per-share fallback, the default -- at ring degrees 8 and 16 as two launches, short lift + carry chain, then the
+ * claim check; 0 = the general chain for every share),
  * "decrypt_chunk_shares", "upload_chunk_bytes", "profile" */
 int pvw_ctx_set_option(pvw_ctx *ctx, const char *name, int64_t value);
 /* per-kernel-kind device timing, measured with CUDA events on the context's stream around every launch while the

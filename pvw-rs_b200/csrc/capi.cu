@@ -73,7 +73,7 @@ struct pvw_ctx {
   std::vector<cudaEvent_t> chunk_ev;
   DevTables T{};
   FusedConst F{};                // decode fast path constants (decode.cu (0))
-  int decode_fused = 1;          // option "decode_fused": 0 = always the three-kernel chain, 1 = fused (two launches at ring degree 8), 2 = fused, one kernel
+  int decode_fused = 1;          // option "decode_fused": 0 = always the three-kernel chain, 1 = the fused fast path first
   DevBuf fb;                     // [count (16 bytes)][list u32[S]] of the shares the fast path hands to the chain
   DevBuf tables;                 // one allocation holding every constant table
   DevBuf A, At, B;
@@ -933,7 +933,7 @@ static void decode_on_device(pvw_ctx* c, const u64* z, size_t z_ls, size_t z_ds,
     CUDA_CHECK(cudaMemsetAsync(count, 0, 4, c->stream));
     bool fused = false;
     u64* scr = nullptr;
-    if (c->decode_fused == 1 && (c->T.ell == 8 || c->T.ell == 16)) {   // two launches (option decode_fused = 2: the one-kernel form)
+    if (c->T.ell == 8 || c->T.ell == 16) {   // thread-per-share form: two launches with l + 2 scratch words per share between them
       c->fscr.ensure(decode_fused_scratch_words(c->T, S) * 8);
       scr = c->fscr.as<u64>();
     }
@@ -1621,7 +1621,7 @@ int pvw_ctx_set_option(pvw_ctx* c, const char* name, int64_t value) {
     else if (n == "gemm_tile") { require(value >= 0 && value <= 3, PVW_ERR_INVALID_PARAMETERS, "gemm_tile must be 0..3"); c->gemm_tile = (int)value; }
     else if (n == "refill_lag") { require(value >= 1 && value <= 5, PVW_ERR_INVALID_PARAMETERS, "refill_lag must be 1..5"); c->refill_lag = (int)value; }
     else if (n == "lift_fast") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "lift_fast must be 0 or 1"); c->T.lift_fast = (value && c->hp.shortL > 0) ? 1 : 0; }
-    else if (n == "decode_fused") { require(value >= 0 && value <= 2, PVW_ERR_INVALID_PARAMETERS, "decode_fused must be 0 (chain), 1 (fused, two launches at ring degree 8) or 2 (fused, one kernel)"); c->decode_fused = (int)value; }
+    else if (n == "decode_fused") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "decode_fused must be 0 (chain for every share) or 1 (fused fast path)"); c->decode_fused = (int)value; }
     else if (n == "tail_impl") { require(value == 0 || value == 1, PVW_ERR_INVALID_PARAMETERS, "tail_impl must be 0 or 1"); c->T.tail_impl = (int)value; }
     else if (n == "decrypt_chunk_shares") { require(value > 0, PVW_ERR_INVALID_PARAMETERS, "decrypt_chunk_shares must be positive"); c->decrypt_chunk_shares = value; }
     else if (n == "upload_chunk_bytes") { require(value >= 4096, PVW_ERR_INVALID_PARAMETERS, "upload_chunk_bytes too small"); c->upload_chunk_bytes = value; }

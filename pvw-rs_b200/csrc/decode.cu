@@ -1124,10 +1124,12 @@ PVW_DEV void share_residues(const u64* __restrict__ z, size_t z_ls, size_t z_ds,
 // by induction on i); with the check it holds modulo Q, so tmp_i = e_{i+1} - D e_i are the centred values the reference works
 // with (|.| < Q/2), H = e_{l-1} - D^(l-1) e_0 telescopes, |e_{l-1}| <= D/2 (centred remainder) gives red = e_{l-1}, every rounded
 // division of the back-substitution is exact, noise_0 = e_0 and the plaintext is centre(-z_0 - e_0) = m.
-// PHASE 0: the whole procedure in one kernel.  PHASE 1 / 2: the same split in two launches -- pass 1 and the carry chain (the
+// PHASE 1 / 2: the procedure runs as two launches -- pass 1 and the carry chain (the
 // register-hungry half: l * (SW + 1) accumulator words) leave |e_i|, |m| and the signs in a scratch of l + 2 words per share, and the
 // claim check of the remaining limbs (72 % of the instructions) runs as its own kernel at <= 80 registers, 24 instead of 16 warps
-// per SM, from 1 000 instead of 9 700 instructions (the one-kernel form waits a fifth of its cycles for instruction fetch).
+// per SM, from 1 000 instead of 9 700 instructions.  (PHASE 0, everything in one kernel, is the form this grew out of: 1.39 against
+// 1.18 ms per million shares, a fifth of its cycles waiting for instruction fetch; it is no longer instantiated -- a third of this
+// file's compile time -- but the template still describes it.)
 template <int ELL, int SW, int ND, int MINB, int PHASE>
 __global__ void __launch_bounds__(128, MINB) decode_fused_claim_kernel(const u64* __restrict__ z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub sub,
                                                                        uint32_t Pc, uint64_t S, u64* __restrict__ out, size_t out_ps, const DevTables T,
@@ -1354,7 +1356,7 @@ template <int ELL, int SW, int MINB>
 static bool launch_fused_claim(const DevTables& T, const FusedConst& F, const u64* z, size_t z_ls, size_t z_ds, size_t z_cs, const DecodeSub& sb, uint32_t Pc,
                                uint64_t S, u64* out, size_t out_ps, uint32_t* fb_list, uint32_t* fb_count, cudaStream_t st, u64* scr) {
   const size_t smem = ((size_t)T.L * ELL * 4 + (size_t)T.L * 8 + (size_t)T.shortL * SW + 2 * SW) * 8;
-  if (smem > 96 * 1024) return false;
+  if (smem > 96 * 1024 || scr == nullptr) return false;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
   // one launch of a phase: persistent-style grid, four CTAs' worth of shares per resident CTA
@@ -1368,8 +1370,7 @@ static bool launch_fused_claim(const DevTables& T, const FusedConst& F, const u6
   };
 #define PVW_FUSED_CLAIM_ND(N)                                                                                                    \
   case N:                                                                                                                        \
-    if (scr) return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 1>) && run(decode_fused_claim_kernel<ELL, SW, N, (ELL == 8 ? PVW_FUSED_P2_MINB : 4), 2>); \
-    return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 0>);
+    return run(decode_fused_claim_kernel<ELL, SW, N, MINB, 1>) && run(decode_fused_claim_kernel<ELL, SW, N, (ELL == 8 ? PVW_FUSED_P2_MINB : 4), 2>);
   switch (F.nd) {
     PVW_FUSED_CLAIM_ND(1)
     PVW_FUSED_CLAIM_ND(2)

@@ -74,7 +74,7 @@ def test_fused_decode_matches_the_oracle_on_both_sides_of_every_check(name):
     for i in rng.choice(len(cs), size=min(12, len(cs)), replace=False):       # the exact (literal) restatement agrees with the C one
         assert O.decode_scalar_pvw_rns(P, polys[i]) == int(co.decode(zhat[i:i + 1])[0])
     eng = pvw.Engine(**engine_kwargs(P))
-    for fused in (1, 2, 0):                               # fast path (two launches at l = 8 / one kernel) + per-share fallback, general chain only
+    for fused in (1, 0):                                  # fast path + per-share fallback, general chain only
         eng.set_option("decode_fused", fused)
         eng.set_option("profile", 2)
         got = eng.decode_batch(batch)

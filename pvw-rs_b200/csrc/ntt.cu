@@ -253,8 +253,9 @@ __global__ void __launch_bounds__(128, ELL == 8 ? 5 : ELL == 16 ? 3 : 1) ntt_pla
         uint32_t gi[4] = {0, 0, 0, 0};
         bool ternary;
         if (cbytes == 1) {
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const signed char*>(coef) + (idx + p) * 16);
-          const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+          const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const signed char*>(coef) + (idx + p) * 16);   // (8-byte loads: the
+          const uint2 v0 = src[0], v1 = src[1];                                                                            //  alignment load_small asks for)
+          const uint32_t vw[4] = {v0.x, v0.y, v1.x, v1.y};
           uint32_t bad = 0;
 #pragma unroll
           for (int g = 0; g < 4; g++) {
